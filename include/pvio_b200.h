@@ -1,0 +1,207 @@
+/* pvio_b200 -- C ABI of the B200-native sliding-window bundle-adjustment + KLT backend.
+ *
+ * Drop-in boundary for ONE hot path of zju3dv/PVIO (reference paths relative to
+ * /root/reference):
+ *   - pvio_b200_ba_solve        replaces the ceres::Solve call in
+ *                               pvio/src/pvio/estimation/bundle_adjustor.cpp:244-249
+ *                               (BundleAdjustorSolver::solve :63-299; post-pass :277-296)
+ *   - pvio_b200_ba_gn_step      one linearise -> Schur -> solve -> Plus -> cost iteration
+ *                               (test / benchmark unit; what Ceres does once per iteration)
+ *   - pvio_b200_ba_marginalize  replaces BundleAdjustor::marginalize_frame,
+ *                               bundle_adjustor.cpp:348-599
+ *   - pvio_b200_klt_track       replaces cv::calcOpticalFlowPyrLK in
+ *                               pvio-extra/src/pvio/extra/opencv_image.cpp:103
+ *                               (OpenCvImage::track_keypoints :88-136)
+ *   - pvio_b200_reprojection_error  BundleAdjustor::compute_reprojection_error :321-336
+ *
+ * Conventions: plain pointers and sizes, caller-owned arrays, the callee
+ * never frees them; doubles at the boundary (the reference's state is fp64); no
+ * exceptions; integer return codes (0 = ok, < 0 = error, see PVIO_B200_E*); one
+ * in-flight call per handle (the reference calls solve from one thread,
+ * core/frontend_worker.cpp:58-77); handles are independent across GPUs.
+ * There is no CPU fallback: every entry point fails with PVIO_B200_ENODEV without a GPU.
+ */
+#ifndef PVIO_B200_H
+#define PVIO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVIO_B200_OK 0
+#define PVIO_B200_ENODEV (-1)   /* no CUDA device / driver error            */
+#define PVIO_B200_EINVAL (-2)   /* bad argument or window exceeds capacity   */
+#define PVIO_B200_ENOMEM (-3)
+#define PVIO_B200_ECUDA (-4)    /* kernel / runtime failure (see last_error) */
+#define PVIO_B200_ENUMERIC (-5) /* reduced system not positive definite      */
+
+#define PVIO_B200_MAX_FRAMES 16      /* N: window frames (reference: 9..11)  */
+#define PVIO_B200_FRAME_STRIDE 16    /* doubles per frame: q(x,y,z,w) p v bg ba, estimation/state.h:43-69 */
+#define PVIO_B200_IMU_STRIDE 288     /* doubles per IMU factor, layout below */
+
+/* IMU factor record = the PreIntegrator outputs the cost functor reads
+ * (estimation/preintegrator.h:29-44, ceres/preintegration_error_cost.h:53-76):
+ *   [0] dt | [1..4] dq (x,y,z,w) | [5..7] dp | [8..10] dv |
+ *   [11..235] sqrt_inv_cov 15x15 row-major |
+ *   [236..244] dq_dbg | [245..253] dp_dbg | [254..262] dp_dba | [263..271] dv_dbg |
+ *   [272..280] dv_dba (3x3 row-major) | [281..283] bg0 | [284..286] ba0 | [287] pad
+ * bg0/ba0: the bias linearisation point (frame_i->motion at integrate() time). */
+#define PVIO_B200_IMU_DT 0
+#define PVIO_B200_IMU_DQ 1
+#define PVIO_B200_IMU_DP 5
+#define PVIO_B200_IMU_DV 8
+#define PVIO_B200_IMU_SQRT_INV_COV 11
+#define PVIO_B200_IMU_DQ_DBG 236
+#define PVIO_B200_IMU_DP_DBG 245
+#define PVIO_B200_IMU_DP_DBA 254
+#define PVIO_B200_IMU_DV_DBG 263
+#define PVIO_B200_IMU_DV_DBA 272
+#define PVIO_B200_IMU_BG0 281
+#define PVIO_B200_IMU_BA0 284
+
+/* One sliding window, gathered by the shim from Map/Frame/Track exactly in the order
+ * bundle_adjustor.cpp:75-242 walks them.  Keypoints are normalised image coordinates. */
+typedef struct pvio_b200_window {
+    int32_t n_frames;            /* map->frame_num()                              :75  */
+    int32_t n_landmarks;         /* VALID non-PLANE tracks with a parameter block :91-103 */
+    int32_t n_obs;               /* reprojection residual blocks (anchor excluded) :149 */
+    int32_t use_inertial;        /* solve(map, config, use_inertial)              :63  */
+    const uint8_t *frame_fixed;  /* [N] Frame::flag(FF_FIX_POSE)                  :79  */
+    double cam_q_cs[4], cam_p_cs[3]; /* Frame::camera (estimation/state.h:38-41)       */
+    double imu_q_cs[4], imu_p_cs[3]; /* Frame::imu                                     */
+    double sqrt_inv_cov[4];      /* Frame::sqrt_inv_cov 2x2 row-major (core/core.cpp:112-116) */
+    double fx, fy;               /* Frame::K(0,0), K(1,1): post-pass pixel error  :291 */
+    double cauchy_a;             /* ceres::CauchyLoss(1.0)                        :58  */
+    const int32_t *lm_anchor;    /* [M] index of Track::first_frame()                  */
+    const double *lm_z_ref;      /* [M][2] first_keypoint()                            */
+    const int32_t *lm_obs_begin; /* [M+1] CSR offsets into obs_*                       */
+    const uint8_t *lm_in_victim; /* [M] track observed by the frame to marginalise :454 (may be NULL) */
+    const int32_t *obs_frame;    /* [K] sorted by landmark, then frame index           */
+    const double *obs_z;         /* [K][2]                                             */
+    int32_t n_imu;               /* pre-integration factors                      :220-242 */
+    const int32_t *imu_frame_i;  /* [n_imu]                                            */
+    const int32_t *imu_frame_j;  /* [n_imu]                                            */
+    const double *imu_data;      /* [n_imu][PVIO_B200_IMU_STRIDE]                      */
+    int32_t n_prior;             /* frames related to the marginalisation prior  :126-139 */
+    const int32_t *prior_frames; /* [n_prior] window index of each related frame       */
+    const double *prior_S;       /* [(15 n)^2] row-major sqrt_inv_cov (marginalization_error_cost.h:103) */
+    const double *prior_e;       /* [15 n] infovec                                     */
+    const double *prior_state0;  /* [n_prior][16] pose_0 / motion_0 snapshots :44-45   */
+    int32_t n_planes;            /* planes with >= 20 tracks                     :165  */
+    const double *plane_param;   /* [n_planes][4] normal(3), distance                  */
+    double plane_sqrt_inv_cov;   /* sqrt(1 / config->plane_distance_cov())       :181  */
+    int32_t n_plane_tracks;
+    const int32_t *pt_plane;     /* [T] plane index of each plane-track          :183  */
+    const int32_t *pt_obs_begin; /* [T+1] CSR offsets                                  */
+    const int32_t *pt_obs_frame; /* [...] every observation of the track         :186  */
+    const double *pt_obs_z;      /* [...][2]                                           */
+} pvio_b200_window;
+
+/* In/out state: Frame::pose, Frame::motion, Track::landmark.inv_depth -- overwritten in
+ * place as ceres does (bundle_adjustor.cpp:77-101). */
+typedef struct pvio_b200_state {
+    double *frames;    /* [N][PVIO_B200_FRAME_STRIDE] */
+    double *inv_depth; /* [M] */
+} pvio_b200_state;
+
+typedef struct pvio_b200_options {
+    int32_t max_iterations; /* config->solver_iteration_limit() (10)   solver_options.h:29 */
+    double max_time;        /* config->solver_time_limit() seconds     solver_options.h:30 */
+    int32_t alias_bias;     /* 1: bias linearisation point follows the accepted state (quirk Q1,
+                               the reference's behaviour); 0: frozen at solve entry          */
+    int32_t run_postpass;   /* 1: run the landmark depth / pixel-error pass :277-296         */
+} pvio_b200_options;
+
+#define PVIO_B200_TERM_CONVERGENCE 0
+#define PVIO_B200_TERM_NO_CONVERGENCE 1
+#define PVIO_B200_TERM_FAILURE 2
+
+typedef struct pvio_b200_summary {
+    int32_t iterations;      /* trust-region iterations executed                          */
+    int32_t accepted_steps;
+    int32_t termination;     /* PVIO_B200_TERM_*                                          */
+    int32_t usable;          /* ceres Summary::IsSolutionUsable()                   :298  */
+    double initial_cost, final_cost;
+    double final_radius, final_mu;
+    double solve_seconds;    /* device time of the solve (CUDA events)                    */
+} pvio_b200_summary;
+
+typedef struct pvio_b200_handle_s *pvio_b200_handle;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+/* Owns device buffers, one stream, CUDA graphs.  max_windows > 1 enables the batched
+ * entry points (BASELINE config 5 and the roofline launch). */
+int pvio_b200_create(int device, int max_windows, int max_frames, int max_landmarks,
+                     int max_obs, pvio_b200_handle *out);
+void pvio_b200_destroy(pvio_b200_handle h);
+const char *pvio_b200_last_error(pvio_b200_handle h);
+/* number of kernels this library launched since creation (bench.py "gpu_launches") */
+int64_t pvio_b200_kernel_launches(pvio_b200_handle h);
+const char *pvio_b200_version(void);
+
+/* ---- single window: the reference-facing calls ------------------------------------- */
+/* Full solve; state updated in place.  valid/quality ([M], may be NULL) receive the
+ * post-pass result (TF_VALID after the depth test, landmark.quality). */
+int pvio_b200_ba_solve(pvio_b200_handle h, const pvio_b200_window *w, pvio_b200_state *s,
+                       const pvio_b200_options *opt, pvio_b200_summary *summary,
+                       uint8_t *valid, double *quality);
+
+/* One regularised Gauss-Newton iteration at `s` (not modified): dx = -(H + mu D)^-1 g in
+ * the local coordinates [N][15] then [M] (theta, p, v, bg, ba per frame; d inv_depth per
+ * landmark; masked coordinates are 0), the cost at s, and the cost after Plus(s, dx).
+ * Hred/gred (may be NULL) receive the reduced system in the same [N][15] layout
+ * (row-major D x D, D = 15 N). */
+int pvio_b200_ba_gn_step(pvio_b200_handle h, const pvio_b200_window *w, const pvio_b200_state *s,
+                         double mu, double *dx, double *cost, double *new_cost,
+                         double *Hred, double *gred);
+
+/* New prior over the remaining frames after marginalising frame `index`:
+ * S_out [(15(N-1))^2] row-major, e_out [15(N-1)]; H_out/b_out (may be NULL) the
+ * information matrix / vector before the eigen factorisation. */
+int pvio_b200_ba_marginalize(pvio_b200_handle h, const pvio_b200_window *w, const pvio_b200_state *s,
+                             int index, double *S_out, double *e_out, double *H_out, double *b_out);
+
+/* Mean pixel reprojection error over all observations of the window's landmarks. */
+int pvio_b200_reprojection_error(pvio_b200_handle h, const pvio_b200_window *w,
+                                 const pvio_b200_state *s, double *error);
+
+/* ---- batched windows (independent problems, one CTA-group each) --------------------- */
+/* Pack window `slot` (0 <= slot < max_windows) into the pinned staging area in device
+ * layout (fp32 observation table, fp64 state).  Nothing is copied to the GPU yet. */
+int pvio_b200_batch_set_window(pvio_b200_handle h, int slot, const pvio_b200_window *w,
+                               const pvio_b200_state *s);
+/* Replicate slot 0 into slots 1..n-1 (synthetic batches of identical shape). */
+int pvio_b200_batch_replicate(pvio_b200_handle h, int n);
+/* Host -> device copy of the first n packed windows (async on the handle's stream). */
+int pvio_b200_batch_upload(pvio_b200_handle h, int n);
+/* One GN iteration for the first n windows, device-resident; apply != 0 keeps the
+ * updated state on the device (as an accepted step). */
+int pvio_b200_batch_gn_step(pvio_b200_handle h, int n, double mu, int apply);
+/* Device -> host: dx [n][15 N + M] (stride dx_stride doubles), costs [n][2]. */
+int pvio_b200_batch_download(pvio_b200_handle h, int n, double *dx, int64_t dx_stride, double *costs);
+/* upload + gn_step + download in one call: the end-to-end path bench.py times. */
+int pvio_b200_batch_gn_step_host(pvio_b200_handle h, int n, double mu, double *dx,
+                                 int64_t dx_stride, double *costs);
+int pvio_b200_sync(pvio_b200_handle h);
+/* CUDA-event timing on the handle's stream (bench.py): start / stop return ms. */
+int pvio_b200_timer_start(pvio_b200_handle h);
+int pvio_b200_timer_stop(pvio_b200_handle h, float *ms);
+/* device-side time (ms) of the most recent linearise+Schur kernel launch */
+int pvio_b200_last_kernel_ms(pvio_b200_handle h, int which, float *ms);
+
+/* ---- KLT ----------------------------------------------------------------------------- */
+/* Pyramidal Lucas-Kanade with OpenCV's semantics: winSize 21x21, maxLevel levels above
+ * level 0, criteria COUNT+EPS (max_iter, eps), OPTFLOW_USE_INITIAL_FLOW (next_pts holds
+ * the guess on entry), minEigThreshold 1e-4.  prev/next: 8-bit single-channel images
+ * (post-CLAHE).  status[i] = 1 if found; err[i] as cv (mean abs patch difference). */
+int pvio_b200_klt_track(pvio_b200_handle h, const uint8_t *prev, const uint8_t *next,
+                        int width, int height, int stride, const float *prev_pts,
+                        float *next_pts, uint8_t *status, float *err, int n_points,
+                        int max_level, int max_iter, double eps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVIO_B200_H */

@@ -1,0 +1,75 @@
+// Internal handle of libpvio_b200 (host side).  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/pvio_b200.h"
+#include "ba_types.h"
+
+namespace pvio {
+
+template <typename T>
+struct DevBuf {
+    T *d = nullptr;      // device
+    T *h = nullptr;      // pinned host staging (optional)
+    size_t n = 0;
+};
+
+struct KltState;         // klt.cu
+
+struct Handle {
+    int device = 0;
+    int W = 1, Ncap = 0, Mcap = 0, Kcap = 0;
+    int Pcap = 4, Tcap = 0, Ocap = 0;            // planes / plane tracks / plane observations
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+
+    // vision (always allocated)
+    DevBuf<WinHdr> hdr;
+    DevBuf<WinConst> cst;
+    DevBuf<ObsRec> obs;
+    DevBuf<LmRec> lms;
+    DevBuf<double> rho, frames;
+    DevBuf<WinCtrl> ctrl;
+    DevBuf<double> rho_cand, frames_cand, lm_scale, dx_lm, dx_pose, pose_scale;
+    DevBuf<LmAux> lm_aux;
+    DevBuf<double> Hred, Hdd, gdir, gred, cost_vis, acc, aux_cost;
+    DevBuf<double> Hfull, gfull;                 // debug dump (single window only)
+    // inertial / prior / planes (allocated on first use)
+    bool have_inertial = false;
+    DevBuf<int32_t> imu_idx, prior_frames;
+    DevBuf<double> imu_data, prior_S, prior_L, prior_e, prior_x0;
+    bool have_planes = false;
+    DevBuf<double> plane_param;
+    DevBuf<int32_t> pt_plane, pt_begin, pt_frame;
+    DevBuf<float> pt_z;
+    // host bookkeeping per slot
+    std::vector<std::vector<int32_t>> perm;      // packed landmark -> caller landmark
+    std::vector<int> slot_M, slot_N, slot_K;
+    int n_uploaded = 0;
+    float last_lin_ms = 0.f;
+    KltState *klt = nullptr;
+};
+
+int fail(Handle *h, int code, const char *what, cudaError_t e = cudaSuccess);
+
+#define CK(h, call)                                                        \
+    do {                                                                   \
+        cudaError_t e__ = (call);                                          \
+        if (e__ != cudaSuccess) return fail((h), PVIO_B200_ECUDA, #call, e__); \
+    } while (0)
+
+// klt.cu
+int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int width, int height, int stride,
+                   const float *prev_pts, float *next_pts, uint8_t *status, float *err, int n_points,
+                   int max_level, int max_iter, double eps);
+void klt_free(Handle *h);
+// ba_marg.cu
+int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s, int index,
+                     double *S_out, double *e_out, double *H_out, double *b_out);
+
+}  // namespace pvio

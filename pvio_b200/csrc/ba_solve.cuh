@@ -1,0 +1,799 @@
+// Reduced-system kernel: assembles the dense pose/velocity/bias system of one window and
+// solves it.  One CTA per window.
+//
+//   * vision part: block-lower-triangular Schur-reduced system from lin_schur_kernel in xi
+//     coordinates, mapped to the reference's local coordinates delta = [dtheta dp] with
+//     H_delta[f,g] = T_f^T H_xi[f,g] T_g  (T_f = [[R_f,0],[-[p_f]x R_f,-I]])
+//   * PreIntegrationErrorCost::Evaluate      estimation/ceres/preintegration_error_cost.h:40-160
+//   * MarginalizationErrorCost::Evaluate     estimation/ceres/marginalization_error_cost.h:53-94
+//   * AugmentedPlaneDistanceErrorCost::Evaluate  .../augmented_plane_distance_error_cost.h:53-136
+//     (+ CauchyLoss corrector, bundle_adjustor.cpp:192)
+//   * constant blocks (FF_FIX_POSE, bundle_adjustor.cpp:79-82), Jacobi scaling and the
+//     mu*diag regulariser of ceres' dogleg Gauss-Newton solve, dense Cholesky, and the
+//     scalars of the trust-region step.
+// Everything here is fp64: it is O(D^3/6) flops on a D <= 210 system, off the HBM-bound path.
+#pragma once
+#include "ba_math.cuh"
+#include "ba_types.h"
+#include "ba_lin.cuh"
+
+namespace pvio {
+
+struct SolveArgs {
+    const WinHdr *hdr;
+    const WinConst *cst;
+    const double *frames;      // [W][Ncap][16]
+    WinCtrl *ctrl;
+    const double *Hred;        // from lin_schur_kernel
+    const double *Hdd;
+    const double *gdir;
+    const double *gred;
+    const double *cost_vis;
+    // IMU
+    const int32_t *imu_idx;    // [W][Ncap][2] (frame_i, frame_j)
+    const double *imu_data;    // [W][Ncap][kImuStride]
+    int alias_bias;            // 1: dbg = dba = 0 at the linearisation point (quirk Q1)
+    // prior
+    const int32_t *prior_frames;   // [W][Ncap]
+    const double *prior_S;         // [W][dcap*dcap], dcap = 15*Ncap
+    const double *prior_L;         // [W][dcap*dcap]  Lambda = S^T S
+    const double *prior_e;         // [W][dcap]
+    const double *prior_x0;        // [W][Ncap][16]
+    // planes
+    const double *plane_param;     // [W][Pcap][4]
+    const int32_t *pt_plane;       // [W][Tcap]
+    const int32_t *pt_begin;       // [W][Tcap+1]
+    const int32_t *pt_frame;       // [W][Ocap]
+    const float *pt_z;             // [W][Ocap][2]  (observations are stored fp32 like the reprojection table)
+    int Pcap, Tcap, Ocap;
+    // scaling / outputs
+    double *pose_scale;        // [W][15*Ncap]
+    double *dx_pose;           // [W][Ncap][15]
+    double *Hfull;             // optional [W][(15 Ncap)^2] dump of the reduced system (delta coords, before regularisation)
+    double *gfull;             // optional [W][15 Ncap]
+    int Ncap;
+    int compute_scale;
+    double mu_override;
+};
+
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
+
+// add v to symmetric packed-lower A at (i,j) (any order)
+__device__ __forceinline__ void sym_add(double *A, int i, int j, double v) {
+    if (i >= j) A[tri(i, j)] += v; else A[tri(j, i)] += v;
+}
+
+// ---- IMU factor: raw residual and Jacobian (before whitening); J is [15][30] row-major.
+__device__ inline void imu_factor_raw(const double *fi, const double *fj, const double *rec,
+                                      const WinConst &wc, int alias_bias, double *r, double *J) {
+    const double g[3] = {0.0, 0.0, -9.80665};                 // preintegration_error_cost.h:41
+    for (int i = 0; i < 450; ++i) J[i] = 0.0;
+    const double *qic = fi, *pic = fi + 4, *vi = fi + 7, *bgi = fi + 10, *bai = fi + 13;
+    const double *qjc = fj, *pjc = fj + 4, *vj = fj + 7, *bgj = fj + 10, *baj = fj + 13;
+    const double dt = rec[0];
+    const double *dq = rec + 1, *dp = rec + 5, *dv = rec + 8;
+    const double *dq_dbg = rec + 236, *dp_dbg = rec + 245, *dp_dba = rec + 254, *dv_dbg = rec + 263, *dv_dba = rec + 272;
+    double dbg[3], dba[3];
+    for (int k = 0; k < 3; ++k) {
+        dbg[k] = alias_bias ? 0.0 : bgi[k] - rec[281 + k];    // :69-70 (Q1: bg_i_0 aliases the parameter)
+        dba[k] = alias_bias ? 0.0 : bai[k] - rec[284 + k];
+    }
+    double qi[4], qj[4], Rci[9], Rcj[9], t3[3], pi[3], pj[3];
+    quat_mul(qic, wc.imu_q, qi);                                // :60
+    quat_mul(qjc, wc.imu_q, qj);                                // :62
+    quat_to_mat(qic, Rci);
+    quat_to_mat(qjc, Rcj);
+    mat3_vec(Rci, wc.imu_p, t3);
+    for (int k = 0; k < 3; ++k) pi[k] = pic[k] + t3[k];         // :61
+    mat3_vec(Rcj, wc.imu_p, t3);
+    for (int k = 0; k < 3; ++k) pj[k] = pjc[k] + t3[k];         // :63
+    // r_q = log( (dq exp(dq_dbg dbg))^-1 qi^-1 qj )            // :79
+    double w3[3], e4[4], dqc[4], c1[4], c2[4], c3[4], c4[4];
+    mat3_vec(dq_dbg, dbg, w3);
+    expmap(w3, e4);
+    quat_mul(dq, e4, dqc);
+    quat_conj(dqc, c1);
+    quat_conj(qi, c2);
+    quat_mul(c1, c2, c3);
+    quat_mul(c3, qj, c4);
+    logmap(c4, r + 0);
+    double Ri[9];
+    quat_to_mat(qi, Ri);
+    double a3[3], b3[3];
+    for (int k = 0; k < 3; ++k) a3[k] = pj[k] - pi[k] - dt * vi[k] - 0.5 * dt * dt * g[k];
+    mat3_tvec(Ri, a3, b3);                                      // qi^-1 * (.)
+    double c_[3], d_[3];
+    mat3_vec(dp_dbg, dbg, c_);
+    mat3_vec(dp_dba, dba, d_);
+    for (int k = 0; k < 3; ++k) r[3 + k] = b3[k] - (dp[k] + c_[k] + d_[k]);   // :80
+    for (int k = 0; k < 3; ++k) a3[k] = vj[k] - vi[k] - dt * g[k];
+    mat3_tvec(Ri, a3, b3);
+    mat3_vec(dv_dbg, dbg, c_);
+    mat3_vec(dv_dba, dba, d_);
+    for (int k = 0; k < 3; ++k) r[6 + k] = b3[k] - (dv[k] + c_[k] + d_[k]);   // :81
+    for (int k = 0; k < 3; ++k) { r[9 + k] = bgj[k] - bgi[k]; r[12 + k] = baj[k] - bai[k]; }  // :82-83
+
+    double Jr[9], Jri[9], Rimu[9], Rj[9];
+    right_jacobian(r, Jr);
+    mat3_inv(Jr, Jri);
+    quat_to_mat(wc.imu_q, Rimu);
+    quat_to_mat(qj, Rj);
+    double M1[9], M2[9], H3[9];
+#define PUT(row0, col0, M, sgn)                                                      \
+    for (int a_ = 0; a_ < 3; ++a_)                                                   \
+        for (int b_ = 0; b_ < 3; ++b_) J[((row0) + a_) * 30 + (col0) + b_] = (sgn) * (M)[3 * a_ + b_];
+    // d/dq_i :86-93
+    mat3_mul_tn(Rj, Rci, M1);               // qj^-1 * q_center_i
+    mat3_mul(Jri, M1, M2);
+    PUT(0, 0, M2, -1.0);
+    for (int k = 0; k < 3; ++k) a3[k] = pj[k] - pic[k] - dt * vi[k] - 0.5 * dt * dt * g[k];
+    mat3_tvec(Rci, a3, b3);
+    hat(b3, H3);
+    mat3_mul_tn(Rimu, H3, M1);
+    PUT(3, 0, M1, 1.0);
+    for (int k = 0; k < 3; ++k) a3[k] = vj[k] - vi[k] - dt * g[k];
+    mat3_tvec(Rci, a3, b3);
+    hat(b3, H3);
+    mat3_mul_tn(Rimu, H3, M1);
+    PUT(6, 0, M1, 1.0);
+    // d/dp_i :94-99, d/dv_i :100-106   (-qi^-1)
+    double Rit[9];
+    for (int a_ = 0; a_ < 3; ++a_) for (int b_ = 0; b_ < 3; ++b_) Rit[3 * a_ + b_] = Ri[3 * b_ + a_];
+    PUT(3, 3, Rit, -1.0);
+    PUT(3, 6, Rit, -dt);
+    PUT(6, 6, Rit, -1.0);
+    // d/dbg_i :107-115
+    {
+        double er[4], erc[4], Rer[9], Jr2[9];
+        expmap(r, er);
+        quat_conj(er, erc);
+        quat_to_mat(erc, Rer);
+        right_jacobian(w3, Jr2);
+        mat3_mul(Jri, Rer, M1);
+        mat3_mul(M1, Jr2, M2);
+        mat3_mul(M2, dq_dbg, M1);
+        PUT(0, 9, M1, -1.0);
+    }
+    PUT(3, 9, dp_dbg, -1.0);
+    PUT(6, 9, dv_dbg, -1.0);
+    for (int k = 0; k < 3; ++k) J[(9 + k) * 30 + 9 + k] = -1.0;
+    // d/dba_i :116-123
+    PUT(3, 12, dp_dba, -1.0);
+    PUT(6, 12, dv_dba, -1.0);
+    for (int k = 0; k < 3; ++k) J[(12 + k) * 30 + 12 + k] = -1.0;
+    // d/dq_j :124-130
+    mat3_mul_tn(Jri, Rimu, M1);             // careful: Jri * Rimu^T
+    for (int a_ = 0; a_ < 3; ++a_)
+        for (int b_ = 0; b_ < 3; ++b_) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s += Jri[3 * a_ + k] * Rimu[3 * b_ + k];
+            M1[3 * a_ + b_] = s;
+        }
+    PUT(0, 15, M1, 1.0);
+    hat(wc.imu_p, H3);
+    mat3_mul(Rit, Rcj, M1);
+    mat3_mul(M1, H3, M2);
+    PUT(3, 15, M2, -1.0);
+    // d/dp_j, dv_j, dbg_j, dba_j :131-154
+    PUT(3, 18, Rit, 1.0);
+    PUT(6, 21, Rit, 1.0);
+    for (int k = 0; k < 3; ++k) { J[(9 + k) * 30 + 24 + k] = 1.0; J[(12 + k) * 30 + 27 + k] = 1.0; }
+#undef PUT
+}
+
+// ---- prior: raw residual [log(q0^-1 q); p-p0; v-v0; bg-bg0; ba-ba0] and Jr^-1 of one frame
+__device__ inline void prior_frame_raw(const double *fs, const double *x0, double *r15, double *Jri) {
+    double c[4], d[4];
+    quat_conj(x0, c);
+    quat_mul(c, fs, d);
+    logmap(d, r15);                                           // marginalization_error_cost.h:65
+    for (int k = 0; k < 12; ++k) r15[3 + k] = fs[4 + k] - x0[4 + k];
+    double Jr[9];
+    right_jacobian(r15, Jr);
+    mat3_inv(Jr, Jri);                                         // :76
+}
+
+// ---- plane factor (one plane track), fp64.  J is [6*K] in delta coordinates of the K frames.
+__device__ inline void plane_factor(int K, const int32_t *fr, const float *z, const double *frames,
+                                    const WinConst &wc, const double *pl, double sic, double *r_out, double *J) {
+    double A[2 * kMaxFrames + 1][3], b[2 * kMaxFrames + 1];
+    double Rcs[9], qcc[4];
+    quat_to_mat(wc.cam_q, Rcs);
+    quat_conj(wc.cam_q, qcc);
+    double tc[3];
+    mat3_tvec(Rcs, wc.cam_p, tc);                              // q_cs^-1 * p_cs
+    for (int i = 0; i < K; ++i) {
+        const double *fs = frames + fr[i] * kFrameStride;
+        double R[9], Rsw[9], Tsw[3];
+        quat_to_mat(fs, R);
+        // Rsw = (q_cs^-1 q_wc^-1).matrix() = Rcs^T R^T            :68
+        for (int a_ = 0; a_ < 3; ++a_)
+            for (int b_ = 0; b_ < 3; ++b_) {
+                double s = 0.0;
+                for (int k = 0; k < 3; ++k) s += Rcs[3 * k + a_] * R[3 * b_ + k];
+                Rsw[3 * a_ + b_] = s;
+            }
+        double pw[3] = {fs[4] - wc.origin[0], fs[5] - wc.origin[1], fs[6] - wc.origin[2]};
+        // NOTE: the functor is evaluated in absolute world coordinates; the origin shift would
+        // change b because the plane distance is not shifted, so undo it here.
+        pw[0] = fs[4]; pw[1] = fs[5]; pw[2] = fs[6];
+        mat3_vec(Rsw, pw, Tsw);
+        for (int k = 0; k < 3; ++k) Tsw[k] = -Tsw[k] - tc[k];      // :69
+        const double u = (double)z[2 * i], v = (double)z[2 * i + 1];
+        for (int k = 0; k < 3; ++k) {
+            A[2 * i][k] = u * Rsw[6 + k] - Rsw[k];                  // :71-72
+            A[2 * i + 1][k] = v * Rsw[6 + k] - Rsw[3 + k];
+        }
+        b[2 * i] = u * Tsw[2] - Tsw[0];
+        b[2 * i + 1] = v * Tsw[2] - Tsw[1];
+    }
+    const double *nrm = pl;
+    const double dist = pl[3];
+    for (int k = 0; k < 3; ++k) A[2 * K][k] = nrm[k];             // regularization_weight = 1 :84-85
+    b[2 * K] = dist;
+    double ATA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ATb[3] = {0, 0, 0};
+    for (int i = 0; i < 2 * K + 1; ++i)
+        for (int a_ = 0; a_ < 3; ++a_) {
+            ATb[a_] += A[i][a_] * b[i];
+            for (int b_ = 0; b_ < 3; ++b_) ATA[3 * a_ + b_] += A[i][a_] * A[i][b_];
+        }
+    double lam[3], V[9], Ainv[9];
+    sym3_eig(ATA, lam, V);                                        // :90
+    for (int a_ = 0; a_ < 3; ++a_)
+        for (int b_ = 0; b_ < 3; ++b_) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s += V[3 * a_ + k] * (lam[k] > 1.0e-8 ? 1.0 / lam[k] : 0.0) * V[3 * b_ + k];
+            Ainv[3 * a_ + b_] = s;
+        }
+    double x[3];
+    mat3_vec(Ainv, ATb, x);
+    for (int k = 0; k < 3; ++k) x[k] = -x[k];                     // :94
+    *r_out = (nrm[0] * x[0] + nrm[1] * x[1] + nrm[2] * x[2] - dist) * sic;   // :96,:133
+    for (int i = 0; i < K; ++i) {
+        const double *fs = frames + fr[i] * kFrameStride;
+        const double u = (double)z[2 * i], v = (double)z[2 * i + 1];
+        double R[9], Rsw[9];
+        quat_to_mat(fs, R);
+        for (int a_ = 0; a_ < 3; ++a_)
+            for (int b_ = 0; b_ < 3; ++b_) {
+                double s = 0.0;
+                for (int k = 0; k < 3; ++k) s += Rcs[3 * k + a_] * R[3 * b_ + k];
+                Rsw[3 * a_ + b_] = s;
+            }
+        const double Jb[2][3] = {{-1.0, 0.0, u}, {0.0, -1.0, v}};
+        double drdth[3] = {0, 0, 0};
+        double M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};               // dxdAdq + dxdbdq
+        for (int rr = 0; rr < 2; ++rr) {
+            const double *Ar = A[2 * i + rr];
+            const double sres = b[2 * i + rr] + Ar[0] * x[0] + Ar[1] * x[1] + Ar[2] * x[2];
+            double AiA[3];                                        // A_row * ATAinv (row vector)
+            for (int k = 0; k < 3; ++k) AiA[k] = Ar[0] * Ainv[k] + Ar[1] * Ainv[3 + k] + Ar[2] * Ainv[6 + k];
+            double dxdA[9];                                       // sres*ATAinv + (x (A_row ATAinv))^T   :105
+            for (int a_ = 0; a_ < 3; ++a_)
+                for (int b_ = 0; b_ < 3; ++b_) dxdA[3 * a_ + b_] = sres * Ainv[3 * a_ + b_] + AiA[a_] * x[b_];
+            double cj[3], H3[9], dAdq[9], T9[9];
+            mat3_vec(Rcs, Jb[rr], cj);                            // q_cs * Jb.row^T
+            hat(cj, H3);
+            mat3_mul(R, H3, dAdq);                                // :107-108
+            mat3_mul(dxdA, dAdq, T9);
+            for (int k = 0; k < 9; ++k) M[k] += T9[k];
+        }
+        {   // dxdbdq = ATAinv A_blk^T Jb Rcs^T hat(qwc^-1 pwc)      :110
+            double pw[3] = {fs[4], fs[5], fs[6]}, pb[3], H3[9];
+            mat3_tvec(R, pw, pb);
+            hat(pb, H3);
+            double AtJb[9];                                       // (A_blk^T Jb) 3x3
+            for (int a_ = 0; a_ < 3; ++a_)
+                for (int b_ = 0; b_ < 3; ++b_) AtJb[3 * a_ + b_] = A[2 * i][a_] * Jb[0][b_] + A[2 * i + 1][a_] * Jb[1][b_];
+            double T1[9], T2[9], T3[9];
+            mat3_mul(Ainv, AtJb, T1);
+            for (int a_ = 0; a_ < 3; ++a_)
+                for (int b_ = 0; b_ < 3; ++b_) {
+                    double s = 0.0;
+                    for (int k = 0; k < 3; ++k) s += T1[3 * a_ + k] * Rcs[3 * b_ + k];   // * Rcs^T
+                    T2[3 * a_ + b_] = s;
+                }
+            mat3_mul(T2, H3, T3);
+            for (int k = 0; k < 9; ++k) M[k] += T3[k];
+            // drdp = n^T (ATAinv A_blk^T Jb Rsw)                   :117
+            mat3_mul(T1, Rsw, T2);
+            for (int k = 0; k < 3; ++k)
+                J[6 * i + 3 + k] = (nrm[0] * T2[k] + nrm[1] * T2[3 + k] + nrm[2] * T2[6 + k]) * sic;
+        }
+        for (int k = 0; k < 3; ++k) drdth[k] = nrm[0] * M[k] + nrm[1] * M[3 + k] + nrm[2] * M[6 + k];
+        for (int k = 0; k < 3; ++k) J[6 * i + k] = drdth[k] * sic;
+    }
+}
+
+// Dense LDL^T (packed lower, in shared memory) + solve A x = rhs; all threads of the CTA.
+// Column k is left unscaled (c_ik = l_ik d_k), so a step only READS column k and the
+// diagonal and WRITES columns > k: one barrier per column.  Returns false (uniformly) if a
+// pivot is not positive / finite (the system must be positive definite, as for ceres'
+// Cholesky-based SPARSE_SCHUR).
+__device__ inline bool chol_solve_packed(double *A, double *x, int D, int *flag_sm) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    bool ok = true;
+    __syncthreads();
+    for (int k = 0; k < D; ++k) {
+        const double dk = A[tri(k, k)];
+        if (!(dk > 0.0) || !isfinite(dk)) { ok = false; break; }   // uniform: same value read by all
+        const double idk = 1.0 / dk;
+        const int n = D - k - 1;
+        if (n > 0) {
+            const int nc = max(1, min(nt / n, 8));        // threads per row
+            const int rows_per_pass = nt / nc;
+            const int c0 = tid % nc;
+            for (int r = tid / nc; r < n; r += rows_per_pass) {
+                const int i = k + 1 + r;
+                const double lik = A[tri(i, k)] * idk;
+                double *row = A + tri(i, 0);
+                for (int j = k + 1 + c0; j <= i; j += nc) row[j] -= lik * A[tri(j, k)];
+            }
+        }
+        __syncthreads();
+    }
+    (void)flag_sm;
+    if (!ok) return false;
+    // L y = b (column oriented), z = y / d, L^T x = z
+    for (int k = 0; k < D; ++k) {
+        const double t = x[k] / A[tri(k, k)];       // x[k] is final here and nobody writes it below
+        for (int i = k + 1 + tid; i < D; i += nt) x[i] -= A[tri(i, k)] * t;
+        __syncthreads();
+    }
+    for (int i = tid; i < D; i += nt) x[i] /= A[tri(i, i)];
+    __syncthreads();
+    for (int k = D - 1; k > 0; --k) {
+        const double xk = x[k];
+        for (int i = tid; i < k; i += nt) x[i] -= A[tri(k, i)] / A[tri(i, i)] * xk;
+        __syncthreads();
+    }
+    return true;
+}
+
+constexpr int kSolveImuSlab = 15 * 30 + 16;     // raw J + r per factor
+
+__global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
+    const int w = blockIdx.x;
+    const WinHdr &H = a.hdr[w];
+    const WinConst &wc = a.cst[w];
+    const int N = H.N;
+    const int inertial = H.use_inertial;
+    const int stride = inertial ? 15 : 6;
+    const int D = stride * N;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double *frames = a.frames + (size_t)w * a.Ncap * kFrameStride;
+    WinCtrl &ctrl = a.ctrl[w];
+    const double mu = a.mu_override >= 0.0 ? a.mu_override : ctrl.mu;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *A = reinterpret_cast<double *>(smem_raw);       // packed lower D(D+1)/2
+    double *g = A + D * (D + 1) / 2;                        // [D] reduced gradient
+    double *gu = g + D;                                     // [D] unreduced gradient (for |g|_inf)
+    double *hcorr = gu + D;                                 // [D] direct - reduced diagonal
+    double *xs = hcorr + D;                                 // [D] solution
+    double *T = xs + D;                                     // [N][36] change of variables
+    double *scr = T + kMaxFrames * 36;                      // scratch: IMU slabs / prior vectors
+    __shared__ double cost_sm[4];
+    __shared__ int flag_sm;
+
+    for (int i = tid; i < D * (D + 1) / 2; i += nt) A[i] = 0.0;
+    for (int i = tid; i < 4 * D; i += nt) g[i] = 0.0;       // g, gu, hcorr, xs contiguous
+    if (tid < 4) cost_sm[tid] = 0.0;
+    if (tid < N) {
+        const double *fs = frames + tid * kFrameStride;
+        double R[9];
+        quat_to_mat(fs, R);
+        const double p[3] = {fs[4] - wc.origin[0], fs[5] - wc.origin[1], fs[6] - wc.origin[2]};
+        double Hp[9], B[9];
+        hat(p, Hp);
+        mat3_mul(Hp, R, B);
+        double *Tf = T + tid * 36;
+        for (int r_ = 0; r_ < 3; ++r_)
+            for (int c_ = 0; c_ < 3; ++c_) {
+                Tf[r_ * 6 + c_] = R[3 * r_ + c_];
+                Tf[r_ * 6 + 3 + c_] = 0.0;
+                Tf[(3 + r_) * 6 + c_] = -B[3 * r_ + c_];
+                Tf[(3 + r_) * 6 + 3 + c_] = (r_ == c_) ? -1.0 : 0.0;
+            }
+    }
+    __syncthreads();
+
+    // ---- vision blocks: H_delta[f,gf] = T_f^T X T_g.  Stage the xi-coordinate blocks in shared
+    // memory (coalesced), X <- X T_g in place, then T_f^T (X T_g) into the packed system.
+    const int npairs = N * (N + 1) / 2;
+    const int npairs_cap = a.Ncap * (a.Ncap + 1) / 2;
+    {
+        const double *Hred = a.Hred + (size_t)w * npairs_cap * 36;
+        const double *Hdd = a.Hdd + (size_t)w * a.Ncap * 36;
+        const double *gdir = a.gdir + (size_t)w * a.Ncap * 6;
+        const double *gred = a.gred + (size_t)w * a.Ncap * 6;
+        double *Xs = scr;                        // [npairs][36]
+        double *Xd = Xs + npairs * 36;           // [N][36]
+        double *gx = Xd + N * 36;                // [2][N][6]
+        for (int i = tid; i < npairs * 36; i += nt) Xs[i] = Hred[i];
+        for (int i = tid; i < N * 36; i += nt) Xd[i] = Hdd[i];
+        for (int i = tid; i < N * 6; i += nt) { gx[i] = gred[i]; gx[N * 6 + i] = gdir[i]; }
+        __syncthreads();
+        // direct (pre-Schur) diagonal, for the Jacobi scaling / LM diagonal: diag(T_f^T Xd T_f)
+        for (int e = tid; e < N * 6; e += nt) {
+            const int f = e / 6, i = e - f * 6;
+            const double *Tf = T + f * 36, *X = Xd + f * 36;
+            double sd = 0.0;
+            for (int aa = 0; aa < 6; ++aa) {
+                double t = 0.0;
+                for (int bb = 0; bb < 6; ++bb) t += X[aa * 6 + bb] * Tf[bb * 6 + i];
+                sd += Tf[aa * 6 + i] * t;
+            }
+            hcorr[f * stride + i] = sd;
+        }
+        const int per_pass = (nt / 36) * 36;     // whole blocks per pass: in-place update is safe
+        for (int base = 0; base < npairs * 36; base += per_pass) {
+            const int e = base + tid;
+            const bool act = tid < per_pass && e < npairs * 36;
+            double v = 0.0;
+            if (act) {
+                const int p = e / 36, ij = e - p * 36, i = ij / 6, j = ij - i * 6;
+                int f = 0;
+                while ((f + 1) * (f + 2) / 2 <= p) ++f;
+                const int gf = p - f * (f + 1) / 2;
+                const double *X = Xs + p * 36 + i * 6, *Tg = T + gf * 36 + j;
+                for (int bb = 0; bb < 6; ++bb) v += X[bb] * Tg[bb * 6];
+            }
+            __syncthreads();
+            if (act) Xs[e] = v;
+            __syncthreads();
+        }
+        for (int e = tid; e < npairs * 36; e += nt) {
+            const int p = e / 36, ij = e - p * 36, i = ij / 6, j = ij - i * 6;
+            int f = 0;
+            while ((f + 1) * (f + 2) / 2 <= p) ++f;
+            const int gf = p - f * (f + 1) / 2;
+            if (f == gf && j > i) continue;
+            const double *Tf = T + f * 36 + i, *Mx = Xs + p * 36 + j;
+            double sv = 0.0;
+            for (int aa = 0; aa < 6; ++aa) sv += Tf[aa * 6] * Mx[aa * 6];
+            const int gi = f * stride + i, gj = gf * stride + j;
+            A[tri(gi, gj)] = sv;
+            if (f == gf && i == j) hcorr[gi] -= sv;     // direct - reduced diagonal
+        }
+        for (int e = tid; e < N * 6; e += nt) {
+            const int f = e / 6, i = e - f * 6;
+            const double *Tf = T + f * 36;
+            double sr = 0.0, sd = 0.0;
+            for (int aa = 0; aa < 6; ++aa) { sr += Tf[aa * 6 + i] * gx[f * 6 + aa]; sd += Tf[aa * 6 + i] * gx[N * 6 + f * 6 + aa]; }
+            g[f * stride + i] = sr;
+            gu[f * stride + i] = sd;
+        }
+    }
+    __syncthreads();
+
+    // ---- IMU factors (bundle_adjustor.cpp:220-242): no loss
+    if (inertial && H.n_imu > 0) {
+        const int32_t *idx = a.imu_idx + (size_t)w * a.Ncap * 2;
+        const double *recs = a.imu_data + (size_t)w * a.Ncap * kImuStride;
+        for (int n0 = 0; n0 < H.n_imu; n0 += 4) {           // 4 factors per round (scratch = 4 slabs of raw + whitened J)
+            const int nb = min(4, H.n_imu - n0);
+            double *Jraw = scr;                              // [4][450], r at [4*450 + n*16]
+            double *rraw = scr + 4 * 450;
+            double *Jw = rraw + 4 * 16;                      // [4][450]
+            double *rw = Jw + 4 * 450;                       // [4][16]
+            if (tid < nb) {
+                const int n = n0 + tid;
+                imu_factor_raw(frames + idx[2 * n] * kFrameStride, frames + idx[2 * n + 1] * kFrameStride,
+                               recs + (size_t)n * kImuStride, wc, a.alias_bias, rraw + tid * 16, Jraw + tid * 450);
+            }
+            __syncthreads();
+            // whiten: Jw = W J, rw = W r                      :157 and the "sqrt_inv_cov *" lines
+            for (int e = tid; e < nb * 15 * 31; e += nt) {
+                const int n = e / (15 * 31), rem = e - n * 15 * 31, row = rem / 31, col = rem - row * 31;
+                const double *Wm = recs + (size_t)(n0 + n) * kImuStride + 11 + row * 15;
+                double s = 0.0;
+                if (col < 30) { for (int k = 0; k < 15; ++k) s += Wm[k] * Jraw[n * 450 + k * 30 + col]; Jw[n * 450 + row * 30 + col] = s; }
+                else { for (int k = 0; k < 15; ++k) s += Wm[k] * rraw[n * 16 + k]; rw[n * 16 + row] = s; }
+            }
+            __syncthreads();
+            for (int n = 0; n < nb; ++n) {                   // factors share frames: accumulate one at a time
+                const int fi = idx[2 * (n0 + n)], fj = idx[2 * (n0 + n) + 1];
+                for (int e = tid; e < 30 * 31; e += nt) {
+                    const int ra = e / 31, cb_ = e - ra * 31;
+                    const int ga = (ra < 15 ? fi * 15 + ra : fj * 15 + ra - 15);
+                    double s = 0.0;
+                    if (cb_ < 30) {
+                        const int gb = (cb_ < 15 ? fi * 15 + cb_ : fj * 15 + cb_ - 15);
+                        if (gb > ga) continue;
+                        for (int k = 0; k < 15; ++k) s += Jw[n * 450 + k * 30 + ra] * Jw[n * 450 + k * 30 + cb_];
+                        A[tri(ga, gb)] += s;
+                    } else {
+                        for (int k = 0; k < 15; ++k) s += Jw[n * 450 + k * 30 + ra] * rw[n * 16 + k];
+                        g[ga] += s; gu[ga] += s;
+                    }
+                }
+                if (tid == 0) { double c = 0.0; for (int k = 0; k < 15; ++k) c += rw[n * 16 + k] * rw[n * 16 + k]; cost_sm[1] += 0.5 * c; }
+                __syncthreads();
+            }
+        }
+    }
+
+    // ---- marginalisation prior (bundle_adjustor.cpp:126-139): no loss
+    if (inertial && H.n_prior > 0) {
+        const int n = H.n_prior, d = 15 * n, dcap = 15 * a.Ncap;
+        const int32_t *pf = a.prior_frames + (size_t)w * a.Ncap;
+        const double *S = a.prior_S + (size_t)w * dcap * dcap;
+        const double *L = a.prior_L + (size_t)w * dcap * dcap;
+        const double *ev = a.prior_e + (size_t)w * dcap;
+        const double *x0 = a.prior_x0 + (size_t)w * a.Ncap * kFrameStride;
+        double *r0 = scr;                 // [d] raw residual
+        double *rr = r0 + d;              // [d] r = S r0 + e
+        double *vv = rr + d;              // [d] S^T r
+        double *Ji = vv + d;              // [n][9] Jr^-1
+        if (tid < n) prior_frame_raw(frames + pf[tid] * kFrameStride, x0 + tid * kFrameStride, r0 + 15 * tid, Ji + 9 * tid);
+        __syncthreads();
+        for (int i = tid; i < d; i += nt) {
+            double s = ev[i];
+            for (int k = 0; k < d; ++k) s += S[(size_t)i * d + k] * r0[k];
+            rr[i] = s;                                         // marginalization_error_cost.h:91
+        }
+        __syncthreads();
+        for (int i = tid; i < d; i += nt) {
+            double s = 0.0;
+            for (int k = 0; k < d; ++k) s += S[(size_t)k * d + i] * rr[k];
+            vv[i] = s;
+        }
+        if (tid == 0) { double c = 0.0; for (int k = 0; k < d; ++k) c += rr[k] * rr[k]; cost_sm[2] = 0.5 * c; }
+        __syncthreads();
+        // g += E^T vv ; H += E^T Lambda E  with E = blockdiag(Jr^-1, I, I, I, I) per frame  (:72-88)
+        for (int i = tid; i < d; i += nt) {
+            const int fi = i / 15, ci = i - fi * 15;
+            double s;
+            if (ci < 3) { s = 0.0; for (int k = 0; k < 3; ++k) s += Ji[9 * fi + 3 * k + ci] * vv[15 * fi + k]; }
+            else s = vv[i];
+            const int gi = pf[fi] * 15 + ci;
+            g[gi] += s; gu[gi] += s;
+        }
+        for (int e = tid; e < d * d; e += nt) {
+            const int i = e / d, j = e - i * d;
+            const int fi = i / 15, ci = i - fi * 15, fj = j / 15, cj = j - fj * 15;
+            const int gi = pf[fi] * 15 + ci, gj = pf[fj] * 15 + cj;
+            if (gj > gi) continue;
+            double s = 0.0;
+            if (ci < 3 && cj < 3) {
+                for (int k = 0; k < 3; ++k)
+                    for (int m = 0; m < 3; ++m)
+                        s += Ji[9 * fi + 3 * k + ci] * L[(size_t)(15 * fi + k) * d + 15 * fj + m] * Ji[9 * fj + 3 * m + cj];
+            } else if (ci < 3) {
+                for (int k = 0; k < 3; ++k) s += Ji[9 * fi + 3 * k + ci] * L[(size_t)(15 * fi + k) * d + j];
+            } else if (cj < 3) {
+                for (int m = 0; m < 3; ++m) s += L[(size_t)i * d + 15 * fj + m] * Ji[9 * fj + 3 * m + cj];
+            } else {
+                s = L[(size_t)i * d + j];
+            }
+            A[tri(gi, gj)] += s;       // each (gi,gj) has a unique (i,j) owner: prior frames are distinct
+        }
+        __syncthreads();
+    }
+
+    // ---- plane factors (bundle_adjustor.cpp:162-196): CauchyLoss
+    if (H.n_ptracks > 0) {
+        const double *pl = a.plane_param + (size_t)w * a.Pcap * 4;
+        const int32_t *ptp = a.pt_plane + (size_t)w * a.Tcap;
+        const int32_t *ptb = a.pt_begin + (size_t)w * (a.Tcap + 1);
+        const int32_t *ptf = a.pt_frame + (size_t)w * a.Ocap;
+        const float *ptz = a.pt_z + (size_t)w * a.Ocap * 2;
+        const double cb = wc.cauchy_a * wc.cauchy_a;
+        for (int t = tid; t < H.n_ptracks; t += nt) {
+            const int b0 = ptb[t], K = ptb[t + 1] - b0;
+            double r, J[6 * kMaxFrames];
+            plane_factor(K, ptf + b0, ptz + 2 * b0, frames, wc, pl + 4 * ptp[t], wc.plane_sic, &r, J);
+            const double s = r * r, tt = 1.0 + s / cb;
+            const double sc = sqrt(1.0 / tt);
+            atomicAdd(&cost_sm[3], 0.5 * cb * log(tt));
+            r *= sc;
+            for (int i = 0; i < 6 * K; ++i) J[i] *= sc;
+            for (int i = 0; i < 6 * K; ++i) {
+                const int gi = ptf[b0 + i / 6] * stride + (i % 6);
+                atomicAdd(&g[gi], J[i] * r);
+                atomicAdd(&gu[gi], J[i] * r);
+                for (int j = 0; j <= i; ++j) {
+                    const int gj = ptf[b0 + j / 6] * stride + (j % 6);
+                    atomicAdd(&A[gi >= gj ? tri(gi, gj) : tri(gj, gi)], J[i] * J[j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- optional dump of the assembled reduced system (delta coordinates, no regulariser)
+    if (a.Hfull) {
+        const int Df = 15 * a.Ncap;
+        double *Ho = a.Hfull + (size_t)w * Df * Df, *go = a.gfull + (size_t)w * Df;
+        for (int e = tid; e < D * D; e += nt) {
+            const int i = e / D, j = e - i * D;
+            const int fi = i / stride, ci = i - fi * stride, fj = j / stride, cj = j - fj * stride;
+            Ho[(size_t)(fi * 15 + ci) * Df + fj * 15 + cj] = (i >= j) ? A[tri(i, j)] : A[tri(j, i)];
+        }
+        for (int i = tid; i < D; i += nt) go[(i / stride) * 15 + (i % stride)] = g[i];
+    }
+
+    // ---- Jacobi scale, LM diagonal, constant blocks
+    double *scale = a.pose_scale + (size_t)w * 15 * a.Ncap;
+    double my_gdx = 0.0;
+    for (int i = tid; i < D; i += nt) {
+        const int f = i / stride, c = i - f * stride;
+        const double hii = A[tri(i, i)] + hcorr[i];          // diagonal of the UNREDUCED J^T J
+        double sc;
+        if (a.compute_scale) { sc = 1.0 / (1.0 + sqrt(fmax(hii, 0.0))); scale[i] = sc; }
+        else sc = scale[i];
+        const double reg = mu > 0.0 ? lm_reg(hii, sc, mu) : 0.0;
+        xs[i] = reg;                                          // keep reg for the scalars below
+        A[tri(i, i)] += reg;
+        hcorr[i] = hii;                                       // now holds the unreduced diagonal
+    }
+    __syncthreads();
+    const int fixed_mask = H.fixed_mask;
+    for (int e = tid; e < D * (D + 1) / 2; e += nt) {
+        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        while (i * (i + 1) / 2 > e) --i;
+        const int j = e - i * (i + 1) / 2;
+        const int fi = i / stride, ci = i - fi * stride, fj = j / stride, cj = j - fj * stride;
+        const bool mi = ((fixed_mask >> fi) & 1) && ci < 6, mj = ((fixed_mask >> fj) & 1) && cj < 6;
+        if (mi || mj) A[e] = (i == j) ? 1.0 : 0.0;
+    }
+    double *reg_keep = scr;       // [D]
+    for (int i = tid; i < D; i += nt) {
+        const int f = i / stride, c = i - f * stride;
+        const bool m = ((fixed_mask >> f) & 1) && c < 6;
+        reg_keep[i] = xs[i];
+        if (m) { g[i] = 0.0; gu[i] = 0.0; }
+        xs[i] = -g[i];
+    }
+    __syncthreads();
+
+    const bool ok = chol_solve_packed(A, xs, D, &flag_sm);
+
+    // ---- outputs
+    double *dxo = a.dx_pose + (size_t)w * a.Ncap * 15;
+    for (int i = tid; i < N * 15; i += nt) {
+        const int f = i / 15, c = i - f * 15;
+        dxo[i] = (ok && c < stride) ? xs[f * stride + c] : 0.0;
+    }
+    {
+        double gdx = 0.0, rdx = 0.0, gn2 = 0.0, dx2 = 0.0, gmax = 0.0;
+        for (int i = tid; i < D; i += nt) {
+            const int f = i / stride, c = i - f * stride;
+            const bool m = ((fixed_mask >> f) & 1) && c < 6;
+            if (m) continue;
+            const double dx = ok ? xs[i] : 0.0;
+            const double sc = scale[i];
+            double d2 = sc * sc * hcorr[i];
+            d2 = fmin(fmax(d2, 1.0e-6), 1.0e32);
+            gdx += g[i] * dx;
+            rdx += reg_keep[i] * dx * dx;
+            gn2 += d2 * (dx / sc) * (dx / sc);
+            dx2 += dx * dx;
+            gmax = fmax(gmax, fabs(gu[i]));
+        }
+        __syncthreads();
+        double *red = A;                 // the factor is no longer needed
+        if (tid < D) { red[tid * 5 + 0] = gdx; red[tid * 5 + 1] = rdx; red[tid * 5 + 2] = gn2; red[tid * 5 + 3] = dx2; red[tid * 5 + 4] = gmax; }
+        __syncthreads();
+        if (tid == 0) {
+            gdx = rdx = gn2 = dx2 = gmax = 0.0;
+            const int nred = min(nt, D);
+            for (int t = 0; t < nred; ++t) {
+                gdx += red[t * 5]; rdx += red[t * 5 + 1]; gn2 += red[t * 5 + 2]; dx2 += red[t * 5 + 3];
+                gmax = fmax(gmax, red[t * 5 + 4]);
+            }
+            // |x|^2 over the ambient parameter blocks (ceres takes norms of the 4-vector quaternion)
+            double x2 = 0.0;
+            for (int f = 0; f < N; ++f) {
+                const double *fs = frames + f * kFrameStride;
+                if (!((fixed_mask >> f) & 1)) for (int k = 0; k < 7; ++k) x2 += fs[k] * fs[k];
+                if (inertial) for (int k = 7; k < 16; ++k) x2 += fs[k] * fs[k];
+            }
+            ctrl.g_dot_dx = gdx;
+            ctrl.dx_reg_dx = rdx;
+            ctrl.gn_norm2 = gn2;
+            ctrl.dxnorm2 = dx2;
+            ctrl.xnorm2 = x2;
+            ctrl.gmax = gmax;
+            ctrl.cost_vis = a.cost_vis[w];
+            ctrl.cost = a.cost_vis[w] + cost_sm[1] + cost_sm[2] + cost_sm[3];
+            ctrl.solve_failed = ok ? 0 : 1;
+            if (a.compute_scale) ctrl.have_scale = 1;
+        }
+    }
+}
+
+// Non-vision part of the cost at the candidate state (IMU + prior + plane), one CTA per window.
+struct CostArgs {
+    const WinHdr *hdr;
+    const WinConst *cst;
+    const double *frames_cand;
+    const double *frames_lin;      // bias linearisation only through the records; unused otherwise
+    const int32_t *imu_idx;
+    const double *imu_data;
+    int alias_bias;                // 1: candidate dbg = cand.bg - current.bg
+    const double *frames_cur;
+    const int32_t *prior_frames;
+    const double *prior_S, *prior_e, *prior_x0;
+    const double *plane_param;
+    const int32_t *pt_plane, *pt_begin, *pt_frame;
+    const float *pt_z;
+    int Pcap, Tcap, Ocap, Ncap;
+    double *out;                   // [W] non-vision candidate cost
+};
+
+__global__ void aux_cost_kernel(CostArgs a) {
+    const int w = blockIdx.x;
+    const WinHdr &H = a.hdr[w];
+    const WinConst &wc = a.cst[w];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double *fc = a.frames_cand + (size_t)w * a.Ncap * kFrameStride;
+    const double *fcur = a.frames_cur + (size_t)w * a.Ncap * kFrameStride;
+    __shared__ double acc;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *r0 = reinterpret_cast<double *>(smem_raw);
+    if (tid == 0) acc = 0.0;
+    __syncthreads();
+    if (H.use_inertial) {
+        const int32_t *idx = a.imu_idx + (size_t)w * a.Ncap * 2;
+        const double *recs = a.imu_data + (size_t)w * a.Ncap * kImuStride;
+        for (int n = tid; n < H.n_imu; n += nt) {
+            // residual only: reuse the raw evaluator (Jacobian discarded)
+            double r[15], J[450];
+            double rec_local[kImuStride];
+            const double *rec = recs + (size_t)n * kImuStride;
+            for (int k = 0; k < kImuStride; ++k) rec_local[k] = rec[k];
+            if (a.alias_bias) {   // Q1: the linearisation point is the CURRENT (accepted) bias of frame i
+                for (int k = 0; k < 3; ++k) {
+                    rec_local[281 + k] = fcur[idx[2 * n] * kFrameStride + 10 + k];
+                    rec_local[284 + k] = fcur[idx[2 * n] * kFrameStride + 13 + k];
+                }
+            }
+            imu_factor_raw(fc + idx[2 * n] * kFrameStride, fc + idx[2 * n + 1] * kFrameStride, rec_local, wc, 0, r, J);
+            double c = 0.0;
+            for (int i = 0; i < 15; ++i) {
+                double s = 0.0;
+                for (int k = 0; k < 15; ++k) s += rec[11 + i * 15 + k] * r[k];
+                c += s * s;
+            }
+            atomicAdd(&acc, 0.5 * c);
+        }
+        if (H.n_prior > 0) {
+            const int n = H.n_prior, d = 15 * n, dcap = 15 * a.Ncap;
+            const int32_t *pf = a.prior_frames + (size_t)w * a.Ncap;
+            const double *S = a.prior_S + (size_t)w * dcap * dcap;
+            const double *ev = a.prior_e + (size_t)w * dcap;
+            const double *x0 = a.prior_x0 + (size_t)w * a.Ncap * kFrameStride;
+            double Ji[9];
+            if (tid < n) prior_frame_raw(fc + pf[tid] * kFrameStride, x0 + tid * kFrameStride, r0 + 15 * tid, Ji);
+            __syncthreads();
+            double c = 0.0;
+            for (int i = tid; i < d; i += nt) {
+                double s = ev[i];
+                for (int k = 0; k < d; ++k) s += S[(size_t)i * d + k] * r0[k];
+                c += s * s;
+            }
+            atomicAdd(&acc, 0.5 * c);
+        }
+    }
+    if (H.n_ptracks > 0) {
+        const double *pl = a.plane_param + (size_t)w * a.Pcap * 4;
+        const int32_t *ptp = a.pt_plane + (size_t)w * a.Tcap;
+        const int32_t *ptb = a.pt_begin + (size_t)w * (a.Tcap + 1);
+        const int32_t *ptf = a.pt_frame + (size_t)w * a.Ocap;
+        const float *ptz = a.pt_z + (size_t)w * a.Ocap * 2;
+        const double cb = wc.cauchy_a * wc.cauchy_a;
+        for (int t = tid; t < H.n_ptracks; t += nt) {
+            const int b0 = ptb[t], K = ptb[t + 1] - b0;
+            double r, J[6 * kMaxFrames];
+            plane_factor(K, ptf + b0, ptz + 2 * b0, fc, wc, pl + 4 * ptp[t], wc.plane_sic, &r, J);
+            atomicAdd(&acc, 0.5 * cb * log(1.0 + r * r / cb));
+        }
+    }
+    __syncthreads();
+    if (tid == 0) a.out[w] = acc;
+}
+
+}  // namespace pvio

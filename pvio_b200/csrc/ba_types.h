@@ -1,0 +1,62 @@
+// Device-side (packed) layout of a batch of sliding windows.  See DESIGN.md "Data layout".
+// Observation / landmark records are the 16-byte fp32 records SURVEY.md 8(d) counts as
+// algorithmic bytes; all STATE (poses, motion, inverse depths) stays fp64 because the
+// residual must be evaluated in fp64 to meet the 1e-5 relative tolerance on dx.
+#pragma once
+#include <stdint.h>
+
+namespace pvio {
+
+constexpr int kMaxFrames = 16;      // PVIO_B200_MAX_FRAMES
+constexpr int kFrameStride = 16;    // doubles per frame state
+constexpr int kImuStride = 288;     // doubles per IMU factor record
+constexpr int kMaxChunks = 96;      // anchor-homogeneous chunks of <= 32 landmarks per window
+
+struct __align__(16) ObsRec {       // one reprojection residual block (non-anchor observation)
+    float zx, zy;                   // normalised keypoint in the target frame
+    int32_t lm;                     // landmark index inside the window (packed order)
+    int32_t frame;                  // target frame index
+};
+
+struct __align__(16) LmRec {        // one inverse-depth landmark
+    float zrx, zry;                 // normalised keypoint in the anchor frame
+    int32_t meta;                   // anchor | n_obs << 8 | in_victim << 16
+    int32_t obs_begin;              // first ObsRec of this landmark
+};
+
+struct WinHdr {                     // per-window integers
+    int32_t N, M, K, use_inertial;
+    int32_t n_imu, n_prior, n_planes, n_ptracks;
+    int32_t fixed_mask;             // bit f: FF_FIX_POSE
+    int32_t n_chunks;
+    int32_t pad0, pad1;
+    int32_t chunk_begin[kMaxChunks];   // first landmark of chunk c
+    int32_t chunk_meta[kMaxChunks];    // count | anchor << 8
+};
+
+struct WinConst {                   // per-window doubles
+    double cam_q[4], cam_p[3];
+    double imu_q[4], imu_p[3];
+    double sic[4];                  // sqrt_inv_cov 2x2
+    double fx, fy, cauchy_a, plane_sic;
+    double origin[3];               // window origin subtracted from all positions (mean frame position)
+    double pad;
+};
+
+struct WinCtrl {                    // per-window solver state (device resident)
+    double mu, radius;
+    double cost, cand_cost;         // 0.5 * sum rho(s): current / candidate
+    double cost_vis, cand_cost_vis; // reprojection part accumulated by the sweeps
+    double g_dot_dx, dx_reg_dx, gn_norm2, gmax, xnorm2, dxnorm2;
+    double model_change;
+    int32_t iteration, accepted, done, termination;
+    int32_t solve_failed, have_scale, usable, pad;
+};
+
+// per-landmark Schur scalars written by the linearise kernel, read by the update kernel
+struct __align__(16) LmAux {
+    double hll_reg;                 // H_ll + mu * clamp(.)  (the pivot the Schur complement divides by)
+    double gl;                      // g_l
+};
+
+}  // namespace pvio

@@ -1,0 +1,168 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C-ABI against the fp64
+oracle on identical seeded inputs.  Tolerance: BASELINE.json north_star -- dx within 1e-5
+relative of the reference step; integer/index results bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import ba_oracle as bo
+from pvio_b200 import synth
+from pvio_b200.bundle_adjustor import BundleAdjustor
+
+pytestmark = pytest.mark.gpu
+
+TOL_DX = 1.0e-5
+
+
+@pytest.fixture(scope="module")
+def ba():
+    b = BundleAdjustor(max_windows=8, max_frames=12, max_landmarks=640, max_obs=6000)
+    yield b
+    b.close()
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _check_step(ba, w, st, tol=TOL_DX):
+    ref = bo.gn_step(w, st, schur=True)
+    out = ba.gn_step(w, st, mu=1e-8, want_system=True)
+    P = 15 * w.N
+    e_pose, e_lm, e_all = _rel(out['dx'][:P], ref['dx'][:P]), _rel(out['dx'][P:], ref['dx'][P:]), _rel(out['dx'], ref['dx'])
+    print(f"N={w.N} M={w.M} K={w.K}: dx rel err pose {e_pose:.2e} lm {e_lm:.2e} all {e_all:.2e}; "
+          f"cost {out['cost']:.6f} vs {ref['cost']:.6f}")
+    assert e_pose < tol and e_lm < tol and e_all < tol
+    assert abs(out['cost'] - ref['cost']) <= 2e-6 * ref['cost']
+    # masked coordinates stay exactly zero
+    assert np.all(out['dx'][~ref['free']] == 0.0)
+    # candidate cost equals the oracle's cost at its own candidate
+    cand = bo.total_cost(w, bo.apply_step(w, st, ref['dx']))
+    assert abs(out['new_cost'] - cand) <= 5e-5 * max(cand, 1.0)
+    # reduced system (delta coordinates); the dump is taken before the mu*diag regulariser
+    free = ref['free'][:P]
+    Href = bo.gn_step(w, st, mu=0.0, schur=True)
+    hs = np.sqrt(np.abs(np.diag(Href['Hred'])))[free]
+    A, B = out['Hred'][np.ix_(free, free)], Href['Hred'][np.ix_(free, free)]
+    assert np.max(np.abs(A - B) / np.outer(hs, hs)) < 2e-5
+    return out, ref
+
+
+def test_gn_step_cfg2_small(ba):
+    w, st, _ = synth.make_cfg2(N=5, M=40)
+    _check_step(ba, w, st)
+
+
+def test_gn_step_cfg2_full(ba):
+    w, st, _ = synth.make_cfg2()
+    assert (w.N, w.M, w.K) == (10, 500, 4500)
+    _check_step(ba, w, st)
+
+
+def test_gn_step_cfg2b_staggered(ba):
+    w, st, _ = synth.make_cfg2(staggered=True)
+    assert w.K == 3500
+    _check_step(ba, w, st)
+
+
+def test_gn_step_unsorted_landmarks_and_ragged(ba):
+    """Landmarks in arbitrary anchor order, tracks of length 1..N-1, a landmark seen once."""
+    w, st, _ = synth.make_cfg2(N=7, M=90, staggered=True, seed=5)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(w.M)
+    beg, of, oz = [0], [], []
+    for l in perm:
+        b0, b1 = int(w.lm_obs_begin[l]), int(w.lm_obs_begin[l + 1])
+        keep = max(1, int(rng.integers(1, b1 - b0 + 1)))
+        of += list(w.obs_frame[b0:b0 + keep])
+        oz += list(w.obs_z[b0:b0 + keep])
+        beg.append(len(of))
+    w.lm_anchor, w.lm_z_ref, w.lm_in_victim = w.lm_anchor[perm], w.lm_z_ref[perm], w.lm_in_victim[perm]
+    w.lm_obs_begin = np.array(beg, dtype=np.int32)
+    w.obs_frame, w.obs_z = np.array(of, dtype=np.int32), np.array(oz).reshape(-1, 2)
+    w.K = len(of)
+    st.rho = st.rho[perm]
+    w.validate()
+    _check_step(ba, w, st)
+
+
+def test_gn_step_cfg3_inertial_prior(ba):
+    w, st, _ = synth.make_cfg3()
+    assert w.N == 9 and w.n_imu == 8 and w.n_prior == 8
+    _check_step(ba, w, st)
+
+
+def test_gn_step_cfg3_gauge_prior(ba):
+    w, st, _ = synth.make_cfg3(prior='gauge', N=6, M=120)
+    _check_step(ba, w, st)
+
+
+def test_gn_step_cfg3_bias_offset(ba):
+    """bias away from its linearisation point exercises the dq_dbg / right-Jacobian terms."""
+    w, st, _ = synth.make_cfg3(N=6, M=100)
+    st.bg = st.bg + np.array([2e-3, -1e-3, 1.5e-3])
+    st.ba = st.ba + np.array([1e-2, 2e-2, -1e-2])
+    _check_step(ba, w, st)
+
+
+def test_gn_step_cfg4_planes(ba):
+    w, st, _ = synth.make_cfg4()
+    assert w.n_ptracks == 80
+    _check_step(ba, w, st)
+
+
+def test_batch_replicas_agree(ba):
+    w, st, _ = synth.make_cfg2(N=6, M=64)
+    ba.batch_set(0, w, st)
+    ba.batch_replicate(8)
+    ba.batch_upload(8)
+    ba.batch_gn_step(8, 1e-8, apply=False)
+    dx, costs = ba.batch_download(8, 15 * w.N + w.M)
+    single = ba.gn_step(w, st)
+    for i in range(8):
+        assert _rel(dx[i], single['dx']) < 1e-9      # same kernels, different CTA split only
+    assert np.allclose(costs[:, 0], single['cost'], rtol=1e-12)
+
+
+def test_batch_distinct_windows_and_apply(ba):
+    ws = [synth.make_cfg2(N=6, M=48, seed=700 + i) for i in range(4)]
+    for i, (w, st, _) in enumerate(ws):
+        ba.batch_set(i, w, st)
+    ba.batch_upload(4)
+    ba.batch_gn_step(4, 1e-8, apply=True)
+    dx, costs = ba.batch_download(4, 15 * 6 + 48)
+    for i, (w, st, _) in enumerate(ws):
+        ref = bo.gn_step(w, st, schur=True)
+        assert _rel(dx[i], ref['dx']) < TOL_DX
+    # second step starts from the applied state: cost equals the first step's candidate cost
+    first_cand = costs[:, 1].copy()
+    ba.batch_gn_step(4, 1e-8, apply=False)
+    _, costs2 = ba.batch_download(4, 15 * 6 + 48)
+    assert np.allclose(costs2[:, 0], first_cand, rtol=1e-6)
+
+
+@pytest.mark.parametrize("maker,kw", [(synth.make_cfg2, dict(N=6, M=80)),
+                                      (synth.make_cfg2, dict()),
+                                      (synth.make_cfg3, dict(N=6, M=100))])
+def test_solve_matches_oracle_loop(ba, maker, kw):
+    w, st, _ = maker(**kw)
+    ref_state, ref_sum = bo.solve(w, st, max_iter=6)
+    out, summ = ba.solve(w, st, max_iterations=6)
+    print(summ['iterations'], ref_sum['iterations'], summ['final_cost'], ref_sum['final_cost'])
+    assert all(ref_sum['accepted'])        # the case exercises the Gauss-Newton leg only
+    assert summ['iterations'] == ref_sum['iterations']
+    assert abs(summ['final_cost'] - ref_sum['final_cost']) <= 1e-5 * ref_sum['final_cost']
+    move = np.linalg.norm(ref_state.p - st.p)
+    assert np.linalg.norm(out.p - ref_state.p) < 2e-5 * max(move, 1e-3) + 1e-9
+    assert np.linalg.norm(out.rho - ref_state.rho) < 2e-5 * np.linalg.norm(ref_state.rho - st.rho) + 1e-9
+    # post-pass flags are bit-exact, quality to fp tolerance
+    valid, quality = bo.landmark_postpass(w, ref_state)
+    assert np.array_equal(summ['valid'], valid)
+    assert np.allclose(summ['quality'][valid], quality[valid], rtol=1e-3, atol=1e-3)
+
+
+def test_reprojection_error(ba):
+    w, st, _ = synth.make_cfg2(N=6, M=80)
+    valid, quality = bo.landmark_postpass(w, st)
+    n = np.diff(w.lm_obs_begin) + 1
+    ref = np.sum(quality * n) / np.sum(n)
+    assert abs(ba.compute_reprojection_error(w, st) - ref) < 1e-6 * ref
