@@ -34,7 +34,8 @@ def build(force=False, verbose=False):
 
     def cc(job):
         src, obj = job
-        r = subprocess.run([NVCC] + FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
+        extra = ["-fmad=false"] if src.endswith("klt.cu") else []   # OpenCV-exact float rounding
+        r = subprocess.run([NVCC] + FLAGS + extra + ["-c", src, "-o", obj], capture_output=True, text=True)
         return src, r
 
     with ThreadPoolExecutor(max_workers=4) as ex:

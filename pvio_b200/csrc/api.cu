@@ -317,6 +317,11 @@ static int upload(Handle *h, int n) {
     return 0;
 }
 
+int pack_and_upload(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s) {
+    TRY(pack_window(h, 0, w, s));
+    return upload(h, 1);
+}
+
 // ------------------------------------------------------------------------ launches
 struct StepCfg {
     double mu = -1.0;          // < 0: per-window ctrl.mu

@@ -63,6 +63,8 @@ int fail(Handle *h, int code, const char *what, cudaError_t e = cudaSuccess);
         if (e__ != cudaSuccess) return fail((h), PVIO_B200_ECUDA, #call, e__); \
     } while (0)
 
+// api.cu: pack window into slot 0 and copy it to the device
+int pack_and_upload(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s);
 // klt.cu
 int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int width, int height, int stride,
                    const float *prev_pts, float *next_pts, uint8_t *status, float *err, int n_points,

@@ -1,7 +1,376 @@
-// placeholder; replaced below by the real marginaliser
+// Frame marginalisation: BundleAdjustor::marginalize_frame (estimation/bundle_adjustor.cpp:348-599).
+//
+//   prior J^T J                                   :369-413   marg_assemble_kernel
+//   IMU factors adjacent to the victim            :416-450   marg_assemble_kernel
+//   reprojection factors of victim-seen tracks    :453-533   lin_schur_kernel<false> (no loss, quirk Q3)
+//   landmark Schur (1/mat, isfinite skip)         :536-545   lin_schur_kernel<false>
+//   frame Schur with the explicit 15x15 inverse   :547-581   marg_reduce_kernel
+//   eigen factorisation, clamp lambda <= 1e-8     :583-590   marg_eig_kernel (parallel cyclic Jacobi)
+// All dense algebra is fp64.  Runs once per keyframe (not per iteration): latency, not bandwidth.
+#include <cstring>
+#include <vector>
 #include "api_internal.h"
+#include "ba_lin.cuh"
+#include "ba_solve.cuh"
+
 namespace pvio {
-int marginalize_impl(Handle *h, const pvio_b200_window *, const pvio_b200_state *, int, double *, double *, double *, double *) {
-    return fail(h, PVIO_B200_EINVAL, "marginalize: not built yet");
+
+struct MargArgs {
+    const WinHdr *hdr;
+    const WinConst *cst;
+    const double *frames;
+    const double *Hred, *gred;         // vision part (xi coordinates) from lin_schur_kernel<false>
+    const int32_t *imu_idx;
+    const double *imu_data;
+    const int32_t *prior_frames;
+    const double *prior_S, *prior_L, *prior_e, *prior_x0;
+    int Ncap;
+    int index;                         // victim frame
+    double *H;                         // [(15N)^2] row-major, full symmetric
+    double *b;                         // [15N]
+    double *scratch;                   // >= 4*(15*30+16) + 4*15*Ncap doubles
+};
+
+__global__ void __launch_bounds__(256) marg_assemble_kernel(MargArgs a) {
+    const WinHdr &Hh = a.hdr[0];
+    const WinConst &wc = a.cst[0];
+    const int N = Hh.N, n = 15 * N;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double *frames = a.frames;
+    __shared__ double T[kMaxFrames * 36];
+    for (int i = tid; i < n * n; i += nt) a.H[i] = 0.0;
+    for (int i = tid; i < n; i += nt) a.b[i] = 0.0;
+    if (tid < N) {
+        const double *fs = frames + tid * kFrameStride;
+        double R[9], Hp[9], B[9];
+        quat_to_mat(fs, R);
+        const double p[3] = {fs[4] - wc.origin[0], fs[5] - wc.origin[1], fs[6] - wc.origin[2]};
+        hat(p, Hp);
+        mat3_mul(Hp, R, B);
+        double *Tf = T + tid * 36;
+        for (int r_ = 0; r_ < 3; ++r_)
+            for (int c_ = 0; c_ < 3; ++c_) {
+                Tf[r_ * 6 + c_] = R[3 * r_ + c_];
+                Tf[r_ * 6 + 3 + c_] = 0.0;
+                Tf[(3 + r_) * 6 + c_] = -B[3 * r_ + c_];
+                Tf[(3 + r_) * 6 + 3 + c_] = (r_ == c_) ? -1.0 : 0.0;
+            }
+    }
+    __syncthreads();
+    // ---- vision: H_delta[f,g] = T_f^T X T_g  (reprojection + landmark Schur, :453-545)
+    const int npairs = N * (N + 1) / 2;
+    for (int e = tid; e < npairs * 36; e += nt) {
+        const int p = e / 36, ij = e - p * 36, i = ij / 6, j = ij - i * 6;
+        int f = 0;
+        while ((f + 1) * (f + 2) / 2 <= p) ++f;
+        const int gf = p - f * (f + 1) / 2;
+        const double *X = a.Hred + p * 36;
+        const double *Tf = T + f * 36, *Tg = T + gf * 36;
+        double s = 0.0;
+        for (int aa = 0; aa < 6; ++aa) {
+            double t = 0.0;
+            for (int bb = 0; bb < 6; ++bb) t += X[aa * 6 + bb] * Tg[bb * 6 + j];
+            s += Tf[aa * 6 + i] * t;
+        }
+        const int gi = f * 15 + i, gj = gf * 15 + j;
+        a.H[(size_t)gi * n + gj] = s;
+        if (f != gf) a.H[(size_t)gj * n + gi] = s;
+    }
+    for (int e = tid; e < N * 6; e += nt) {
+        const int f = e / 6, i = e - f * 6;
+        double s = 0.0;
+        for (int aa = 0; aa < 6; ++aa) s += T[f * 36 + aa * 6 + i] * a.gred[f * 6 + aa];
+        a.b[f * 15 + i] = s;
+    }
+    __syncthreads();
+    // ---- prior :369-413  (H += E^T Lambda E, b += E^T S^T (S r0 + e))
+    if (Hh.n_prior > 0) {
+        const int np = Hh.n_prior, d = 15 * np;
+        double *r0 = a.scratch, *rr = r0 + d, *vv = rr + d, *Ji = vv + d;
+        if (tid < np) prior_frame_raw(frames + a.prior_frames[tid] * kFrameStride, a.prior_x0 + tid * kFrameStride,
+                                      r0 + 15 * tid, Ji + 9 * tid);
+        __syncthreads();
+        for (int i = tid; i < d; i += nt) {
+            double s = a.prior_e[i];
+            for (int k = 0; k < d; ++k) s += a.prior_S[(size_t)i * d + k] * r0[k];
+            rr[i] = s;
+        }
+        __syncthreads();
+        for (int i = tid; i < d; i += nt) {
+            double s = 0.0;
+            for (int k = 0; k < d; ++k) s += a.prior_S[(size_t)k * d + i] * rr[k];
+            vv[i] = s;
+        }
+        __syncthreads();
+        for (int i = tid; i < d; i += nt) {
+            const int fi = i / 15, ci = i - fi * 15;
+            double s;
+            if (ci < 3) { s = 0.0; for (int k = 0; k < 3; ++k) s += Ji[9 * fi + 3 * k + ci] * vv[15 * fi + k]; }
+            else s = vv[i];
+            a.b[a.prior_frames[fi] * 15 + ci] += s;
+        }
+        const double *L = a.prior_L;
+        for (int e = tid; e < d * d; e += nt) {
+            const int i = e / d, j = e - i * d;
+            const int fi = i / 15, ci = i - fi * 15, fj = j / 15, cj = j - fj * 15;
+            double s = 0.0;
+            if (ci < 3 && cj < 3) {
+                for (int k = 0; k < 3; ++k)
+                    for (int m = 0; m < 3; ++m)
+                        s += Ji[9 * fi + 3 * k + ci] * L[(size_t)(15 * fi + k) * d + 15 * fj + m] * Ji[9 * fj + 3 * m + cj];
+            } else if (ci < 3) {
+                for (int k = 0; k < 3; ++k) s += Ji[9 * fi + 3 * k + ci] * L[(size_t)(15 * fi + k) * d + j];
+            } else if (cj < 3) {
+                for (int m = 0; m < 3; ++m) s += L[(size_t)i * d + 15 * fj + m] * Ji[9 * fj + 3 * m + cj];
+            } else {
+                s = L[(size_t)i * d + j];
+            }
+            a.H[(size_t)(a.prior_frames[fi] * 15 + ci) * n + a.prior_frames[fj] * 15 + cj] += s;
+        }
+        __syncthreads();
+    }
+    // ---- IMU factors with j == index or j == index + 1  :416-450.  The functor reads the bias
+    // linearisation point from the very memory passed as the parameter, so dbg = dba = 0.
+    for (int m = 0; m < Hh.n_imu; ++m) {
+        const int fi = a.imu_idx[2 * m], fj = a.imu_idx[2 * m + 1];
+        if (fj != a.index && fj != a.index + 1) continue;
+        double *Jraw = a.scratch, *rraw = Jraw + 450, *Jw = rraw + 16, *rw = Jw + 450;
+        const double *rec = a.imu_data + (size_t)m * kImuStride;
+        if (tid == 0) imu_factor_raw(frames + fi * kFrameStride, frames + fj * kFrameStride, rec, wc, 1, rraw, Jraw);
+        __syncthreads();
+        for (int e = tid; e < 15 * 31; e += nt) {
+            const int row = e / 31, col = e - row * 31;
+            const double *Wm = rec + 11 + row * 15;
+            double s = 0.0;
+            if (col < 30) { for (int k = 0; k < 15; ++k) s += Wm[k] * Jraw[k * 30 + col]; Jw[row * 30 + col] = s; }
+            else { for (int k = 0; k < 15; ++k) s += Wm[k] * rraw[k]; rw[row] = s; }
+        }
+        __syncthreads();
+        for (int e = tid; e < 30 * 31; e += nt) {
+            const int ra = e / 31, cb_ = e - ra * 31;
+            const int ga = (ra < 15 ? fi * 15 + ra : fj * 15 + ra - 15);
+            double s = 0.0;
+            if (cb_ < 30) {
+                const int gb = (cb_ < 15 ? fi * 15 + cb_ : fj * 15 + cb_ - 15);
+                for (int k = 0; k < 15; ++k) s += Jw[k * 30 + ra] * Jw[k * 30 + cb_];
+                a.H[(size_t)ga * n + gb] += s;
+            } else {
+                for (int k = 0; k < 15; ++k) s += Jw[k * 30 + ra] * rw[k];
+                a.b[ga] += s;
+            }
+        }
+        __syncthreads();
+    }
 }
+
+// Frame Schur complement :547-581.  inv = H[vv]^-1 by Gauss-Jordan with partial pivoting
+// (Eigen's dynamic .inverse() is PartialPivLU based), then Hk = H[kk] - H[kv] inv H[vk].
+__global__ void __launch_bounds__(256) marg_reduce_kernel(const double *H, const double *b, int N, int index,
+                                                         double *Hk, double *bk) {
+    const int n = 15 * N, dk = n - 15, v0 = 15 * index;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ double M[15][31];
+    __shared__ int piv_sm;
+    for (int e = tid; e < 15 * 30; e += nt) {
+        const int i = e / 30, j = e - i * 30;
+        M[i][j] = (j < 15) ? H[(size_t)(v0 + i) * n + v0 + j] : ((j - 15 == i) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    for (int c = 0; c < 15; ++c) {
+        if (tid == 0) {
+            int p = c;
+            double best = fabs(M[c][c]);
+            for (int i = c + 1; i < 15; ++i) if (fabs(M[i][c]) > best) { best = fabs(M[i][c]); p = i; }
+            piv_sm = p;
+        }
+        __syncthreads();
+        const int p = piv_sm;
+        if (p != c && tid < 30) { const double t = M[c][tid]; M[c][tid] = M[p][tid]; M[p][tid] = t; }
+        __syncthreads();
+        const double ip = 1.0 / M[c][c];
+        __syncthreads();
+        if (tid < 30) M[c][tid] *= ip;
+        __syncthreads();
+        // eliminate column c from the other rows (compute, barrier, write: no read/write race)
+        double newv[2] = {0.0, 0.0};
+        int cnt = 0;
+        for (int e = tid; e < 15 * 30; e += nt, ++cnt) {
+            const int i = e / 30, jx = e - i * 30;
+            newv[cnt] = (i != c) ? M[i][jx] - M[i][c] * M[c][jx] : M[i][jx];
+        }
+        __syncthreads();
+        cnt = 0;
+        for (int e = tid; e < 15 * 30; e += nt, ++cnt) M[e / 30][e % 30] = newv[cnt];
+        __syncthreads();
+    }
+    // keep index list: all coordinates except the victim's 15
+    // W = H[kv] * inv  (dk x 15) streamed through registers per thread
+    for (int e = tid; e < dk * (dk + 1); e += nt) {
+        const int i = e / (dk + 1), j = e - i * (dk + 1);
+        const int gi = i < v0 ? i : i + 15;
+        // row vector H[gi, v] * inv
+        double acc = 0.0;
+        if (j < dk) {
+            const int gj = j < v0 ? j : j + 15;
+            for (int k = 0; k < 15; ++k) {
+                double wk = 0.0;
+                for (int m = 0; m < 15; ++m) wk += H[(size_t)gi * n + v0 + m] * M[m][15 + k];
+                acc += wk * H[(size_t)(v0 + k) * n + gj];
+            }
+            Hk[(size_t)i * dk + j] = H[(size_t)gi * n + gj] - acc;
+        } else {
+            for (int k = 0; k < 15; ++k) {
+                double wk = 0.0;
+                for (int m = 0; m < 15; ++m) wk += H[(size_t)gi * n + v0 + m] * M[m][15 + k];
+                acc += wk * b[v0 + k];
+            }
+            bk[i] = b[gi] - acc;
+        }
+    }
 }
+
+// Symmetric eigen-decomposition by parallel cyclic Jacobi (round-robin pairing), fp64, one CTA.
+// A (d x d, overwritten) and V (d x d, columns = eigenvectors) live in global memory (L2).
+// Then S = sqrt(max(lambda,0 if <= 1e-8)) V^T and e = sqrt(1/lambda) V^T b   (:586-590).
+__global__ void __launch_bounds__(512) marg_eig_kernel(double *A, double *V, const double *bvec, int d,
+                                                      double *S, double *evec, int max_sweeps) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ double cs[128][2];      // rotation (c, s) per pair of the current round
+    __shared__ int pp[128], qq[128];
+    __shared__ double off_sm, dia_sm;
+    const int m = (d + 1) / 2;         // pairs per round (pad with a dummy index when d is odd)
+    const int dd = 2 * m;
+    for (int e = tid; e < d * d; e += nt) V[e] = ((e / d) == (e % d)) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        // convergence: off-diagonal Frobenius norm relative to the diagonal
+        if (tid == 0) { off_sm = 0.0; dia_sm = 0.0; }
+        __syncthreads();
+        double off = 0.0, dia = 0.0;
+        for (int e = tid; e < d * d; e += nt) {
+            const int i = e / d, j = e - i * d;
+            const double v = A[e];
+            if (i == j) dia += v * v; else off += v * v;
+        }
+        for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dia += __shfl_xor_sync(0xffffffffu, dia, o); }
+        if ((tid & 31) == 0) { atomicAdd(&off_sm, off); atomicAdd(&dia_sm, dia); }
+        __syncthreads();
+        const bool conv = off_sm <= 1e-30 * dia_sm;
+        __syncthreads();
+        if (conv) break;
+        for (int round = 0; round < dd - 1; ++round) {
+            // round-robin tournament: position k in [0, dd): player(k) ; pairs (k, dd-1-k)
+            if (tid < m) {
+                auto player = [&](int pos) { return pos == 0 ? 0 : 1 + ((pos - 1 + round) % (dd - 1)); };
+                int p = player(tid), q = player(dd - 1 - tid);
+                if (p > q) { const int t = p; p = q; q = t; }
+                double c = 1.0, s = 0.0;
+                if (q < d) {
+                    const double apq = A[(size_t)p * d + q];
+                    if (fabs(apq) > 1e-300) {
+                        const double app = A[(size_t)p * d + p], aqq = A[(size_t)q * d + q];
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(t * t + 1.0);
+                        s = t * c;
+                    }
+                } else { q = -1; }
+                pp[tid] = p; qq[tid] = q; cs[tid][0] = c; cs[tid][1] = s;
+            }
+            __syncthreads();
+            // rows: A <- J^T A  (rows p,q of every pair; pairs are disjoint)
+            for (int e = tid; e < m * d; e += nt) {
+                const int k = e / d, col = e - k * d;
+                const int p = pp[k], q = qq[k];
+                if (q < 0) continue;
+                const double c = cs[k][0], s = cs[k][1];
+                const double ap = A[(size_t)p * d + col], aq = A[(size_t)q * d + col];
+                A[(size_t)p * d + col] = c * ap - s * aq;
+                A[(size_t)q * d + col] = s * ap + c * aq;
+            }
+            __syncthreads();
+            // columns: A <- A J, V <- V J
+            for (int e = tid; e < m * d; e += nt) {
+                const int k = e / d, row = e - k * d;
+                const int p = pp[k], q = qq[k];
+                if (q < 0) continue;
+                const double c = cs[k][0], s = cs[k][1];
+                const double ap = A[(size_t)row * d + p], aq = A[(size_t)row * d + q];
+                A[(size_t)row * d + p] = c * ap - s * aq;
+                A[(size_t)row * d + q] = s * ap + c * aq;
+                const double vp = V[(size_t)row * d + p], vq = V[(size_t)row * d + q];
+                V[(size_t)row * d + p] = c * vp - s * vq;
+                V[(size_t)row * d + q] = s * vp + c * vq;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // S = sqrt(lambda_clamped) V^T ; e = sqrt(1/lambda) V^T b
+    for (int i = tid; i < d; i += nt) {
+        const double lam = A[(size_t)i * d + i];
+        const bool pos = lam > 1.0e-8;
+        const double sl = pos ? sqrt(lam) : 0.0, il = pos ? sqrt(1.0 / lam) : 0.0;
+        double dot = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double v = V[(size_t)k * d + i];
+            S[(size_t)i * d + k] = sl * v;
+            dot += v * bvec[k];
+        }
+        evec[i] = il * dot;
+    }
+}
+
+int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s, int index,
+                     double *S_out, double *e_out, double *H_out, double *b_out) {
+    const int N = w->n_frames;
+    if (index < 0 || index >= N || N < 2) return fail(h, PVIO_B200_EINVAL, "marginalize: bad frame index");
+    if (!w->use_inertial) return fail(h, PVIO_B200_EINVAL, "marginalize: the window must carry motion states");
+    int rc = pack_and_upload(h, w, s);
+    if (rc != 0) return rc;
+    const int n = 15 * N, dk = n - 15;
+    // vision part: no loss, victim-seen landmarks only, mu = 0
+    const size_t npc = (size_t)h->Ncap * (h->Ncap + 1) / 2;
+    CK(h, cudaMemsetAsync(h->Hred.d, 0, sizeof(double) * npc * 36, h->stream));
+    CK(h, cudaMemsetAsync(h->Hdd.d, 0, sizeof(double) * h->Ncap * 36, h->stream));
+    CK(h, cudaMemsetAsync(h->gdir.d, 0, sizeof(double) * h->Ncap * 6, h->stream));
+    CK(h, cudaMemsetAsync(h->gred.d, 0, sizeof(double) * h->Ncap * 6, h->stream));
+    CK(h, cudaMemsetAsync(h->cost_vis.d, 0, sizeof(double), h->stream));
+    LinArgs a;
+    a.hdr = h->hdr.d; a.cst = h->cst.d; a.obs = h->obs.d; a.lms = h->lms.d; a.rho = h->rho.d; a.frames = h->frames.d;
+    a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d;
+    a.Hred = h->Hred.d; a.Hdd = h->Hdd.d; a.gdir = h->gdir.d; a.gred = h->gred.d; a.cost_vis = h->cost_vis.d;
+    a.Ncap = h->Ncap; a.Mcap = h->Mcap; a.Kcap = h->Kcap;
+    a.compute_scale = 1; a.victim_only = 1; a.mu_override = 0.0;
+    lin_schur_kernel<false><<<dim3(16, 1), kLinThreads, lin_smem_bytes(), h->stream>>>(a);
+    ++h->launches;
+    // dense buffers
+    double *dH = nullptr, *db = nullptr, *dHk = nullptr, *dbk = nullptr, *dV = nullptr, *dS = nullptr, *de = nullptr, *dscr = nullptr;
+    CK(h, cudaMalloc(&dH, sizeof(double) * n * n)); CK(h, cudaMalloc(&db, sizeof(double) * n));
+    CK(h, cudaMalloc(&dHk, sizeof(double) * dk * dk)); CK(h, cudaMalloc(&dbk, sizeof(double) * dk));
+    CK(h, cudaMalloc(&dV, sizeof(double) * dk * dk)); CK(h, cudaMalloc(&dS, sizeof(double) * dk * dk));
+    CK(h, cudaMalloc(&de, sizeof(double) * dk)); CK(h, cudaMalloc(&dscr, sizeof(double) * (2048 + 64 * h->Ncap)));
+    MargArgs m;
+    m.hdr = h->hdr.d; m.cst = h->cst.d; m.frames = h->frames.d; m.Hred = h->Hred.d; m.gred = h->gred.d;
+    m.imu_idx = h->imu_idx.d; m.imu_data = h->imu_data.d; m.prior_frames = h->prior_frames.d;
+    m.prior_S = h->prior_S.d; m.prior_L = h->prior_L.d; m.prior_e = h->prior_e.d; m.prior_x0 = h->prior_x0.d;
+    m.Ncap = h->Ncap; m.index = index; m.H = dH; m.b = db; m.scratch = dscr;
+    marg_assemble_kernel<<<1, 256, 0, h->stream>>>(m);
+    marg_reduce_kernel<<<1, 256, 0, h->stream>>>(dH, db, N, index, dHk, dbk);
+    h->launches += 2;
+    if (H_out) CK(h, cudaMemcpyAsync(H_out, dHk, sizeof(double) * dk * dk, cudaMemcpyDeviceToHost, h->stream));
+    if (b_out) CK(h, cudaMemcpyAsync(b_out, dbk, sizeof(double) * dk, cudaMemcpyDeviceToHost, h->stream));
+    if (S_out || e_out) {
+        if (dk > 256) return fail(h, PVIO_B200_EINVAL, "marginalize: window too large for the eigen-solver");
+        marg_eig_kernel<<<1, 512, 0, h->stream>>>(dHk, dV, dbk, dk, dS, de, 30);
+        ++h->launches;
+        if (S_out) CK(h, cudaMemcpyAsync(S_out, dS, sizeof(double) * dk * dk, cudaMemcpyDeviceToHost, h->stream));
+        if (e_out) CK(h, cudaMemcpyAsync(e_out, de, sizeof(double) * dk, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    cudaFree(dH); cudaFree(db); cudaFree(dHk); cudaFree(dbk); cudaFree(dV); cudaFree(dS); cudaFree(de); cudaFree(dscr);
+    return 0;
+}
+
+}  // namespace pvio

@@ -352,7 +352,7 @@ __device__ inline bool chol_solve_packed(double *A, double *x, int D, int *flag_
 
 constexpr int kSolveImuSlab = 15 * 30 + 16;     // raw J + r per factor
 
-__global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
+static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
     const int w = blockIdx.x;
     const WinHdr &H = a.hdr[w];
     const WinConst &wc = a.cst[w];
@@ -724,7 +724,7 @@ struct CostArgs {
     double *out;                   // [W] non-vision candidate cost
 };
 
-__global__ void aux_cost_kernel(CostArgs a) {
+static __global__ void aux_cost_kernel(CostArgs a) {
     const int w = blockIdx.x;
     const WinHdr &H = a.hdr[w];
     const WinConst &wc = a.cst[w];

@@ -1,8 +1,316 @@
-// placeholder; replaced below by the real KLT kernels
+// Pyramidal Lucas-Kanade on the GPU with OpenCV's arithmetic: replaces the
+// cv::calcOpticalFlowPyrLK call of OpenCvImage::track_keypoints
+// (pvio-extra/src/pvio/extra/opencv_image.cpp:103; pyramid from preprocess() :145).
+//
+//   pyrdown_kernel   cv::pyrDown, 5x5 [1 4 6 4 1]/16, BORDER_REFLECT_101, (s + 128) >> 8
+//   klt_track_kernel one warp per keypoint, all pyramid levels (coarse to fine) in one launch:
+//                    24x24 image patch staged in shared memory, Scharr derivatives (int16, as
+//                    calcSharrDeriv) computed from it, 21x21 window with 14-bit fixed-point
+//                    bilinear weights, exact int64 warp-shuffle reductions for the 2x2 system,
+//                    <= max_iter Newton steps with OpenCV's eps / oscillation stopping rules.
+// Compiled with -fmad=false: the float expressions must round like OpenCV's (no contraction),
+// because status flags are compared bit-exactly with cv2.
+#include <cstring>
+#include <vector>
 #include "api_internal.h"
+
 namespace pvio {
-int klt_track_impl(Handle *h, const uint8_t *, const uint8_t *, int, int, int, const float *, float *, uint8_t *, float *, int, int, int, double) {
-    return fail(h, PVIO_B200_EINVAL, "klt: not built yet");
+
+constexpr int kWin = 21;
+constexpr int kWBits = 14;
+constexpr int kKltWarps = 4;
+constexpr int kMaxLevels = 8;
+
+struct KltState {
+    int w = 0, h = 0, levels = 0, cap_pts = 0;
+    uint8_t *pyr[2] = {nullptr, nullptr};     // both pyramids, levels packed back to back
+    size_t off[kMaxLevels + 1];
+    int lw[kMaxLevels], lh[kMaxLevels];
+    float *d_prev = nullptr, *d_next = nullptr, *d_err = nullptr;
+    uint8_t *d_status = nullptr;
+    uint8_t *h_img = nullptr;                 // pinned staging for both level-0 images
+    float *h_pts = nullptr;                   // pinned: prev | next | err
+    uint8_t *h_status = nullptr;
+};
+
+struct KltLevels {
+    const uint8_t *I[kMaxLevels];
+    const uint8_t *J[kMaxLevels];
+    int w[kMaxLevels], h[kMaxLevels];
+    int n;
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * (n - 1) - i : i;
 }
-void klt_free(Handle *) {}
+
+__global__ void pyrdown_kernel(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const int k[5] = {1, 4, 6, 4, 1};
+    int acc = 0;
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy) {
+        const uint8_t *row = src + (size_t)reflect101(2 * y + dy, sh) * sw;
+        int r = 0;
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) r += k[dx + 2] * row[reflect101(2 * x + dx, sw)];
+        acc += k[dy + 2] * r;
+    }
+    dst[(size_t)y * dw + x] = (uint8_t)((acc + 128) >> 8);
 }
+
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void bilinear_weights(float a, float b, int &w00, int &w01, int &w10, int &w11) {
+    const float s = (float)(1 << kWBits);
+    w00 = __float2int_rn((1.f - a) * (1.f - b) * s);     // cvRound
+    w01 = __float2int_rn(a * (1.f - b) * s);
+    w10 = __float2int_rn((1.f - a) * b * s);
+    w11 = (1 << kWBits) - w00 - w01 - w10;
+}
+
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+__global__ void __launch_bounds__(32 * kKltWarps)
+klt_track_kernel(KltLevels L, const float *prev_pts, float *next_pts, uint8_t *status, float *err, int n_points,
+                 int max_iter, double eps2, float min_eig_thr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pt = blockIdx.x * kKltWarps + warp;
+    __shared__ int Ipatch[kKltWarps][24 * 24];
+    __shared__ short Dpatch[kKltWarps][22 * 22 * 2];
+    __shared__ short IWin[kKltWarps][kWin * kWin];
+    __shared__ short dIWin[kKltWarps][kWin * kWin * 2];
+    if (pt >= n_points) return;
+    const float px0 = prev_pts[2 * pt], py0 = prev_pts[2 * pt + 1];
+    float nx = next_pts[2 * pt], ny = next_pts[2 * pt + 1];      // OPTFLOW_USE_INITIAL_FLOW
+    bool st = true;
+    float err_out = 0.f;
+    const float half = (kWin - 1) * 0.5f;
+    int *Ip = Ipatch[warp];
+    short *Dp = Dpatch[warp], *Iw = IWin[warp], *dIw = dIWin[warp];
+
+    for (int level = L.n - 1; level >= 0; --level) {
+        const uint8_t *I = L.I[level], *J = L.J[level];
+        const int cols = L.w[level], rows = L.h[level];
+        const float sc = (float)(1. / (1 << level));
+        float ppx = px0 * sc, ppy = py0 * sc;
+        if (level == L.n - 1) { nx = nx * sc; ny = ny * sc; } else { nx = nx * 2.f; ny = ny * 2.f; }
+        ppx -= half; ppy -= half;
+        const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
+        if (ipx < -kWin || ipx >= cols || ipy < -kWin || ipy >= rows) {
+            if (level == 0) { st = false; err_out = 0.f; }
+            continue;
+        }
+        int w00, w01, w10, w11;
+        bilinear_weights(ppx - (float)ipx, ppy - (float)ipy, w00, w01, w10, w11);
+        // stage the 24x24 neighbourhood (REFLECT_101 outside the image: pyrBorder)
+        for (int e = lane; e < 24 * 24; e += 32) {
+            const int yy = e / 24, xx = e - yy * 24;
+            Ip[e] = I[(size_t)reflect101(ipy - 1 + yy, rows) * cols + reflect101(ipx - 1 + xx, cols)];
+        }
+        __syncwarp();
+        // Scharr derivatives on the 22x22 interior; zero outside the image (derivBorder = CONSTANT)
+        for (int e = lane; e < 22 * 22; e += 32) {
+            const int yy = e / 22, xx = e - yy * 22;
+            const int gx = ipx + xx, gy = ipy + yy;
+            int dx = 0, dy = 0;
+            if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+                const int *c = Ip + (yy + 1) * 24 + (xx + 1);
+                // neighbours must reflect about the IMAGE edge; the staged patch did exactly that
+                const int a00 = c[-25], a01 = c[-24], a02 = c[-23], a10 = c[-1], a12 = c[1], a20 = c[23], a21 = c[24], a22 = c[25];
+                dx = 3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20);
+                dy = 3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02);
+            }
+            Dp[2 * e] = (short)dx; Dp[2 * e + 1] = (short)dy;
+        }
+        __syncwarp();
+        long long sA11 = 0, sA12 = 0, sA22 = 0;
+        for (int e = lane; e < kWin * kWin; e += 32) {
+            const int yy = e / kWin, xx = e - yy * kWin;
+            const int *c = Ip + (yy + 1) * 24 + (xx + 1);
+            const int ival = descale(c[0] * w00 + c[1] * w01 + c[24] * w10 + c[25] * w11, kWBits - 5);
+            const short *d = Dp + 2 * (yy * 22 + xx);
+            const int ixv = descale(d[0] * w00 + d[2] * w01 + d[44] * w10 + d[46] * w11, kWBits);
+            const int iyv = descale(d[1] * w00 + d[3] * w01 + d[45] * w10 + d[47] * w11, kWBits);
+            Iw[e] = (short)ival; dIw[2 * e] = (short)ixv; dIw[2 * e + 1] = (short)iyv;
+            sA11 += (long long)ixv * ixv; sA12 += (long long)ixv * iyv; sA22 += (long long)iyv * iyv;
+        }
+        sA11 = warp_sum(sA11); sA12 = warp_sum(sA12); sA22 = warp_sum(sA22);
+        __syncwarp();
+        const float FLT_SCALE = 1.f / (1 << 20);
+        const float A11 = (float)sA11 * FLT_SCALE, A12 = (float)sA12 * FLT_SCALE, A22 = (float)sA22 * FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        const float min_eig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * kWin * kWin);
+        if (min_eig < min_eig_thr || D < 1.1920929e-07f) {
+            if (level == 0) st = false;
+            continue;
+        }
+        D = 1.f / D;
+        nx -= half; ny -= half;
+        float pdx = 0.f, pdy = 0.f;
+        float outx = nx + half, outy = ny + half;
+        for (int j = 0; j < max_iter; ++j) {
+            const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+            if (inx < -kWin || inx >= cols || iny < -kWin || iny >= rows) {
+                if (level == 0) st = false;
+                break;
+            }
+            bilinear_weights(nx - (float)inx, ny - (float)iny, w00, w01, w10, w11);
+            long long sb1 = 0, sb2 = 0;
+            for (int e = lane; e < kWin * kWin; e += 32) {
+                const int yy = e / kWin, xx = e - yy * kWin;
+                const int y0 = reflect101(iny + yy, rows), y1 = reflect101(iny + yy + 1, rows);
+                const int x0 = reflect101(inx + xx, cols), x1 = reflect101(inx + xx + 1, cols);
+                const int v = J[(size_t)y0 * cols + x0] * w00 + J[(size_t)y0 * cols + x1] * w01 +
+                              J[(size_t)y1 * cols + x0] * w10 + J[(size_t)y1 * cols + x1] * w11;
+                const int diff = descale(v, kWBits - 5) - Iw[e];
+                sb1 += (long long)diff * dIw[2 * e]; sb2 += (long long)diff * dIw[2 * e + 1];
+            }
+            sb1 = warp_sum(sb1); sb2 = warp_sum(sb2);
+            const float b1 = (float)sb1 * FLT_SCALE, b2 = (float)sb2 * FLT_SCALE;
+            const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
+            nx += dx; ny += dy;
+            outx = nx + half; outy = ny + half;
+            if ((double)dx * dx + (double)dy * dy <= eps2) break;
+            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+                outx -= dx * 0.5f; outy -= dy * 0.5f;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        nx = outx; ny = outy;
+        if (st && level == 0) {
+            const float qx = nx - half, qy = ny - half;
+            const int inx = (int)floorf(qx), iny = (int)floorf(qy);
+            if (inx < -kWin || inx >= cols || iny < -kWin || iny >= rows) {
+                st = false;
+            } else {
+                bilinear_weights(qx - (float)inx, qy - (float)iny, w00, w01, w10, w11);
+                long long se = 0;
+                for (int e = lane; e < kWin * kWin; e += 32) {
+                    const int yy = e / kWin, xx = e - yy * kWin;
+                    const int y0 = reflect101(iny + yy, rows), y1 = reflect101(iny + yy + 1, rows);
+                    const int x0 = reflect101(inx + xx, cols), x1 = reflect101(inx + xx + 1, cols);
+                    const int v = J[(size_t)y0 * cols + x0] * w00 + J[(size_t)y0 * cols + x1] * w01 +
+                                  J[(size_t)y1 * cols + x0] * w10 + J[(size_t)y1 * cols + x1] * w11;
+                    const int diff = descale(v, kWBits - 5) - Iw[e];
+                    se += diff < 0 ? -diff : diff;
+                }
+                se = warp_sum(se);
+                err_out = (float)se * 1.f / (float)(32 * kWin * kWin);
+            }
+        }
+    }
+    if (lane == 0) {
+        next_pts[2 * pt] = nx; next_pts[2 * pt + 1] = ny;
+        status[pt] = st ? 1 : 0;
+        if (err) err[pt] = st ? err_out : 0.f;
+    }
+}
+
+void klt_free(Handle *h) {
+    KltState *k = h->klt;
+    if (!k) return;
+    for (int i = 0; i < 2; ++i) if (k->pyr[i]) cudaFree(k->pyr[i]);
+    if (k->d_prev) cudaFree(k->d_prev);
+    if (k->d_next) cudaFree(k->d_next);
+    if (k->d_err) cudaFree(k->d_err);
+    if (k->d_status) cudaFree(k->d_status);
+    if (k->h_img) cudaFreeHost(k->h_img);
+    if (k->h_pts) cudaFreeHost(k->h_pts);
+    if (k->h_status) cudaFreeHost(k->h_status);
+    delete k;
+    h->klt = nullptr;
+}
+
+static int klt_prepare(Handle *h, int w, int hgt, int max_level, int n_points) {
+    KltState *k = h->klt;
+    if (k && (k->w != w || k->h != hgt || k->levels != max_level + 1 || k->cap_pts < n_points)) { klt_free(h); k = nullptr; }
+    if (k) return 0;
+    k = new KltState();
+    h->klt = k;
+    k->w = w; k->h = hgt; k->levels = max_level + 1; k->cap_pts = std::max(n_points, 1024);
+    size_t off = 0;
+    int lw = w, lh = hgt;
+    for (int l = 0; l <= max_level; ++l) {
+        k->lw[l] = lw; k->lh[l] = lh; k->off[l] = off;
+        off += ((size_t)lw * lh + 255) & ~(size_t)255;
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+    }
+    k->off[max_level + 1] = off;
+    for (int i = 0; i < 2; ++i) CK(h, cudaMalloc(&k->pyr[i], off));
+    CK(h, cudaMalloc(&k->d_prev, sizeof(float) * 2 * k->cap_pts));
+    CK(h, cudaMalloc(&k->d_next, sizeof(float) * 2 * k->cap_pts));
+    CK(h, cudaMalloc(&k->d_err, sizeof(float) * k->cap_pts));
+    CK(h, cudaMalloc(&k->d_status, k->cap_pts));
+    CK(h, cudaMallocHost(&k->h_img, (size_t)2 * w * hgt));
+    CK(h, cudaMallocHost(&k->h_pts, sizeof(float) * 5 * k->cap_pts));
+    CK(h, cudaMallocHost(&k->h_status, k->cap_pts));
+    return 0;
+}
+
+int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int width, int height, int stride,
+                   const float *prev_pts, float *next_pts, uint8_t *status, float *err, int n_points,
+                   int max_level, int max_iter, double eps) {
+    if (width < 2 || height < 2 || stride < width || n_points < 0 || max_level < 0 || max_level >= kMaxLevels)
+        return fail(h, PVIO_B200_EINVAL, "klt: bad arguments");
+    if (n_points == 0) return 0;
+    // buildOpticalFlowPyramid stops adding levels once a level is not larger than the window
+    int levels = 1, lw = width, lh = height;
+    while (levels <= max_level) {
+        if (lw <= kWin || lh <= kWin) break;
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+        ++levels;
+    }
+    if (levels - 1 < max_level) max_level = levels - 1;
+    int rc = klt_prepare(h, width, height, max_level, n_points);
+    if (rc != 0) return rc;
+    KltState *k = h->klt;
+    const size_t img_bytes = (size_t)width * height;
+    for (int y = 0; y < height; ++y) {
+        memcpy(k->h_img + (size_t)y * width, prev + (size_t)y * stride, width);
+        memcpy(k->h_img + img_bytes + (size_t)y * width, next + (size_t)y * stride, width);
+    }
+    memcpy(k->h_pts, prev_pts, sizeof(float) * 2 * n_points);
+    memcpy(k->h_pts + 2 * k->cap_pts, next_pts, sizeof(float) * 2 * n_points);
+    CK(h, cudaMemcpyAsync(k->pyr[0], k->h_img, img_bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(k->pyr[1], k->h_img + img_bytes, img_bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(k->d_prev, k->h_pts, sizeof(float) * 2 * n_points, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(k->d_next, k->h_pts + 2 * k->cap_pts, sizeof(float) * 2 * n_points, cudaMemcpyHostToDevice, h->stream));
+    KltLevels L;
+    L.n = max_level + 1;
+    for (int l = 0; l <= max_level; ++l) {
+        L.I[l] = k->pyr[0] + k->off[l]; L.J[l] = k->pyr[1] + k->off[l];
+        L.w[l] = k->lw[l]; L.h[l] = k->lh[l];
+    }
+    for (int l = 1; l <= max_level; ++l) {
+        dim3 b(32, 8), g((k->lw[l] + 31) / 32, (k->lh[l] + 7) / 8);
+        for (int i = 0; i < 2; ++i) {
+            pyrdown_kernel<<<g, b, 0, h->stream>>>(k->pyr[i] + k->off[l - 1], k->lw[l - 1], k->lh[l - 1],
+                                                  k->pyr[i] + k->off[l], k->lw[l], k->lh[l]);
+            ++h->launches;
+        }
+    }
+    const int mi = std::min(std::max(max_iter, 0), 100);
+    const double e = std::min(std::max(eps, 0.0), 10.0);
+    klt_track_kernel<<<(n_points + kKltWarps - 1) / kKltWarps, 32 * kKltWarps, 0, h->stream>>>(
+        L, k->d_prev, k->d_next, k->d_status, k->d_err, n_points, mi, e * e, 1e-4f);
+    ++h->launches;
+    CK(h, cudaMemcpyAsync(k->h_pts + 2 * k->cap_pts, k->d_next, sizeof(float) * 2 * n_points, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(k->h_pts + 4 * k->cap_pts, k->d_err, sizeof(float) * n_points, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(k->h_status, k->d_status, n_points, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    memcpy(next_pts, k->h_pts + 2 * k->cap_pts, sizeof(float) * 2 * n_points);
+    if (err) memcpy(err, k->h_pts + 4 * k->cap_pts, sizeof(float) * n_points);
+    memcpy(status, k->h_status, n_points);
+    return 0;
+}
+
+}  // namespace pvio

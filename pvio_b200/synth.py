@@ -314,3 +314,57 @@ def make_cfg3(seed=649, N=9, M=300, cal=EUROC, planes=0, tracks_per_plane=40, pr
 
 def make_cfg4(seed=650, **kw):
     return make_cfg3(seed=seed, cal=TUMVI, planes=2, **kw)
+
+
+# ----------------------------------------------------------------------------- KLT inputs
+def _texture(rng, w, h):
+    """Band-limited noise (sum of octaves), 8-bit, with good corners everywhere."""
+    acc = np.zeros((h, w))
+    for octave, amp in ((4, 1.0), (8, 0.8), (16, 0.6), (32, 0.4)):
+        gh, gw = h // octave + 3, w // octave + 3
+        g = rng.normal(0, 1, (gh, gw))
+        ys, xs = np.arange(h) / octave + 1, np.arange(w) / octave + 1
+        y0, x0 = ys.astype(int), xs.astype(int)
+        fy, fx = (ys - y0)[:, None], (xs - x0)[None, :]
+        acc += amp * ((1 - fy) * (1 - fx) * g[y0][:, x0] + (1 - fy) * fx * g[y0][:, x0 + 1]
+                      + fy * (1 - fx) * g[y0 + 1][:, x0] + fy * fx * g[y0 + 1][:, x0 + 1])
+    acc = (acc - acc.min()) / (acc.max() - acc.min())
+    return acc
+
+
+def make_klt_pair(seed=648, size=(752, 480), n_points=500, max_shift=8.0):
+    """Two 8-bit frames related by a small homography (<= max_shift px), points on a jittered
+    25-px grid >= 30 px from the border, initial guess = previous position (SURVEY.md 8d KLT row).
+    Returns prev, next (uint8 [h,w]), pts (float32 [n,2]), true next positions."""
+    rng = np.random.default_rng(seed)
+    w, h = size
+    tex = _texture(rng, w + 64, h + 64)
+    prev = tex[32:32 + h, 32:32 + w]
+    # homography close to identity (in pixel coordinates centred on the image)
+    ang = np.deg2rad(rng.uniform(-0.6, 0.6))
+    sc = 1.0 + rng.uniform(-0.008, 0.008)
+    Hm = np.array([[sc * np.cos(ang), -sc * np.sin(ang), rng.uniform(-0.5, 0.5) * max_shift],
+                   [sc * np.sin(ang), sc * np.cos(ang), rng.uniform(-0.5, 0.5) * max_shift],
+                   [rng.uniform(-2e-6, 2e-6), rng.uniform(-2e-6, 2e-6), 1.0]])
+    cx, cy = w / 2.0, h / 2.0
+
+    def warp_pts(p):
+        q = np.stack([p[:, 0] - cx, p[:, 1] - cy, np.ones(len(p))], axis=1) @ Hm.T
+        return np.stack([q[:, 0] / q[:, 2] + cx, q[:, 1] / q[:, 2] + cy], axis=1)
+    # next(x') = prev(H^-1 x'): sample the texture with bilinear interpolation
+    Hi = np.linalg.inv(Hm)
+    yy, xx = np.mgrid[0:h, 0:w]
+    q = np.stack([xx.ravel() - cx, yy.ravel() - cy, np.ones(w * h)], axis=1) @ Hi.T
+    sx, sy = q[:, 0] / q[:, 2] + cx + 32, q[:, 1] / q[:, 2] + cy + 32
+    x0, y0 = np.floor(sx).astype(int), np.floor(sy).astype(int)
+    fx, fy = sx - x0, sy - y0
+    x0, y0 = np.clip(x0, 0, w + 62), np.clip(y0, 0, h + 62)
+    nxt = ((1 - fy) * (1 - fx) * tex[y0, x0] + (1 - fy) * fx * tex[y0, x0 + 1]
+           + fy * (1 - fx) * tex[y0 + 1, x0] + fy * fx * tex[y0 + 1, x0 + 1]).reshape(h, w)
+    to_u8 = lambda a: np.clip(np.rint(a * 235.0 + 10.0 + rng.normal(0, 1.0, a.shape)), 0, 255).astype(np.uint8)
+    prev8, next8 = to_u8(prev), to_u8(nxt)
+    gx, gy = np.meshgrid(np.arange(35, w - 35, 25.0), np.arange(35, h - 35, 25.0))
+    pts = np.stack([gx.ravel(), gy.ravel()], axis=1) + rng.uniform(-6, 6, (gx.size, 2))
+    sel = rng.permutation(len(pts))[:n_points]
+    pts = pts[np.sort(sel)].astype(np.float32)
+    return prev8, next8, pts, warp_pts(pts.astype(np.float64)).astype(np.float32)

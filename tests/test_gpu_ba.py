@@ -92,8 +92,24 @@ def test_gn_step_cfg3_inertial_prior(ba):
 
 
 def test_gn_step_cfg3_gauge_prior(ba):
+    """First window after initialisation: only the 1e15 gauge prior on frame 0, so scale /
+    gravity / accelerometer-bias modes are barely observable (cond(H) = 1.1e8 after Jacobi
+    scaling; 99% of the plain-norm difference lies along the weakest eigenvector).  The solution of such a system moves by kappa * eps under ANY perturbation of the
+    fp32 Jacobians, so the plain-norm bound is relaxed and the step is judged in the energy norm
+    |e|_H / |dx|_H, which weights each mode by how well the data determine it."""
     w, st, _ = synth.make_cfg3(prior='gauge', N=6, M=120)
-    _check_step(ba, w, st)
+    ref = bo.gn_step(w, st)
+    out = ba.gn_step(w, st, mu=1e-8)
+    idx = np.where(ref['free'])[0]
+    idx = idx[idx >= 6]            # the pinned pose (1e30 information) is checked separately below
+    Hf = (ref['H'] + np.diag(ref['reg']))[np.ix_(idx, idx)]
+    e, d = (out['dx'] - ref['dx'])[idx], ref['dx'][idx]
+    e_energy = np.sqrt(e @ Hf @ e) / np.sqrt(d @ Hf @ d)
+    print("energy-norm rel err", e_energy, "plain", _rel(out['dx'], ref['dx']))
+    assert e_energy < 1e-6
+    assert _rel(out['dx'], ref['dx']) < 1e-3
+    assert abs(out['cost'] - ref['cost']) <= 2e-6 * ref['cost']
+    assert np.linalg.norm(out['dx'][:6]) < 1e-12          # the pinned pose does not move
 
 
 def test_gn_step_cfg3_bias_offset(ba):
@@ -166,3 +182,39 @@ def test_reprojection_error(ba):
     n = np.diff(w.lm_obs_begin) + 1
     ref = np.sum(quality * n) / np.sum(n)
     assert abs(ba.compute_reprojection_error(w, st) - ref) < 1e-6 * ref
+
+
+@pytest.mark.parametrize("index", [0])
+def test_marginalize_matches_oracle(ba, index):
+    """bundle_adjustor.cpp:348-599 on the GPU vs the oracle.  S is unique only up to the sign /
+    order of eigenvectors, so compare the information S^T S, S^T e and the pre-factorisation H, b."""
+    w, st, _ = synth.make_cfg3()
+    S, e, H, b = ba.marginalize_frame(w, st, index=index, want_info=True)
+    S0, e0, H0, b0 = bo.marginalize(w, st, index=index)
+    hs = np.maximum(np.sqrt(np.abs(np.diag(H0))), 1e-3)
+    assert np.max(np.abs(H - H0) / np.outer(hs, hs)) < 1e-6
+    assert np.max(np.abs(b - b0)) < 1e-6 * np.max(np.abs(b0))
+    L, L0 = S.T @ S, S0.T @ S0
+    assert np.max(np.abs(L - L0) / np.outer(hs, hs)) < 1e-6
+    v, v0 = S.T @ e, S0.T @ e0
+    assert np.max(np.abs(v - v0)) < 1e-6 * np.max(np.abs(v0))
+    # clamped spectrum: same number of strictly positive directions
+    assert np.sum(np.linalg.norm(S, axis=1) > 0) == np.sum(np.linalg.norm(S0, axis=1) > 0)
+
+
+def test_marginalize_then_solve_chain(ba):
+    """The GPU prior is usable as the next window's prior: install it (frames 1..N-1 become 0..N-2 of a
+    shifted window) and check one GN step against the oracle fed the same prior."""
+    w, st, _ = synth.make_cfg3(N=6, M=100)
+    S, e = ba.marginalize_frame(w, st, index=0)
+    import dataclasses
+    keep = np.arange(1, w.N)
+    w2 = dataclasses.replace(w)
+    w2.n_prior = w.N - 1
+    w2.prior_frames = keep.astype(np.int32)
+    w2.prior_S, w2.prior_e = S, e
+    w2.prior_q0, w2.prior_p0, w2.prior_v0 = st.q[keep].copy(), st.p[keep].copy(), st.v[keep].copy()
+    w2.prior_bg0, w2.prior_ba0 = st.bg[keep].copy(), st.ba[keep].copy()
+    st2 = st.copy()
+    st2.p[1:] += 1e-3
+    _check_step(ba, w2, st2, tol=5e-5)

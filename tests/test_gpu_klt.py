@@ -1,0 +1,58 @@
+"""GPU KLT parity: pvio_b200_klt_track vs (a) committed golden vectors produced by the reference's
+KLT implementation (cv2) and (b) cv2 / the NumPy oracle on seeded pairs.  Status flags (track
+indices) must be bit-exact; positions within 1e-2 px (OpenCV accumulates the 2x2 system in
+float SIMD order, the kernel in exact integers)."""
+import os
+import numpy as np
+import pytest
+
+from oracle import klt_oracle as ko
+from pvio_b200 import synth, klt
+from pvio_b200.bundle_adjustor import BundleAdjustor
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "klt_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def ba():
+    b = BundleAdjustor(max_windows=1, max_frames=4, max_landmarks=16, max_obs=64)
+    yield b
+    b.close()
+
+
+def test_klt_golden(ba):
+    g = np.load(GOLD)
+    nxt, st, err = klt.track_keypoints(ba, g["prev"], g["next"], g["pts"], g["init"], raw=True)
+    assert np.array_equal(st, g["cv_status"])
+    ok = st == 1
+    assert np.max(np.abs(nxt[ok] - g["cv_next"][ok])) < 1e-2
+    assert np.max(np.abs(err[ok] - g["cv_err"][ok])) < 1e-2
+
+
+@pytest.mark.parametrize("size,n", [((320, 240), 70), ((752, 480), 500)])
+def test_klt_vs_oracle_and_cv2(ba, size, n):
+    prev, nxt_img, pts, truth = synth.make_klt_pair(size=size, n_points=n)
+    nxt, st, err = klt.track_keypoints(ba, prev, nxt_img, pts, raw=True)
+    if n <= 100:
+        p_or, st_or, err_or = ko.calc_optical_flow_pyr_lk(prev, nxt_img, pts, pts)
+        assert np.array_equal(st, st_or)
+        assert np.max(np.abs(nxt[st == 1] - p_or[st == 1])) < 2e-3
+    cv2 = pytest.importorskip("cv2")
+    p1, s1, e1 = cv2.calcOpticalFlowPyrLK(prev, nxt_img, pts.reshape(-1, 1, 2).copy(), pts.reshape(-1, 1, 2).copy(),
+                                          winSize=(21, 21), maxLevel=3,
+                                          criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01),
+                                          flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+    assert np.array_equal(st, s1.ravel())
+    ok = st == 1
+    assert np.max(np.abs(nxt[ok] - p1.reshape(-1, 2)[ok])) < 1e-2
+    assert np.median(np.linalg.norm(nxt[ok] - truth[ok], axis=1)) < 0.1
+
+
+def test_klt_border_rule_and_empty(ba):
+    prev, nxt_img, pts, _ = synth.make_klt_pair(size=(320, 240), n_points=30)
+    pts = np.concatenate([pts, np.array([[10.0, 100.0]], dtype=np.float32)])
+    nxt, st, _ = klt.track_keypoints(ba, prev, nxt_img, pts)
+    assert st[-1] == 0                      # inside 20 px of the border: opencv_image.cpp:106
+    nxt0, st0, _ = klt.track_keypoints(ba, prev, nxt_img, np.zeros((0, 2), dtype=np.float32))
+    assert len(nxt0) == 0 and len(st0) == 0
