@@ -372,9 +372,15 @@ static int run_linearize(Handle *h, int n, const StepCfg &c) {
     a.Hred = h->Hred.d; a.Hdd = h->Hdd.d; a.gdir = h->gdir.d; a.gred = h->gred.d; a.cost_vis = h->cost_vis.d;
     a.Ncap = h->Ncap; a.Mcap = h->Mcap; a.Kcap = h->Kcap;
     a.compute_scale = c.compute_scale; a.victim_only = 0; a.mu_override = c.mu;
-    CK(h, cudaEventRecord(h->evk0, h->stream));
+    const int slot = (h->kev_count % 512) * 2;
+    if (h->kev.empty()) {
+        h->kev.resize(1024);
+        for (auto &e : h->kev) CK(h, cudaEventCreate(&e));
+    }
+    CK(h, cudaEventRecord(h->kev[slot], h->stream));
     lin_schur_kernel<true><<<dim3(gx, n), kLinThreads, lin_smem_bytes(), h->stream>>>(a);
-    CK(h, cudaEventRecord(h->evk1, h->stream));
+    CK(h, cudaEventRecord(h->kev[slot + 1], h->stream));
+    ++h->kev_count;
     ++h->launches;
     CK(h, cudaGetLastError());
     return 0;
@@ -523,6 +529,7 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     release(h->imu_idx); release(h->imu_data); release(h->prior_frames); release(h->prior_S); release(h->prior_L);
     release(h->prior_e); release(h->prior_x0);
     release(h->plane_param); release(h->pt_plane); release(h->pt_begin); release(h->pt_frame); release(h->pt_z);
+    for (auto &e : h->kev) cudaEventDestroy(e);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evk0); cudaEventDestroy(h->evk1);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -558,11 +565,22 @@ int pvio_b200_timer_stop(pvio_b200_handle hh, float *ms) {
     return 0;
 }
 
+// which = 0: duration of the most recent linearise+Schur launch; which = 1: MEAN duration over the
+// launches since the last reset (at most the latest 512); which = -1: reset the accumulation.
 int pvio_b200_last_kernel_ms(pvio_b200_handle hh, int which, float *ms) {
     Handle *h = reinterpret_cast<Handle *>(hh);
-    (void)which;
-    CK(h, cudaEventSynchronize(h->evk1));
-    CK(h, cudaEventElapsedTime(ms, h->evk0, h->evk1));
+    if (which < 0) { h->kev_count = 0; if (ms) *ms = 0.f; return 0; }
+    if (h->kev_count == 0) return fail(h, PVIO_B200_EINVAL, "no linearise launch recorded");
+    CK(h, cudaStreamSynchronize(h->stream));
+    const int n = which == 0 ? 1 : std::min(h->kev_count, 512);
+    double tot = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int slot = ((h->kev_count - 1 - i) % 512) * 2;
+        float t = 0.f;
+        CK(h, cudaEventElapsedTime(&t, h->kev[slot], h->kev[slot + 1]));
+        tot += t;
+    }
+    *ms = (float)(tot / n);
     return 0;
 }
 

@@ -52,6 +52,9 @@ struct Handle {
     std::vector<int> slot_M, slot_N, slot_K;
     int n_uploaded = 0;
     float last_lin_ms = 0.f;
+    // ring of event pairs around every linearise+Schur launch (roofline timing without host syncs)
+    std::vector<cudaEvent_t> kev;
+    int kev_count = 0;
     KltState *klt = nullptr;
 };
 

@@ -161,3 +161,18 @@ def test_solve_converges_and_gauge_prior_holds_frame0():
     assert summ['usable'] and summ['final_cost'] < summ['initial_cost']
     assert np.linalg.norm(s.p[0] - st.p[0]) < 1e-9      # 1e15 sqrt-information pins the pose
     assert summ['final_cost'] < bo.total_cost(w, truth)   # the optimum fits the noise
+
+
+def test_c_restatement_matches_numpy_oracle():
+    """oracle/ba_oracle.c (the timed CPU baseline) against oracle/ba_oracle.py."""
+    from oracle import c_oracle
+    for kw in (dict(N=5, M=40), dict(N=7, M=90, staggered=True)):
+        w, st, _ = synth.make_cfg2(**kw)
+        ref = bo.gn_step(w, st, schur=True)
+        out = c_oracle.gn_step(w, st)
+        assert np.linalg.norm(out['dx'] - ref['dx']) < 1e-9 * np.linalg.norm(ref['dx'])
+        assert abs(out['cost'] - ref['cost']) < 1e-10 * ref['cost']
+        cand = bo.total_cost(w, bo.apply_step(w, st, ref['dx']))
+        assert abs(out['new_cost'] - cand) < 1e-8 * cand
+    dxb, costs, used = c_oracle.gn_step_batch(w, st, 4, n_threads=2)
+    assert used == 2 and np.allclose(dxb, out['dx'][None, :], rtol=0, atol=0)
