@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include "api_internal.h"
@@ -75,8 +76,8 @@ static int ensure_planes(Handle *h, int T, int O) {
 // ------------------------------------------------------------------------ small kernels
 __global__ void finalize_kernel(WinCtrl *ctrl, const double *acc, const double *aux_cost, int apply,
                                 double *frames, const double *frames_cand, double *rho, const double *rho_cand,
-                                const WinHdr *hdr, int Ncap, int Mcap, double beta) {
-    const int w = blockIdx.x;
+                                const WinHdr *hdr, int Ncap, int Mcap, double beta, int w0) {
+    const int w = blockIdx.x + w0;
     WinCtrl &c = ctrl[w];
     const double *a = acc + (size_t)w * 8;
     if (threadIdx.x == 0) {
@@ -97,8 +98,8 @@ __global__ void finalize_kernel(WinCtrl *ctrl, const double *acc, const double *
 }
 
 // Lambda = S^T S of the marginalisation prior (once per solve; constant across iterations)
-__global__ void prior_lambda_kernel(const WinHdr *hdr, const double *S, double *L, int Ncap) {
-    const int w = blockIdx.x;
+__global__ void prior_lambda_kernel(const WinHdr *hdr, const double *S, double *L, int Ncap, int w0) {
+    const int w = blockIdx.x + w0;
     const int d = 15 * hdr[w].n_prior, dcap = 15 * Ncap;
     const double *Sw = S + (size_t)w * dcap * dcap;
     double *Lw = L + (size_t)w * dcap * dcap;
@@ -240,6 +241,7 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
     }
     H.n_chunks = nch;
     h->slot_M[slot] = M; h->slot_N[slot] = N; h->slot_K[slot] = K;
+    h->perm_identity[slot] = sorted ? 1 : 0;
     // inertial part
     H.n_imu = w->use_inertial ? w->n_imu : 0;
     H.n_prior = w->use_inertial ? w->n_prior : 0;
@@ -276,43 +278,49 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
 }
 
 template <typename T>
-static int h2d(Handle *h, DevBuf<T> &b, size_t per, int n) {
+static int h2d(Handle *h, DevBuf<T> &b, size_t per, int w0, int n, cudaStream_t st) {
     if (!b.d || !b.h || per == 0) return 0;
-    CK(h, cudaMemcpyAsync(b.d, b.h, per * n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(b.d + per * w0, b.h + per * w0, per * n * sizeof(T), cudaMemcpyHostToDevice, st));
     return 0;
 }
 
-static int upload(Handle *h, int n) {
-    if (n < 1 || n > h->W) return fail(h, PVIO_B200_EINVAL, "bad window count");
+// Host -> device copy of windows [w0, w0 + n) on stream st
+static int upload_range(Handle *h, int w0, int n, cudaStream_t st) {
+    if (n < 1 || w0 < 0 || w0 + n > h->W) return fail(h, PVIO_B200_EINVAL, "bad window range");
     const size_t N = h->Ncap;
-    TRY(h2d(h, h->hdr, 1, n));
-    TRY(h2d(h, h->cst, 1, n));
-    TRY(h2d(h, h->obs, h->Kcap, n));
-    TRY(h2d(h, h->lms, h->Mcap, n));
-    TRY(h2d(h, h->rho, h->Mcap, n));
-    TRY(h2d(h, h->frames, N * kFrameStride, n));
+    TRY(h2d(h, h->hdr, 1, w0, n, st));
+    TRY(h2d(h, h->cst, 1, w0, n, st));
+    TRY(h2d(h, h->obs, h->Kcap, w0, n, st));
+    TRY(h2d(h, h->lms, h->Mcap, w0, n, st));
+    TRY(h2d(h, h->rho, h->Mcap, w0, n, st));
+    TRY(h2d(h, h->frames, N * kFrameStride, w0, n, st));
     bool any_prior = false;
     if (h->have_inertial) {
         const size_t dcap = 15 * N;
-        TRY(h2d(h, h->imu_idx, N * 2, n));
-        TRY(h2d(h, h->imu_data, N * kImuStride, n));
-        TRY(h2d(h, h->prior_frames, N, n));
-        TRY(h2d(h, h->prior_S, dcap * dcap, n));
-        TRY(h2d(h, h->prior_e, dcap, n));
-        TRY(h2d(h, h->prior_x0, N * kFrameStride, n));
-        for (int i = 0; i < n; ++i) any_prior |= h->hdr.h[i].n_prior > 0;
+        TRY(h2d(h, h->imu_idx, N * 2, w0, n, st));
+        TRY(h2d(h, h->imu_data, N * kImuStride, w0, n, st));
+        TRY(h2d(h, h->prior_frames, N, w0, n, st));
+        TRY(h2d(h, h->prior_S, dcap * dcap, w0, n, st));
+        TRY(h2d(h, h->prior_e, dcap, w0, n, st));
+        TRY(h2d(h, h->prior_x0, N * kFrameStride, w0, n, st));
+        for (int i = w0; i < w0 + n; ++i) any_prior |= h->hdr.h[i].n_prior > 0;
         if (any_prior) {
-            prior_lambda_kernel<<<n, 256, 0, h->stream>>>(h->hdr.d, h->prior_S.d, h->prior_L.d, h->Ncap);
+            prior_lambda_kernel<<<n, 256, 0, st>>>(h->hdr.d, h->prior_S.d, h->prior_L.d, h->Ncap, w0);
             ++h->launches;
         }
     }
     if (h->have_planes) {
-        TRY(h2d(h, h->plane_param, (size_t)h->Pcap * 4, n));
-        TRY(h2d(h, h->pt_plane, h->Tcap, n));
-        TRY(h2d(h, h->pt_begin, h->Tcap + 1, n));
-        TRY(h2d(h, h->pt_frame, h->Ocap, n));
-        TRY(h2d(h, h->pt_z, (size_t)h->Ocap * 2, n));
+        TRY(h2d(h, h->plane_param, (size_t)h->Pcap * 4, w0, n, st));
+        TRY(h2d(h, h->pt_plane, h->Tcap, w0, n, st));
+        TRY(h2d(h, h->pt_begin, h->Tcap + 1, w0, n, st));
+        TRY(h2d(h, h->pt_frame, h->Ocap, w0, n, st));
+        TRY(h2d(h, h->pt_z, (size_t)h->Ocap * 2, w0, n, st));
     }
+    return 0;
+}
+
+static int upload(Handle *h, int n) {
+    TRY(upload_range(h, 0, n, h->stream));
     h->n_uploaded = n;
     return 0;
 }
@@ -331,6 +339,8 @@ struct StepCfg {
     int alias_bias = 0;
     int dump = 0;
     bool skip_linearize = false;   // reuse the previous linearisation (trust-region retry)
+    int w0 = 0;                    // first window (sub-batch pipelining)
+    cudaStream_t stream = nullptr; // nullptr: the handle's stream
 };
 
 static int lin_grid_x(Handle *h, int n) {
@@ -340,17 +350,18 @@ static int lin_grid_x(Handle *h, int n) {
     return std::min(gx, 32);
 }
 
-static size_t solve_smem(Handle *h, int n) {
-    // worst case over the windows of the batch
+static size_t solve_smem(Handle *h, int w0, int n) {
+    // worst case over the windows of the launch
     size_t best = 0;
-    for (int i = 0; i < n; ++i) {
+    for (int i = w0; i < w0 + n; ++i) {
         const WinHdr &H = h->hdr.h[i];
         const size_t D = (H.use_inertial ? 15 : 6) * (size_t)H.N;
         const size_t np_ = (size_t)H.N * (H.N + 1) / 2;
         size_t scr = std::max<size_t>(D, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);
         if (H.use_inertial) scr = std::max<size_t>(scr, 2 * (4 * 450 + 64));
         if (H.n_prior > 0) scr = std::max<size_t>(scr, 3 * 15 * (size_t)H.n_prior + 9 * (size_t)H.n_prior);
-        const size_t bytes = sizeof(double) * (D * (D + 1) / 2 + 4 * D + kMaxFrames * 36 + scr);
+        const size_t nb = (D + 3) / 4;
+        const size_t bytes = sizeof(double) * (nb * (nb + 1) / 2 * 16 + 4 * nb * 4 + nb * 16 + kMaxFrames * 36 + scr);
         best = std::max(best, bytes);
     }
     return best;
@@ -358,28 +369,24 @@ static size_t solve_smem(Handle *h, int n) {
 
 static int run_linearize(Handle *h, int n, const StepCfg &c) {
     const int gx = lin_grid_x(h, n);
+    cudaStream_t st = c.stream ? c.stream : h->stream;
     const size_t npc = (size_t)h->Ncap * (h->Ncap + 1) / 2;
-    if (gx > 1) {
-        CK(h, cudaMemsetAsync(h->Hred.d, 0, sizeof(double) * npc * 36 * n, h->stream));
-        CK(h, cudaMemsetAsync(h->Hdd.d, 0, sizeof(double) * h->Ncap * 36 * n, h->stream));
-        CK(h, cudaMemsetAsync(h->gdir.d, 0, sizeof(double) * h->Ncap * 6 * n, h->stream));
-        CK(h, cudaMemsetAsync(h->gred.d, 0, sizeof(double) * h->Ncap * 6 * n, h->stream));
-        CK(h, cudaMemsetAsync(h->cost_vis.d, 0, sizeof(double) * n, h->stream));
-    }
+    if (gx > 1) CK(h, cudaMemsetAsync(h->Hred.d, 0, sizeof(double) * h->Hred.n, st));
+    (void)npc;
     LinArgs a;
     a.hdr = h->hdr.d; a.cst = h->cst.d; a.obs = h->obs.d; a.lms = h->lms.d; a.rho = h->rho.d; a.frames = h->frames.d;
     a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d;
     a.Hred = h->Hred.d; a.Hdd = h->Hdd.d; a.gdir = h->gdir.d; a.gred = h->gred.d; a.cost_vis = h->cost_vis.d;
     a.Ncap = h->Ncap; a.Mcap = h->Mcap; a.Kcap = h->Kcap;
-    a.compute_scale = c.compute_scale; a.victim_only = 0; a.mu_override = c.mu;
+    a.compute_scale = c.compute_scale; a.victim_only = 0; a.mu_override = c.mu; a.w0 = c.w0;
     const int slot = (h->kev_count % 512) * 2;
     if (h->kev.empty()) {
         h->kev.resize(1024);
         for (auto &e : h->kev) CK(h, cudaEventCreate(&e));
     }
-    CK(h, cudaEventRecord(h->kev[slot], h->stream));
-    lin_schur_kernel<true><<<dim3(gx, n), kLinThreads, lin_smem_bytes(), h->stream>>>(a);
-    CK(h, cudaEventRecord(h->kev[slot + 1], h->stream));
+    CK(h, cudaEventRecord(h->kev[slot], st));
+    lin_schur_kernel<true><<<dim3(gx, n), kLinThreads, lin_smem_bytes(), st>>>(a);
+    CK(h, cudaEventRecord(h->kev[slot + 1], st));
     ++h->kev_count;
     ++h->launches;
     CK(h, cudaGetLastError());
@@ -398,26 +405,42 @@ static int run_solve(Handle *h, int n, const StepCfg &c) {
     a.pt_z = h->pt_z.d; a.Pcap = h->Pcap; a.Tcap = h->Tcap; a.Ocap = h->Ocap;
     a.pose_scale = h->pose_scale.d; a.dx_pose = h->dx_pose.d;
     a.Hfull = c.dump ? h->Hfull.d : nullptr; a.gfull = c.dump ? h->gfull.d : nullptr;
-    a.Ncap = h->Ncap; a.compute_scale = c.compute_scale; a.mu_override = c.mu;
-    const size_t smem = solve_smem(h, n);
+    a.Ncap = h->Ncap; a.compute_scale = c.compute_scale; a.mu_override = c.mu; a.w0 = c.w0;
+    a.dbg = nullptr;
+    if (getenv("PVIO_B200_SOLVE_STAMPS")) {       // profiling aid: clock64 stamps of the solve kernel's phases
+        static long long *dbg = nullptr;
+        long long hst[16];
+        if (!dbg) { cudaMalloc(&dbg, 16 * sizeof(long long)); cudaMemset(dbg, 0, 16 * sizeof(long long)); }
+        else {
+            cudaStreamSynchronize(h->stream);
+            cudaMemcpy(hst, dbg, sizeof(hst), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "solve stamps (clk):");
+            for (int i = 1; i < 6; ++i) fprintf(stderr, " %lld", hst[i] - hst[i - 1]);
+            fprintf(stderr, "\n");
+        }
+        a.dbg = dbg;
+    }
+    cudaStream_t st = c.stream ? c.stream : h->stream;
+    const size_t smem = solve_smem(h, c.w0, n);
     if (smem > 220 * 1024) return fail(h, PVIO_B200_EINVAL, "reduced system too large for shared memory");
     // small systems: a narrow CTA per window (many resident per SM); large: a full CTA
     const int threads = (smem <= 24 * 1024 && n >= 64) ? 64 : 256;
-    solve_kernel<<<n, threads, smem, h->stream>>>(a);
+    solve_kernel<<<n, threads, smem, st>>>(a);
     ++h->launches;
     CK(h, cudaGetLastError());
     return 0;
 }
 
 static int run_update(Handle *h, int n, const StepCfg &c) {
-    CK(h, cudaMemsetAsync(h->acc.d, 0, sizeof(double) * 8 * n, h->stream));
+    cudaStream_t st = c.stream ? c.stream : h->stream;
+    CK(h, cudaMemsetAsync(h->acc.d + (size_t)8 * c.w0, 0, sizeof(double) * 8 * n, st));
     UpdArgs u;
     u.hdr = h->hdr.d; u.cst = h->cst.d; u.obs = h->obs.d; u.lms = h->lms.d; u.rho = h->rho.d; u.frames = h->frames.d;
     u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.dx_pose = h->dx_pose.d;
     u.rho_cand = h->rho_cand.d; u.frames_cand = h->frames_cand.d; u.dx_lm = h->dx_lm.d; u.acc = h->acc.d;
-    u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.beta = c.beta;
+    u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.beta = c.beta; u.w0 = c.w0;
     const int gx = lin_grid_x(h, n);
-    update_cost_kernel<true><<<dim3(gx, n), kLinThreads, 0, h->stream>>>(u);
+    update_cost_kernel<true><<<dim3(gx, n), kLinThreads, 0, st>>>(u);
     ++h->launches;
     CostArgs k;
     memset(&k, 0, sizeof(k));
@@ -426,10 +449,11 @@ static int run_update(Handle *h, int n, const StepCfg &c) {
     k.prior_frames = h->prior_frames.d; k.prior_S = h->prior_S.d; k.prior_e = h->prior_e.d; k.prior_x0 = h->prior_x0.d;
     k.plane_param = h->plane_param.d; k.pt_plane = h->pt_plane.d; k.pt_begin = h->pt_begin.d; k.pt_frame = h->pt_frame.d;
     k.pt_z = h->pt_z.d; k.Pcap = h->Pcap; k.Tcap = h->Tcap; k.Ocap = h->Ocap; k.Ncap = h->Ncap; k.out = h->aux_cost.d;
-    aux_cost_kernel<<<n, 64, sizeof(double) * 15 * kMaxFrames, h->stream>>>(k);
+    k.w0 = c.w0;
+    aux_cost_kernel<<<n, 64, sizeof(double) * 15 * kMaxFrames, st>>>(k);
     ++h->launches;
-    finalize_kernel<<<n, 128, 0, h->stream>>>(h->ctrl.d, h->acc.d, h->aux_cost.d, c.apply, h->frames.d, h->frames_cand.d,
-                                             h->rho.d, h->rho_cand.d, h->hdr.d, h->Ncap, h->Mcap, c.beta);
+    finalize_kernel<<<n, 128, 0, st>>>(h->ctrl.d, h->acc.d, h->aux_cost.d, c.apply, h->frames.d, h->frames_cand.d,
+                                      h->rho.d, h->rho_cand.d, h->hdr.d, h->Ncap, h->Mcap, c.beta, c.w0);
     ++h->launches;
     CK(h, cudaGetLastError());
     return 0;
@@ -444,25 +468,29 @@ static int run_step(Handle *h, int n, const StepCfg &c) {
     return 0;
 }
 
-static int download_dx(Handle *h, int n, double *dx, int64_t dx_stride, double *costs) {
-    // pinned staging reuse: dx_pose / dx_lm / ctrl have host mirrors
-    CK(h, cudaMemcpyAsync(h->dx_pose.h, h->dx_pose.d, sizeof(double) * h->Ncap * 15 * n, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaMemcpyAsync(h->dx_lm.h, h->dx_lm.d, sizeof(double) * h->Mcap * n, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaMemcpyAsync(h->ctrl.h, h->ctrl.d, sizeof(WinCtrl) * n, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < n; ++i) {
+// pinned staging -> caller arrays (landmark order un-permuted), windows [w0, w0 + n)
+static int scatter_dx(Handle *h, int w0, int n, double *dx, int64_t dx_stride, double *costs) {
+    for (int i = w0; i < w0 + n; ++i) {
         const int N = h->slot_N[i], M = h->slot_M[i];
         if (dx) {
             double *o = dx + (size_t)i * dx_stride;
             memcpy(o, h->dx_pose.h + (size_t)i * h->Ncap * 15, sizeof(double) * N * 15);
             const double *dl = h->dx_lm.h + (size_t)i * h->Mcap;
-            const std::vector<int32_t> &perm = h->perm[i];
-            for (int lp = 0; lp < M; ++lp) o[N * 15 + perm[lp]] = dl[lp];
+            if (h->perm_identity[i]) memcpy(o + N * 15, dl, sizeof(double) * M);
+            else { const std::vector<int32_t> &perm = h->perm[i]; for (int lp = 0; lp < M; ++lp) o[N * 15 + perm[lp]] = dl[lp]; }
         }
         if (costs) { costs[2 * i] = h->ctrl.h[i].cost; costs[2 * i + 1] = h->ctrl.h[i].cand_cost; }
         if (h->ctrl.h[i].solve_failed) return fail(h, PVIO_B200_ENUMERIC, "reduced system not positive definite");
     }
     return 0;
+}
+
+static int download_dx(Handle *h, int n, double *dx, int64_t dx_stride, double *costs) {
+    CK(h, cudaMemcpyAsync(h->dx_pose.h, h->dx_pose.d, sizeof(double) * h->Ncap * 15 * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(h->dx_lm.h, h->dx_lm.d, sizeof(double) * h->Mcap * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(h->ctrl.h, h->ctrl.d, sizeof(WinCtrl) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return scatter_dx(h, 0, n, dx, dx_stride, costs);
 }
 
 }  // namespace pvio
@@ -500,12 +528,18 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     TRY(alloc(h, h->lm_scale, W * M, false)); TRY(alloc(h, h->lm_aux, W * M, false));
     TRY(alloc(h, h->dx_lm, W * M, true)); TRY(alloc(h, h->dx_pose, W * N * 15, true));
     TRY(alloc(h, h->pose_scale, W * N * 15, false));
-    TRY(alloc(h, h->Hred, W * npc * 36, false)); TRY(alloc(h, h->Hdd, W * N * 36, false));
-    TRY(alloc(h, h->gdir, W * N * 6, false)); TRY(alloc(h, h->gred, W * N * 6, false));
-    TRY(alloc(h, h->cost_vis, W, false)); TRY(alloc(h, h->acc, W * 8, true)); TRY(alloc(h, h->aux_cost, W, false));
+    {   // the reduced-system outputs of the linearise kernel live in ONE allocation so that the
+        // multi-CTA-per-window mode (atomic accumulation) needs a single memset per launch
+        const size_t n_sys = W * (npc * 36 + N * 36 + N * 6 + N * 6 + 1);
+        TRY(alloc(h, h->Hred, n_sys, false));
+        h->Hdd.d = h->Hred.d + W * npc * 36; h->Hdd.n = 0;
+        h->gdir.d = h->Hdd.d + W * N * 36; h->gdir.n = 0;
+        h->gred.d = h->gdir.d + W * N * 6; h->gred.n = 0;
+        h->cost_vis.d = h->gred.d + W * N * 6; h->cost_vis.n = 0;
+    } TRY(alloc(h, h->acc, W * 8, true)); TRY(alloc(h, h->aux_cost, W, false));
     TRY(alloc(h, h->Hfull, (15 * N) * (15 * N), true)); TRY(alloc(h, h->gfull, 15 * N, true));
     // unallocated optional buffers still need valid (dummy) device pointers? kernels never touch them
-    h->perm.resize(W); h->slot_M.assign(W, 0); h->slot_N.assign(W, 0); h->slot_K.assign(W, 0);
+    h->perm.resize(W); h->perm_identity.assign(W, 1); h->slot_M.assign(W, 0); h->slot_N.assign(W, 0); h->slot_K.assign(W, 0);
     CK(h, cudaFuncSetAttribute(lin_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem_bytes()));
     CK(h, cudaFuncSetAttribute(lin_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem_bytes()));
     CK(h, cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -523,14 +557,19 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     klt_free(h);
     release(h->hdr); release(h->cst); release(h->obs); release(h->lms); release(h->rho); release(h->frames);
     release(h->ctrl); release(h->rho_cand); release(h->frames_cand); release(h->lm_scale); release(h->lm_aux);
-    release(h->dx_lm); release(h->dx_pose); release(h->pose_scale); release(h->Hred); release(h->Hdd);
-    release(h->gdir); release(h->gred); release(h->cost_vis); release(h->acc); release(h->aux_cost);
+    release(h->dx_lm); release(h->dx_pose); release(h->pose_scale); release(h->Hred);
+    release(h->acc); release(h->aux_cost);
     release(h->Hfull); release(h->gfull);
     release(h->imu_idx); release(h->imu_data); release(h->prior_frames); release(h->prior_S); release(h->prior_L);
     release(h->prior_e); release(h->prior_x0);
     release(h->plane_param); release(h->pt_plane); release(h->pt_begin); release(h->pt_frame); release(h->pt_z);
     for (auto &e : h->kev) cudaEventDestroy(e);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evk0); cudaEventDestroy(h->evk1);
+    for (auto &e : h->ev_up) cudaEventDestroy(e);
+    for (auto &e : h->ev_done) cudaEventDestroy(e);
+    for (auto &e : h->ev_down) cudaEventDestroy(e);
+    if (h->stream_up) cudaStreamDestroy(h->stream_up);
+    if (h->stream_down) cudaStreamDestroy(h->stream_down);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -600,7 +639,7 @@ int pvio_b200_batch_replicate(pvio_b200_handle hh, int n) {
         memcpy(h->lms.h + (size_t)i * h->Mcap, h->lms.h, sizeof(LmRec) * h->slot_M[0]);
         memcpy(h->rho.h + (size_t)i * h->Mcap, h->rho.h, sizeof(double) * h->slot_M[0]);
         memcpy(h->frames.h + (size_t)i * N * kFrameStride, h->frames.h, sizeof(double) * N * kFrameStride);
-        h->perm[i] = h->perm[0]; h->slot_M[i] = h->slot_M[0]; h->slot_N[i] = h->slot_N[0]; h->slot_K[i] = h->slot_K[0];
+        h->perm[i] = h->perm[0]; h->perm_identity[i] = h->perm_identity[0]; h->slot_M[i] = h->slot_M[0]; h->slot_N[i] = h->slot_N[0]; h->slot_K[i] = h->slot_K[0];
         if (h->have_inertial) {
             const size_t dcap = 15 * N;
             memcpy(h->imu_idx.h + (size_t)i * N * 2, h->imu_idx.h, sizeof(int32_t) * N * 2);
@@ -632,13 +671,61 @@ int pvio_b200_batch_download(pvio_b200_handle hh, int n, double *dx, int64_t dx_
     return download_dx(h, n, dx, dx_stride, costs);
 }
 
+// End-to-end step with HOST buffers.  Large batches are cut into sub-batches and pipelined over
+// three streams: host->device copy of sub-batch i+1 overlaps the kernels of sub-batch i and the
+// device->host copy of sub-batch i-1 (PCIe is full duplex), so the call costs
+// max(copy, compute) instead of their sum.
 int pvio_b200_batch_gn_step_host(pvio_b200_handle hh, int n, double mu, double *dx, int64_t dx_stride, double *costs) {
     Handle *h = reinterpret_cast<Handle *>(hh);
-    TRY(upload(h, n));
-    StepCfg c;
-    c.mu = mu; c.apply = 0; c.compute_scale = 1;
-    TRY(run_step(h, n, c));
-    return download_dx(h, n, dx, dx_stride, costs);
+    if (n < 1 || n > h->W) return fail(h, PVIO_B200_EINVAL, "bad window count");
+    const int sub = n >= 1024 ? 512 : n;
+    const int nsub = (n + sub - 1) / sub;
+    if (nsub == 1) {
+        TRY(upload(h, n));
+        StepCfg c;
+        c.mu = mu; c.apply = 0; c.compute_scale = 1;
+        TRY(run_step(h, n, c));
+        return download_dx(h, n, dx, dx_stride, costs);
+    }
+    if (!h->stream_up) {
+        CK(h, cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
+        CK(h, cudaStreamCreateWithFlags(&h->stream_down, cudaStreamNonBlocking));
+    }
+    while ((int)h->ev_up.size() < nsub) {
+        cudaEvent_t a, b;
+        CK(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_up.push_back(a); h->ev_done.push_back(b);
+        cudaEvent_t c_;
+        CK(h, cudaEventCreateWithFlags(&c_, cudaEventDisableTiming));
+        h->ev_down.push_back(c_);
+    }
+    for (int i = 0; i < nsub; ++i) {
+        const int w0 = i * sub, m = std::min(sub, n - w0);
+        TRY(upload_range(h, w0, m, h->stream_up));
+        CK(h, cudaEventRecord(h->ev_up[i], h->stream_up));
+        CK(h, cudaStreamWaitEvent(h->stream, h->ev_up[i], 0));
+        StepCfg c;
+        c.mu = mu; c.apply = 0; c.compute_scale = 1; c.w0 = w0;
+        TRY(run_step(h, m, c));
+        CK(h, cudaEventRecord(h->ev_done[i], h->stream));
+        CK(h, cudaStreamWaitEvent(h->stream_down, h->ev_done[i], 0));
+        CK(h, cudaMemcpyAsync(h->dx_pose.h + (size_t)w0 * h->Ncap * 15, h->dx_pose.d + (size_t)w0 * h->Ncap * 15,
+                              sizeof(double) * h->Ncap * 15 * m, cudaMemcpyDeviceToHost, h->stream_down));
+        CK(h, cudaMemcpyAsync(h->dx_lm.h + (size_t)w0 * h->Mcap, h->dx_lm.d + (size_t)w0 * h->Mcap,
+                              sizeof(double) * h->Mcap * m, cudaMemcpyDeviceToHost, h->stream_down));
+        CK(h, cudaMemcpyAsync(h->ctrl.h + w0, h->ctrl.d + w0, sizeof(WinCtrl) * m, cudaMemcpyDeviceToHost, h->stream_down));
+        CK(h, cudaEventRecord(h->ev_down[i], h->stream_down));
+    }
+    h->n_uploaded = n;
+    // scatter each sub-batch as soon as it has landed, while the GPU works on the later ones
+    for (int i = 0; i < nsub; ++i) {
+        const int w0 = i * sub, m = std::min(sub, n - w0);
+        CK(h, cudaEventSynchronize(h->ev_down[i]));
+        TRY(scatter_dx(h, w0, m, dx, dx_stride, costs));
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 int pvio_b200_ba_gn_step(pvio_b200_handle hh, const pvio_b200_window *w, const pvio_b200_state *s, double mu,
@@ -744,7 +831,7 @@ int pvio_b200_ba_solve(pvio_b200_handle hh, const pvio_b200_window *w, pvio_b200
         if (rel > 1e-3) {
             // accept: candidate becomes the state
             finalize_kernel<<<1, 128, 0, h->stream>>>(h->ctrl.d, h->acc.d, h->aux_cost.d, 1, h->frames.d, h->frames_cand.d,
-                                                     h->rho.d, h->rho_cand.d, h->hdr.d, h->Ncap, h->Mcap, beta);
+                                                     h->rho.d, h->rho_cand.d, h->hdr.d, h->Ncap, h->Mcap, beta, 0);
             ++h->launches;
             ++sm.accepted_steps;
             cost = ct.cand_cost;

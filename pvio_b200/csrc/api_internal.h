@@ -23,6 +23,8 @@ struct Handle {
     int W = 1, Ncap = 0, Mcap = 0, Kcap = 0;
     int Pcap = 4, Tcap = 0, Ocap = 0;            // planes / plane tracks / plane observations
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_up = nullptr, stream_down = nullptr;   // copy streams of the pipelined host path
+    std::vector<cudaEvent_t> ev_up, ev_done, ev_down;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     std::string err;
     int64_t launches = 0;
@@ -50,6 +52,7 @@ struct Handle {
     // host bookkeeping per slot
     std::vector<std::vector<int32_t>> perm;      // packed landmark -> caller landmark
     std::vector<int> slot_M, slot_N, slot_K;
+    std::vector<uint8_t> perm_identity;
     int n_uploaded = 0;
     float last_lin_ms = 0.f;
     // ring of event pairs around every linearise+Schur launch (roofline timing without host syncs)

@@ -187,12 +187,13 @@ struct LinArgs {
     int compute_scale;       // 1: this is iteration 0, (re)compute lm_scale
     int victim_only;         // marginaliser: only landmarks flagged in_victim
     double mu_override;      // >= 0: use this mu instead of ctrl->mu
+    int w0;                  // first window of this launch (sub-batch pipelining)
 };
 
 template <bool kLoss>
 __global__ void __launch_bounds__(kLinThreads, 2)
 lin_schur_kernel(LinArgs a) {
-    const int w = blockIdx.y;
+    const int w = blockIdx.y + a.w0;
     const WinHdr &H = a.hdr[w];
     const WinConst &wc = a.cst[w];
     const int N = H.N;

@@ -331,17 +331,14 @@ int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state
     const int n = 15 * N, dk = n - 15;
     // vision part: no loss, victim-seen landmarks only, mu = 0
     const size_t npc = (size_t)h->Ncap * (h->Ncap + 1) / 2;
-    CK(h, cudaMemsetAsync(h->Hred.d, 0, sizeof(double) * npc * 36, h->stream));
-    CK(h, cudaMemsetAsync(h->Hdd.d, 0, sizeof(double) * h->Ncap * 36, h->stream));
-    CK(h, cudaMemsetAsync(h->gdir.d, 0, sizeof(double) * h->Ncap * 6, h->stream));
-    CK(h, cudaMemsetAsync(h->gred.d, 0, sizeof(double) * h->Ncap * 6, h->stream));
-    CK(h, cudaMemsetAsync(h->cost_vis.d, 0, sizeof(double), h->stream));
+    CK(h, cudaMemsetAsync(h->Hred.d, 0, sizeof(double) * h->Hred.n, h->stream));
+    (void)npc;
     LinArgs a;
     a.hdr = h->hdr.d; a.cst = h->cst.d; a.obs = h->obs.d; a.lms = h->lms.d; a.rho = h->rho.d; a.frames = h->frames.d;
     a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d;
     a.Hred = h->Hred.d; a.Hdd = h->Hdd.d; a.gdir = h->gdir.d; a.gred = h->gred.d; a.cost_vis = h->cost_vis.d;
     a.Ncap = h->Ncap; a.Mcap = h->Mcap; a.Kcap = h->Kcap;
-    a.compute_scale = 1; a.victim_only = 1; a.mu_override = 0.0;
+    a.compute_scale = 1; a.victim_only = 1; a.mu_override = 0.0; a.w0 = 0;
     lin_schur_kernel<false><<<dim3(16, 1), kLinThreads, lin_smem_bytes(), h->stream>>>(a);
     ++h->launches;
     // dense buffers

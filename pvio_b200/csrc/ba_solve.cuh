@@ -53,14 +53,16 @@ struct SolveArgs {
     double *gfull;             // optional [W][15 Ncap]
     int Ncap;
     int compute_scale;
+    int w0;
     double mu_override;
+    long long *dbg;            // optional [16] clock64 stamps of window w0 (profiling aid)
 };
 
-__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
-
-// add v to symmetric packed-lower A at (i,j) (any order)
-__device__ __forceinline__ void sym_add(double *A, int i, int j, double v) {
-    if (i >= j) A[tri(i, j)] += v; else A[tri(j, i)] += v;
+// The dense system is stored as packed lower-triangular 4x4 TILES (tile (I,J), J <= I, at
+// I(I+1)/2 + J, 16 doubles row-major) so that the factorisation works on register-sized blocks.
+__device__ __forceinline__ int tri(int i, int j) {   // element (i,j), j <= i
+    const int I = i >> 2, J = j >> 2;
+    return ((I * (I + 1) / 2 + J) << 4) + ((i & 3) << 2) + (j & 3);
 }
 
 // ---- IMU factor: raw residual and Jacobian (before whitening); J is [15][30] row-major.
@@ -305,46 +307,144 @@ __device__ inline void plane_factor(int K, const int32_t *fr, const float *z, co
     }
 }
 
-// Dense LDL^T (packed lower, in shared memory) + solve A x = rhs; all threads of the CTA.
-// Column k is left unscaled (c_ik = l_ik d_k), so a step only READS column k and the
-// diagonal and WRITES columns > k: one barrier per column.  Returns false (uniformly) if a
-// pivot is not positive / finite (the system must be positive definite, as for ceres'
-// Cholesky-based SPARSE_SCHUR).
-__device__ inline bool chol_solve_packed(double *A, double *x, int D, int *flag_sm) {
+// Tiled dense Cholesky A = L L^T + solve, all threads of the CTA, fp64, in shared memory.
+// nb block rows of 4 (padding rows carry an identity diagonal).  Per block column kb:
+//   (a) one thread factors the 4x4 diagonal tile and stores inv(L_kk);
+//   (b) one thread per panel tile: A_Ik <- A_Ik L_kk^-T;
+//   (c) one thread per trailing tile: A_IJ -= A_Ik A_Jk^T   (64 independent FMAs).
+// 3 barriers per block column (15 block columns for D = 60) instead of 2-3 per scalar column.
+// Linv: [nb][16] scratch.  Returns false (uniformly) if a pivot is not positive / finite (the
+// system must be positive definite, as for ceres' Cholesky-based SPARSE_SCHUR).
+__device__ inline bool chol_solve_tiled(double *A, double *x, int nb, double *Linv, int *flag_sm) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    bool ok = true;
+    if (tid == 0) *flag_sm = 1;
     __syncthreads();
-    for (int k = 0; k < D; ++k) {
-        const double dk = A[tri(k, k)];
-        if (!(dk > 0.0) || !isfinite(dk)) { ok = false; break; }   // uniform: same value read by all
-        const double idk = 1.0 / dk;
-        const int n = D - k - 1;
-        if (n > 0) {
-            const int nc = max(1, min(nt / n, 8));        // threads per row
-            const int rows_per_pass = nt / nc;
-            const int c0 = tid % nc;
-            for (int r = tid / nc; r < n; r += rows_per_pass) {
-                const int i = k + 1 + r;
-                const double lik = A[tri(i, k)] * idk;
-                double *row = A + tri(i, 0);
-                for (int j = k + 1 + c0; j <= i; j += nc) row[j] -= lik * A[tri(j, k)];
+    for (int kb = 0; kb < nb; ++kb) {
+        double *Akk = A + ((kb * (kb + 1) / 2 + kb) << 4);
+        if (tid == 0) {
+            double L[16], Li[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { L[e] = Akk[e]; Li[e] = 0.0; }
+            bool good = true;
+            double idg[4];                       // reciprocals of the diagonal of L (no divisions below)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                double d = L[c * 4 + c];
+#pragma unroll
+                for (int m = 0; m < c; ++m) d -= L[c * 4 + m] * L[c * 4 + m];
+                if (!(d > 0.0) || !isfinite(d)) { good = false; d = 1.0; }
+                const double id = rsqrt(d);
+                idg[c] = id;
+                L[c * 4 + c] = d * id;
+#pragma unroll
+                for (int r = c + 1; r < 4; ++r) {
+                    double v = L[r * 4 + c];
+#pragma unroll
+                    for (int m = 0; m < c; ++m) v -= L[r * 4 + m] * L[c * 4 + m];
+                    L[r * 4 + c] = v * id;
+                }
             }
+            // inverse of the lower-triangular 4x4
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                Li[c * 4 + c] = idg[c];
+#pragma unroll
+                for (int r = c + 1; r < 4; ++r) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int m = c; m < r; ++m) v -= L[r * 4 + m] * Li[m * 4 + c];
+                    Li[r * 4 + c] = v * idg[r];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { Akk[e] = L[e]; Linv[kb * 16 + e] = Li[e]; }
+            if (!good) *flag_sm = 0;
+        }
+        __syncthreads();
+        if (*flag_sm == 0) break;                      // uniform
+        // (b) panel tiles: X <- X * Linv^T   (X L^-T)
+        for (int I = kb + 1 + tid; I < nb; I += nt) {
+            double *X = A + ((I * (I + 1) / 2 + kb) << 4);
+            const double *Li = Linv + kb * 16;
+            double t[16];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int m = 0; m <= c; ++m) v += X[r * 4 + m] * Li[c * 4 + m];
+                    t[r * 4 + c] = v;
+                }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) X[e] = t[e];
+        }
+        __syncthreads();
+        // (c) trailing tiles (I,J), kb < J <= I
+        const int n = nb - kb - 1, ntile = n * (n + 1) / 2;
+        for (int e = tid; e < ntile; e += nt) {
+            int ii = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+            while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+            while (ii * (ii + 1) / 2 > e) --ii;
+            const int jj = e - ii * (ii + 1) / 2;
+            const int I = kb + 1 + ii, J = kb + 1 + jj;
+            const double *P = A + ((I * (I + 1) / 2 + kb) << 4), *Q = A + ((J * (J + 1) / 2 + kb) << 4);
+            double *C = A + ((I * (I + 1) / 2 + J) << 4);
+            double p[16], q[16];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) { p[m] = P[m]; q[m] = Q[m]; }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    C[r * 4 + c] -= p[r * 4] * q[c * 4] + p[r * 4 + 1] * q[c * 4 + 1] + p[r * 4 + 2] * q[c * 4 + 2] + p[r * 4 + 3] * q[c * 4 + 3];
         }
         __syncthreads();
     }
-    (void)flag_sm;
-    if (!ok) return false;
-    // L y = b (column oriented), z = y / d, L^T x = z
-    for (int k = 0; k < D; ++k) {
-        const double t = x[k] / A[tri(k, k)];       // x[k] is final here and nobody writes it below
-        for (int i = k + 1 + tid; i < D; i += nt) x[i] -= A[tri(i, k)] * t;
+    if (*flag_sm == 0) return false;
+    // forward: y = L^-1 b (block rows), backward: x = L^-T y
+    for (int kb = 0; kb < nb; ++kb) {
+        if (tid == 0) {
+            const double *Li = Linv + kb * 16;
+            double v[4], o[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r] = x[kb * 4 + r];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { o[r] = 0.0;
+#pragma unroll
+                for (int m = 0; m <= r; ++m) o[r] += Li[r * 4 + m] * v[m]; }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) x[kb * 4 + r] = o[r];
+        }
+        __syncthreads();
+        for (int I = kb + 1 + tid; I < nb; I += nt) {
+            const double *X = A + ((I * (I + 1) / 2 + kb) << 4);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                x[I * 4 + r] -= X[r * 4] * x[kb * 4] + X[r * 4 + 1] * x[kb * 4 + 1] + X[r * 4 + 2] * x[kb * 4 + 2] + X[r * 4 + 3] * x[kb * 4 + 3];
+        }
         __syncthreads();
     }
-    for (int i = tid; i < D; i += nt) x[i] /= A[tri(i, i)];
-    __syncthreads();
-    for (int k = D - 1; k > 0; --k) {
-        const double xk = x[k];
-        for (int i = tid; i < k; i += nt) x[i] -= A[tri(k, i)] / A[tri(i, i)] * xk;
+    for (int kb = nb - 1; kb >= 0; --kb) {
+        if (tid == 0) {
+            const double *Li = Linv + kb * 16;
+            double v[4], o[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r] = x[kb * 4 + r];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { o[r] = 0.0;
+#pragma unroll
+                for (int m = r; m < 4; ++m) o[r] += Li[m * 4 + r] * v[m]; }   // Linv^T
+#pragma unroll
+            for (int r = 0; r < 4; ++r) x[kb * 4 + r] = o[r];
+        }
+        __syncthreads();
+        for (int J = tid; J < kb; J += nt) {
+            const double *X = A + ((kb * (kb + 1) / 2 + J) << 4);      // tile (kb, J): rows of kb, cols of J
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                x[J * 4 + c] -= X[c] * x[kb * 4] + X[4 + c] * x[kb * 4 + 1] + X[8 + c] * x[kb * 4 + 2] + X[12 + c] * x[kb * 4 + 3];
+        }
         __syncthreads();
     }
     return true;
@@ -353,7 +453,7 @@ __device__ inline bool chol_solve_packed(double *A, double *x, int D, int *flag_
 constexpr int kSolveImuSlab = 15 * 30 + 16;     // raw J + r per factor
 
 static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
-    const int w = blockIdx.x;
+    const int w = blockIdx.x + a.w0;
     const WinHdr &H = a.hdr[w];
     const WinConst &wc = a.cst[w];
     const int N = H.N;
@@ -364,20 +464,26 @@ static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
     const double *frames = a.frames + (size_t)w * a.Ncap * kFrameStride;
     WinCtrl &ctrl = a.ctrl[w];
     const double mu = a.mu_override >= 0.0 ? a.mu_override : ctrl.mu;
+    int stamp_i = 0;
+#define STAMP() do { if (a.dbg && tid == 0 && blockIdx.x == 0) a.dbg[stamp_i] = clock64(); ++stamp_i; } while (0)
+    STAMP();
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *A = reinterpret_cast<double *>(smem_raw);       // packed lower D(D+1)/2
-    double *g = A + D * (D + 1) / 2;                        // [D] reduced gradient
-    double *gu = g + D;                                     // [D] unreduced gradient (for |g|_inf)
-    double *hcorr = gu + D;                                 // [D] direct - reduced diagonal
-    double *xs = hcorr + D;                                 // [D] solution
-    double *T = xs + D;                                     // [N][36] change of variables
+    const int nb = (D + 3) >> 2, Dp = nb * 4;               // block rows of 4; rows >= D are identity padding
+    const int nA = nb * (nb + 1) / 2 * 16;
+    double *A = reinterpret_cast<double *>(smem_raw);       // packed lower 4x4 tiles
+    double *g = A + nA;                                     // [Dp] reduced gradient
+    double *gu = g + Dp;                                    // [Dp] unreduced gradient (for |g|_inf)
+    double *hcorr = gu + Dp;                                // [Dp] direct - reduced diagonal
+    double *xs = hcorr + Dp;                                // [Dp] solution
+    double *Linv = xs + Dp;                                 // [nb][16] inverses of the diagonal tiles
+    double *T = Linv + nb * 16;                             // [N][36] change of variables
     double *scr = T + kMaxFrames * 36;                      // scratch: IMU slabs / prior vectors
     __shared__ double cost_sm[4];
     __shared__ int flag_sm;
 
-    for (int i = tid; i < D * (D + 1) / 2; i += nt) A[i] = 0.0;
-    for (int i = tid; i < 4 * D; i += nt) g[i] = 0.0;       // g, gu, hcorr, xs contiguous
+    for (int i = tid; i < nA; i += nt) A[i] = 0.0;
+    for (int i = tid; i < 4 * Dp; i += nt) g[i] = 0.0;      // g, gu, hcorr, xs contiguous
     if (tid < 4) cost_sm[tid] = 0.0;
     if (tid < N) {
         const double *fs = frames + tid * kFrameStride;
@@ -398,6 +504,7 @@ static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
     }
     __syncthreads();
 
+    STAMP();   // 1: init done
     // ---- vision blocks: H_delta[f,gf] = T_f^T X T_g.  Stage the xi-coordinate blocks in shared
     // memory (coalesced), X <- X T_g in place, then T_f^T (X T_g) into the packed system.
     const int npairs = N * (N + 1) / 2;
@@ -467,6 +574,7 @@ static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
     }
     __syncthreads();
 
+    STAMP();   // 2: vision transform done
     // ---- IMU factors (bundle_adjustor.cpp:220-242): no loss
     if (inertial && H.n_imu > 0) {
         const int32_t *idx = a.imu_idx + (size_t)w * a.Ncap * 2;
@@ -614,6 +722,7 @@ static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
         for (int i = tid; i < D; i += nt) go[(i / stride) * 15 + (i % stride)] = g[i];
     }
 
+    STAMP();   // 3: factors done
     // ---- Jacobi scale, LM diagonal, constant blocks
     double *scale = a.pose_scale + (size_t)w * 15 * a.Ncap;
     double my_gdx = 0.0;
@@ -630,14 +739,13 @@ static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
     }
     __syncthreads();
     const int fixed_mask = H.fixed_mask;
-    for (int e = tid; e < D * (D + 1) / 2; e += nt) {
-        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-        while (i * (i + 1) / 2 > e) --i;
-        const int j = e - i * (i + 1) / 2;
+    for (int e = tid; e < Dp * Dp; e += nt) {
+        const int i = e / Dp, j = e - i * Dp;
+        if (j > i) continue;
+        if (i >= D) { A[tri(i, j)] = (i == j) ? 1.0 : 0.0; continue; }     // padding rows
         const int fi = i / stride, ci = i - fi * stride, fj = j / stride, cj = j - fj * stride;
         const bool mi = ((fixed_mask >> fi) & 1) && ci < 6, mj = ((fixed_mask >> fj) & 1) && cj < 6;
-        if (mi || mj) A[e] = (i == j) ? 1.0 : 0.0;
+        if (mi || mj) A[tri(i, j)] = (i == j) ? 1.0 : 0.0;
     }
     double *reg_keep = scr;       // [D]
     for (int i = tid; i < D; i += nt) {
@@ -649,7 +757,9 @@ static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
     }
     __syncthreads();
 
-    const bool ok = chol_solve_packed(A, xs, D, &flag_sm);
+    STAMP();   // 4: scaling/masking done
+    const bool ok = chol_solve_tiled(A, xs, nb, Linv, &flag_sm);
+    STAMP();   // 5: solve done
 
     // ---- outputs
     double *dxo = a.dx_pose + (size_t)w * a.Ncap * 15;
@@ -721,11 +831,12 @@ struct CostArgs {
     const int32_t *pt_plane, *pt_begin, *pt_frame;
     const float *pt_z;
     int Pcap, Tcap, Ocap, Ncap;
+    int w0;
     double *out;                   // [W] non-vision candidate cost
 };
 
 static __global__ void aux_cost_kernel(CostArgs a) {
-    const int w = blockIdx.x;
+    const int w = blockIdx.x + a.w0;
     const WinHdr &H = a.hdr[w];
     const WinConst &wc = a.cst[w];
     const int tid = threadIdx.x, nt = blockDim.x;

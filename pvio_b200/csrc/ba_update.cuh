@@ -30,13 +30,14 @@ struct UpdArgs {
     double *acc;              // [W][8]: cand_cost_vis, g.dx(lm), dx.reg.dx(lm), gn_norm2(lm), dxnorm2(lm), xnorm2(lm)
     int Ncap, Mcap, Kcap;
     double mu_override;
+    int w0;
     double beta;              // step scale (1 = full Gauss-Newton step; < 1 when the trust region truncates it)
 };
 
 template <bool kLoss>
 __global__ void __launch_bounds__(kLinThreads, 2)
 update_cost_kernel(UpdArgs a) {
-    const int w = blockIdx.y;
+    const int w = blockIdx.y + a.w0;
     const WinHdr &H = a.hdr[w];
     const WinConst &wc = a.cst[w];
     const int N = H.N;
