@@ -9,6 +9,7 @@
 #include <numeric>
 #include "api_internal.h"
 #include "ba_lin.cuh"
+#include "ba_lin2.cuh"
 #include "ba_solve.cuh"
 #include "ba_update.cuh"
 
@@ -222,7 +223,8 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
         unsigned seen = 1u << a;
         for (int k = b0; k < b1; ++k) {
             const int f = w->obs_frame[k];
-            if (f < 0 || f >= N || (seen >> f) & 1) return fail(h, PVIO_B200_EINVAL, "observation frames must be distinct and differ from the anchor");
+            if (f <= a || f >= N || (seen >> f) & 1)
+                return fail(h, PVIO_B200_EINVAL, "observation frames must be distinct and later than the anchor (Track::first_frame is the lowest id)");
             seen |= 1u << f;
             ob[k_out].zx = (float)w->obs_z[2 * k];
             ob[k_out].zy = (float)w->obs_z[2 * k + 1];
@@ -347,7 +349,7 @@ static int lin_grid_x(Handle *h, int n) {
     // one CTA per window once the batch fills the machine; otherwise split a window's chunks
     const int target = 2 * h->sm_count;
     int gx = std::max(1, target / std::max(n, 1));
-    return std::min(gx, 32);
+    return std::min(gx, n * 2 < h->sm_count ? 32 : 16);
 }
 
 static size_t solve_smem(Handle *h, int w0, int n) {
@@ -385,7 +387,10 @@ static int run_linearize(Handle *h, int n, const StepCfg &c) {
         for (auto &e : h->kev) CK(h, cudaEventCreate(&e));
     }
     CK(h, cudaEventRecord(h->kev[slot], st));
-    lin_schur_kernel<true><<<dim3(gx, n), kLinThreads, lin_smem_bytes(), st>>>(a);
+    // few windows: the group-per-landmark kernel exposes more parallelism per window (latency);
+    // many windows: the thread-per-landmark kernel issues ~2x fewer instructions (throughput)
+    if (n * 2 < h->sm_count) lin_schur_kernel<true><<<dim3(gx, n), kLinThreads, lin_smem_bytes(), st>>>(a);
+    else lin_tpl_kernel<true><<<dim3(gx, n), kLinThreads, lin2_smem_bytes(h->Ncap), st>>>(a);
     CK(h, cudaEventRecord(h->kev[slot + 1], st));
     ++h->kev_count;
     ++h->launches;
@@ -423,9 +428,15 @@ static int run_solve(Handle *h, int n, const StepCfg &c) {
     cudaStream_t st = c.stream ? c.stream : h->stream;
     const size_t smem = solve_smem(h, c.w0, n);
     if (smem > 220 * 1024) return fail(h, PVIO_B200_EINVAL, "reduced system too large for shared memory");
-    // small systems: a narrow CTA per window (many resident per SM); large: a full CTA
-    const int threads = (smem <= 24 * 1024 && n >= 64) ? 64 : 256;
-    solve_kernel<<<n, threads, smem, st>>>(a);
+    // visual-only batches: the lean kernel (no IMU / prior / plane code), a narrow CTA per window so
+    // that many windows are resident per SM; otherwise the full kernel with a wide CTA
+    bool visual = true;
+    for (int i = c.w0; i < c.w0 + n; ++i) {
+        const WinHdr &H = h->hdr.h[i];
+        if (H.use_inertial || H.n_ptracks > 0) { visual = false; break; }
+    }
+    if (visual && smem <= 48 * 1024 && n >= 64) solve_kernel_visual<<<n, 64, smem, st>>>(a);
+    else solve_kernel<<<n, 256, smem, st>>>(a);
     ++h->launches;
     CK(h, cudaGetLastError());
     return 0;
@@ -440,7 +451,8 @@ static int run_update(Handle *h, int n, const StepCfg &c) {
     u.rho_cand = h->rho_cand.d; u.frames_cand = h->frames_cand.d; u.dx_lm = h->dx_lm.d; u.acc = h->acc.d;
     u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.beta = c.beta; u.w0 = c.w0;
     const int gx = lin_grid_x(h, n);
-    update_cost_kernel<true><<<dim3(gx, n), kLinThreads, 0, st>>>(u);
+    if (n * 2 < h->sm_count) update_cost_kernel<true><<<dim3(gx, n), kLinThreads, 0, st>>>(u);
+    else update_tpl_kernel<true><<<dim3(gx, n), kLinThreads, 0, st>>>(u);
     ++h->launches;
     CostArgs k;
     memset(&k, 0, sizeof(k));
@@ -541,8 +553,11 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     // unallocated optional buffers still need valid (dummy) device pointers? kernels never touch them
     h->perm.resize(W); h->perm_identity.assign(W, 1); h->slot_M.assign(W, 0); h->slot_N.assign(W, 0); h->slot_K.assign(W, 0);
     CK(h, cudaFuncSetAttribute(lin_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem_bytes()));
+    CK(h, cudaFuncSetAttribute(lin_tpl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin2_smem_bytes(kMaxFrames)));
+    CK(h, cudaFuncSetAttribute(lin_tpl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin2_smem_bytes(kMaxFrames)));
     CK(h, cudaFuncSetAttribute(lin_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem_bytes()));
     CK(h, cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(h, cudaFuncSetAttribute(solve_kernel_visual, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
     init_ctrl_kernel<<<(int)W, 32, 0, h->stream>>>(h->ctrl.d, 1e-8, 1e4);
     ++h->launches;
     CK(h, cudaStreamSynchronize(h->stream));

@@ -452,7 +452,8 @@ __device__ inline bool chol_solve_tiled(double *A, double *x, int nb, double *Li
 
 constexpr int kSolveImuSlab = 15 * 30 + 16;     // raw J + r per factor
 
-static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
+template <bool kFull>
+static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     const int w = blockIdx.x + a.w0;
     const WinHdr &H = a.hdr[w];
     const WinConst &wc = a.cst[w];
@@ -576,7 +577,7 @@ static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
 
     STAMP();   // 2: vision transform done
     // ---- IMU factors (bundle_adjustor.cpp:220-242): no loss
-    if (inertial && H.n_imu > 0) {
+    if (kFull && inertial && H.n_imu > 0) {
         const int32_t *idx = a.imu_idx + (size_t)w * a.Ncap * 2;
         const double *recs = a.imu_data + (size_t)w * a.Ncap * kImuStride;
         for (int n0 = 0; n0 < H.n_imu; n0 += 4) {           // 4 factors per round (scratch = 4 slabs of raw + whitened J)
@@ -623,7 +624,7 @@ static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
     }
 
     // ---- marginalisation prior (bundle_adjustor.cpp:126-139): no loss
-    if (inertial && H.n_prior > 0) {
+    if (kFull && inertial && H.n_prior > 0) {
         const int n = H.n_prior, d = 15 * n, dcap = 15 * a.Ncap;
         const int32_t *pf = a.prior_frames + (size_t)w * a.Ncap;
         const double *S = a.prior_S + (size_t)w * dcap * dcap;
@@ -681,7 +682,7 @@ static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
     }
 
     // ---- plane factors (bundle_adjustor.cpp:162-196): CauchyLoss
-    if (H.n_ptracks > 0) {
+    if (kFull && H.n_ptracks > 0) {
         const double *pl = a.plane_param + (size_t)w * a.Pcap * 4;
         const int32_t *ptp = a.pt_plane + (size_t)w * a.Tcap;
         const int32_t *ptb = a.pt_begin + (size_t)w * (a.Tcap + 1);
@@ -814,6 +815,10 @@ static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
         }
     }
 }
+
+static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) { solve_body<true>(a); }
+// visual-only windows (no IMU / prior / plane factors): small register footprint, many CTAs per SM
+static __global__ void __launch_bounds__(64, 10) solve_kernel_visual(SolveArgs a) { solve_body<false>(a); }
 
 // Non-vision part of the cost at the candidate state (IMU + prior + plane), one CTA per window.
 struct CostArgs {

@@ -181,4 +181,131 @@ update_cost_kernel(UpdArgs a) {
     }
 }
 
+// Second generation: one LANE per landmark (see ba_lin2.cuh).  Same outputs.
+template <bool kLoss>
+__global__ void __launch_bounds__(kLinThreads, 2)
+update_tpl_kernel(UpdArgs a) {
+    const int w = blockIdx.y + a.w0;
+    const WinHdr &H = a.hdr[w];
+    const WinConst &wc = a.cst[w];
+    const int N = H.N;
+    const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+
+    __shared__ FrameSm F[kMaxFrames];      // current state
+    __shared__ FrameSm Fc[kMaxFrames];     // candidate state
+    __shared__ double dxi[kMaxFrames][6];  // xi = T delta per frame
+    __shared__ double red[8];
+
+    if (tid < N) {
+        const double *fs = a.frames + ((size_t)w * a.Ncap + tid) * kFrameStride;
+        const double *d = a.dx_pose + ((size_t)w * a.Ncap + tid) * 15;
+        make_frame(fs, wc, F[tid]);
+        double fc[kFrameStride];
+        const double db[3] = {a.beta * d[0], a.beta * d[1], a.beta * d[2]};
+        quat_plus(fs, db, fc);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) fc[4 + i] = fs[4 + i] + a.beta * d[3 + i];
+        make_frame(fc, wc, Fc[tid]);
+        if (blockIdx.x == 0) {
+            double *o = a.frames_cand + ((size_t)w * a.Ncap + tid) * kFrameStride;
+            double amb = 0.0;
+#pragma unroll
+            for (int i = 0; i < kFrameStride; ++i) {
+                o[i] = fc[i];
+                const bool pose = i < 7;
+                const bool live = pose ? !((H.fixed_mask >> tid) & 1) : (H.use_inertial != 0);
+                if (live) amb += (fc[i] - fs[i]) * (fc[i] - fs[i]);
+            }
+            atomicAdd(&a.acc[(size_t)w * 8 + 6], amb);
+        }
+        double R[9], om[3];
+        quat_to_mat(fs, R);
+        mat3_vec(R, d, om);
+        const double p0 = fs[4] - wc.origin[0], p1 = fs[5] - wc.origin[1], p2 = fs[6] - wc.origin[2];
+        dxi[tid][0] = om[0]; dxi[tid][1] = om[1]; dxi[tid][2] = om[2];
+        dxi[tid][3] = -(p1 * om[2] - p2 * om[1]) - d[3];
+        dxi[tid][4] = -(p2 * om[0] - p0 * om[2]) - d[4];
+        dxi[tid][5] = -(p0 * om[1] - p1 * om[0]) - d[5];
+    }
+    if (tid < 8) red[tid] = 0.0;
+    __syncthreads();
+
+    const float W[4] = {(float)wc.sic[0], (float)wc.sic[1], (float)wc.sic[2], (float)wc.sic[3]};
+    const float cb = (float)(wc.cauchy_a * wc.cauchy_a);
+    const double mu = a.mu_override >= 0.0 ? a.mu_override : a.ctrl[w].mu;
+    const ObsRec *obs = a.obs + (size_t)w * a.Kcap;
+    const LmRec *lms = a.lms + (size_t)w * a.Mcap;
+    const double *rho = a.rho + (size_t)w * a.Mcap;
+    const double *lm_scale = a.lm_scale + (size_t)w * a.Mcap;
+    const LmAux *aux = a.lm_aux + (size_t)w * a.Mcap;
+    double *rho_c = a.rho_cand + (size_t)w * a.Mcap;
+    double *dxl = a.dx_lm + (size_t)w * a.Mcap;
+
+    double s_cost = 0.0, s_gdx = 0.0, s_reg = 0.0, s_gn = 0.0, s_dx2 = 0.0, s_x2 = 0.0;
+    for (int c0 = blockIdx.x * 8; c0 < H.n_chunks; c0 += gridDim.x * 8) {
+        const int ch = c0 + wv;
+        if (ch >= H.n_chunks) continue;
+        const int lm0 = H.chunk_begin[ch];
+        const int cnt = H.chunk_meta[ch] & 0xff;
+        const int anchor = H.chunk_meta[ch] >> 8;
+        if (lane >= cnt) continue;
+        const int l = lm0 + lane;
+        const LmRec lr = lms[l];
+        const int n_obs = (lr.meta >> 8) & 0xff;
+        const double rl = rho[l];
+        double x[3];
+        float xf[3], cl[3];
+        world_point(F[anchor], lr.zrx, lr.zry, rl, x, xf, cl);
+        double hdx = 0.0, hll = 0.0;
+        for (int j = 0; j < n_obs; ++j) {
+            const ObsRec o = obs[lr.obs_begin + j];
+            ObsLin ol;
+            linearize_obs<kLoss>(F[o.frame], x, xf, cl, o.zx, o.zy, W, cb, ol);
+            hll += (double)(ol.j0 * ol.j0 + ol.j1 * ol.j1);
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+                hdx += (double)(ol.j0 * ol.Y0[i] + ol.j1 * ol.Y1[i]) * (dxi[o.frame][i] - dxi[anchor][i]);
+        }
+        double drho = 0.0;
+        if (n_obs > 0) {
+            const LmAux ax = aux[l];
+            const double wl = 1.0 / ax.hll_reg;
+            drho = isfinite(wl) ? -(ax.gl + hdx) * wl : 0.0;
+            const double sc = lm_scale[l];
+            const double reg = mu > 0.0 ? lm_reg(hll, sc, mu) : 0.0;
+            double d2 = sc * sc * hll;
+            d2 = fmin(fmax(d2, 1.0e-6), 1.0e32);
+            s_gdx += hdx * ax.gl * wl + ax.gl * drho;
+            s_reg += reg * drho * drho;
+            s_gn += d2 * (drho / sc) * (drho / sc);
+            s_dx2 += a.beta * a.beta * drho * drho;
+            s_x2 += rl * rl;
+        }
+        drho *= a.beta;
+        rho_c[l] = rl + drho;
+        dxl[l] = drho;
+        if (n_obs > 0) {
+            double xc[3];
+            float xcf[3], clc[3];
+            world_point(Fc[anchor], lr.zrx, lr.zry, rl + drho, xc, xcf, clc);
+            for (int j = 0; j < n_obs; ++j) {
+                const ObsRec o = obs[lr.obs_begin + j];
+                s_cost += (double)residual_cost<kLoss>(Fc[o.frame], xc, o.zx, o.zy, W, cb);
+            }
+        }
+    }
+    double v[6] = {s_cost, s_gdx, s_reg, s_gn, s_dx2, s_x2};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+        if (lane == 0 && v[k] != 0.0) atomicAdd(&red[k], v[k]);
+    }
+    __syncthreads();
+    if (tid < 6) {
+        double *o = a.acc + (size_t)w * 8 + tid;
+        if (gridDim.x == 1) *o = red[tid]; else atomicAdd(o, red[tid]);
+    }
+}
+
 }  // namespace pvio
