@@ -229,6 +229,8 @@ def free_mask(win):
             m[15 * f:15 * f + 6] = False
         if not win.use_inertial:
             m[15 * f + 6:15 * f + 15] = False
+    # a landmark without residual blocks is dropped from ceres' reduced program (stays constant)
+    m[15 * win.N:] = np.diff(win.lm_obs_begin) > 0
     return m
 
 
@@ -379,11 +381,11 @@ def gn_step(win, st, mu=MIN_MU, scale=None, schur=False):
         pf = np.where(free[:P])[0]
         Hpp = Hr[:P, :P]
         Hpl = Hr[:P, P:]
-        Hll = np.diag(Hr)[P:]
+        Hll = np.where(free[P:], np.diag(Hr)[P:], 1.0)
         Hred = Hpp - (Hpl / Hll) @ Hpl.T
         gred = g[:P] - Hpl @ (g[P:] / Hll)
         dx[pf] = -np.linalg.solve(Hred[np.ix_(pf, pf)], gred[pf])
-        dx[P:] = -(g[P:] + Hpl.T @ dx[:P]) / Hll
+        dx[P:] = np.where(free[P:], -(g[P:] + Hpl.T @ dx[:P]) / Hll, 0.0)
         out.update(Hred=Hred, gred=gred)
     out['dx'] = dx
     return out

@@ -389,7 +389,8 @@ static int run_linearize(Handle *h, int n, const StepCfg &c) {
     CK(h, cudaEventRecord(h->kev[slot], st));
     // few windows: the group-per-landmark kernel exposes more parallelism per window (latency);
     // many windows: the thread-per-landmark kernel issues ~2x fewer instructions (throughput)
-    if (n * 2 < h->sm_count) lin_schur_kernel<true><<<dim3(gx, n), kLinThreads, lin_smem_bytes(), st>>>(a);
+    // (the group kernel owns at most 256 Phase-B tiles: N <= 15)
+    if (n * 2 < h->sm_count && h->Ncap * (h->Ncap + 1) <= kLinThreads) lin_schur_kernel<true><<<dim3(gx, n), kLinThreads, lin_smem_bytes(), st>>>(a);
     else lin_tpl_kernel<true><<<dim3(gx, n), kLinThreads, lin2_smem_bytes(h->Ncap), st>>>(a);
     CK(h, cudaEventRecord(h->kev[slot + 1], st));
     ++h->kev_count;

@@ -2,8 +2,8 @@
 //
 //   prior J^T J                                   :369-413   marg_assemble_kernel
 //   IMU factors adjacent to the victim            :416-450   marg_assemble_kernel
-//   reprojection factors of victim-seen tracks    :453-533   lin_schur_kernel<false> (no loss, quirk Q3)
-//   landmark Schur (1/mat, isfinite skip)         :536-545   lin_schur_kernel<false>
+//   reprojection factors of victim-seen tracks    :453-533   lin_tpl_kernel<false> (no loss, quirk Q3)
+//   landmark Schur (1/mat, isfinite skip)         :536-545   lin_tpl_kernel<false>
 //   frame Schur with the explicit 15x15 inverse   :547-581   marg_reduce_kernel
 //   eigen factorisation, clamp lambda <= 1e-8     :583-590   marg_eig_kernel (parallel cyclic Jacobi)
 // All dense algebra is fp64.  Runs once per keyframe (not per iteration): latency, not bandwidth.
@@ -11,6 +11,7 @@
 #include <vector>
 #include "api_internal.h"
 #include "ba_lin.cuh"
+#include "ba_lin2.cuh"
 #include "ba_solve.cuh"
 
 namespace pvio {
@@ -339,7 +340,7 @@ int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state
     a.Hred = h->Hred.d; a.Hdd = h->Hdd.d; a.gdir = h->gdir.d; a.gred = h->gred.d; a.cost_vis = h->cost_vis.d;
     a.Ncap = h->Ncap; a.Mcap = h->Mcap; a.Kcap = h->Kcap;
     a.compute_scale = 1; a.victim_only = 1; a.mu_override = 0.0; a.w0 = 0;
-    lin_schur_kernel<false><<<dim3(16, 1), kLinThreads, lin_smem_bytes(), h->stream>>>(a);
+    lin_tpl_kernel<false><<<dim3(4, 1), kLinThreads, lin2_smem_bytes(h->Ncap), h->stream>>>(a);
     ++h->launches;
     // dense buffers
     double *dH = nullptr, *db = nullptr, *dHk = nullptr, *dbk = nullptr, *dV = nullptr, *dS = nullptr, *de = nullptr, *dscr = nullptr;

@@ -241,3 +241,68 @@ def test_pipelined_host_step_matches_resident_step():
         assert _rel(dx_h[i], ref['dx']) < TOL_DX
     assert _rel(dx_h[1098], dx_h[1098 % 3]) < 1e-9 and _rel(dx_h[1099], dx_h[1099 % 3]) < 1e-9
     b.close()
+
+
+# ------------------------------------------------------------------ golden vectors and edge cases
+import os as _os
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "ba_golden.npz")
+_CASES = {
+    "cfg2": lambda: synth.make_cfg2(N=6, M=64, seed=648),
+    "cfg2b": lambda: synth.make_cfg2(N=7, M=70, seed=648, staggered=True),
+    "cfg3": lambda: synth.make_cfg3(N=6, M=80, seed=649),
+    "cfg4": lambda: synth.make_cfg4(N=6, M=60, seed=650, tracks_per_plane=20),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_CASES))
+def test_golden_vectors(ba, name):
+    """Committed fixtures (tests/golden/make_ba_golden.py): no oracle code runs in this test."""
+    g = np.load(_GOLD)
+    w, st, _ = _CASES[name]()
+    out = ba.gn_step(w, st, mu=1e-8, want_system=True)
+    tol = 1e-5 if name != "cfg3" else 5e-5      # 6-frame inertial windows are weakly conditioned
+    assert _rel(out["dx"], g[name + "_dx"]) < tol
+    assert abs(out["cost"] - float(g[name + "_cost"])) < 2e-6 * float(g[name + "_cost"])
+    assert abs(out["new_cost"] - float(g[name + "_newcost"])) < 5e-5 * max(float(g[name + "_newcost"]), 1.0)
+    P = 15 * w.N
+    assert np.max(np.abs(out["gred"] - g[name + "_gred"])) < 1e-5 * np.max(np.abs(g[name + "_gred"]))
+    if name + "_margH" in g:
+        S, e, Hm, bm = ba.marginalize_frame(w, st, 0, want_info=True)
+        hs = np.maximum(np.sqrt(np.abs(np.diag(g[name + "_margH"]))), 1e-3)
+        assert np.max(np.abs(Hm - g[name + "_margH"]) / np.outer(hs, hs)) < 1e-6
+
+
+def test_edge_cases_ragged_and_extreme_sizes(ba):
+    # (a) landmarks with a single observation, a landmark with none, one fixed frame only
+    w, st, _ = synth.make_cfg2(N=6, M=40, staggered=True, seed=11)
+    beg, of, oz = [0], [], []
+    for l in range(w.M):
+        b0, b1 = int(w.lm_obs_begin[l]), int(w.lm_obs_begin[l + 1])
+        keep = 0 if l == 7 else (1 if l % 3 == 0 else b1 - b0)
+        of += list(w.obs_frame[b0:b0 + keep]); oz += list(w.obs_z[b0:b0 + keep]); beg.append(len(of))
+    w.lm_obs_begin = np.array(beg, dtype=np.int32)
+    w.obs_frame, w.obs_z, w.K = np.array(of, dtype=np.int32), np.array(oz).reshape(-1, 2), len(of)
+    w.validate()
+    # two thirds of the landmarks keep a single observation: depth and pose trade off freely, the
+    # system is an order of magnitude worse conditioned than a normal window
+    out, ref = _check_step(ba, w, st, tol=1e-4)
+    assert out['dx'][15 * w.N + 7] == 0.0           # the unobserved landmark does not move
+    # (b) the largest visual window the ABI supports (16 frames) and 1..15 observations per landmark
+    big = BundleAdjustor(max_windows=1, max_frames=16, max_landmarks=300, max_obs=4096)
+    w, st, _ = synth.make_cfg2(N=16, M=240, staggered=True, seed=12)
+    _check_step(big, w, st)
+    # (c) the reference's default window (10 + 1 frames, config.cpp) with IMU + prior: D = 165
+    w, st, _ = synth.make_cfg3(N=11, M=200, seed=13)
+    _check_step(big, w, st, tol=5e-5)
+    big.close()
+    # (d) capacity overflow and malformed input are rejected, not truncated
+    from pvio_b200.bundle_adjustor import PvioB200Error
+    small = BundleAdjustor(max_windows=1, max_frames=4, max_landmarks=8, max_obs=16)
+    w, st, _ = synth.make_cfg2(N=6, M=40)
+    with pytest.raises(PvioB200Error):
+        small.gn_step(w, st)
+    w, st, _ = synth.make_cfg2(N=4, M=6)
+    w.obs_frame = w.obs_frame.copy(); w.obs_frame[0] = 0          # observation in the anchor frame
+    with pytest.raises(PvioB200Error):
+        small.gn_step(w, st)
+    small.close()
