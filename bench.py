@@ -221,12 +221,13 @@ def run_gpu(args):
             traffic = json.load(open(tp))["dram_bytes_per_window"] * W
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "lin_schur_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "lin_tpl_kernel (linearise + Schur)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_alg_per_window": balg, "windows_per_launch": W, "kernel_ms": lin_ms,
                 "kernel_share_of_step": lin_ms / (ms / args.steps),
-                "note": "arithmetic intensity ~33 flop/B puts this kernel above the fp32 ridge (11.5 flop/B); "
-                        "it is FP32/FP64-issue bound, see DESIGN.md"}
+                "note": "algorithmic bytes / CUDA-event kernel time; DRAM traffic equals the algorithmic bytes (no re-reads); "
+                        "arithmetic intensity ~33 flop/B is above the fp32 ridge (11.5 flop/B), so on CUDA cores the kernel is "
+                        "FP32-issue bound, see DESIGN.md 4.1"}
 
     # ---- single window: latency of one GN iteration and of a whole solve() through the C-ABI
     ba1 = BundleAdjustor(device=local_rank, max_windows=1, max_frames=N, max_landmarks=512, max_obs=4608)
