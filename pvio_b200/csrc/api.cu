@@ -228,7 +228,6 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
             seen |= 1u << f;
             ob[k_out].zx = (float)w->obs_z[2 * k];
             ob[k_out].zy = (float)w->obs_z[2 * k + 1];
-            ob[k_out].lm = lp;
             ob[k_out].frame = f;
             ++k_out;
         }

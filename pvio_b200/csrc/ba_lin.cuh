@@ -271,7 +271,7 @@ lin_schur_kernel(LinArgs a) {
             // the two groups of a warp must run the same shuffle sequence
             const int n_max = max(n_obs, __shfl_xor_sync(0xffffffffu, n_obs, 16));
             ObsRec o;
-            o.frame = -1; o.zx = 0.f; o.zy = 0.f; o.lm = 0;
+            o.frame = -1; o.zx = 0.f; o.zy = 0.f;
             if (lane < n_obs) o = obs[lr.obs_begin + lane];
             int src = -1;
             for (int j = 0; j < n_max; ++j) {

@@ -154,7 +154,7 @@ lin_tpl_kernel(LinArgs a) {
             for (int j = 0; j < n_max; ++j) {
                 const bool act = j < n_obs;
                 ObsRec o;
-                o.frame = 0; o.zx = 0.f; o.zy = 0.f; o.lm = 0;
+                o.frame = 0; o.zx = 0.f; o.zy = 0.f;
                 if (act) o = obs[lr.obs_begin + j];
                 const int t = o.frame;
                 float q[32];

@@ -110,7 +110,7 @@ update_cost_kernel(UpdArgs a) {
             const int n_obs = lm_ok ? ((lr.meta >> 8) & 0xff) : 0;
             const int n_max = max(n_obs, __shfl_xor_sync(0xffffffffu, n_obs, 16));
             ObsRec o;
-            o.frame = -1; o.zx = 0.f; o.zy = 0.f; o.lm = 0;
+            o.frame = -1; o.zx = 0.f; o.zy = 0.f;
             if (lane < n_obs) o = obs[lr.obs_begin + lane];
             int src = -1;
             for (int j = 0; j < n_max; ++j) {
