@@ -351,18 +351,18 @@ static int lin_grid_x(Handle *h, int n) {
     return std::min(gx, n * 2 < h->sm_count ? 32 : 16);
 }
 
-static size_t solve_smem(Handle *h, int w0, int n) {
+static size_t solve_smem(Handle *h, int w0, int n, bool lean) {
     // worst case over the windows of the launch
     size_t best = 0;
     for (int i = w0; i < w0 + n; ++i) {
         const WinHdr &H = h->hdr.h[i];
         const size_t D = (H.use_inertial ? 15 : 6) * (size_t)H.N;
+        const size_t nb = (D + 3) / 4, Dp = nb * 4;
         const size_t np_ = (size_t)H.N * (H.N + 1) / 2;
-        size_t scr = std::max<size_t>(D, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);
+        size_t scr = lean ? Dp + 10 * 36 + 36 : std::max<size_t>(Dp, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);
         if (H.use_inertial) scr = std::max<size_t>(scr, 2 * (4 * 450 + 64));
         if (H.n_prior > 0) scr = std::max<size_t>(scr, 3 * 15 * (size_t)H.n_prior + 9 * (size_t)H.n_prior);
-        const size_t nb = (D + 3) / 4;
-        const size_t bytes = sizeof(double) * (nb * (nb + 1) / 2 * 16 + 4 * nb * 4 + nb * 16 + kMaxFrames * 36 + scr);
+        const size_t bytes = sizeof(double) * (nb * (nb + 1) / 2 * 16 + 4 * Dp + nb * 16 + (size_t)H.N * 36 + scr);
         best = std::max(best, bytes);
     }
     return best;
@@ -426,16 +426,17 @@ static int run_solve(Handle *h, int n, const StepCfg &c) {
         a.dbg = dbg;
     }
     cudaStream_t st = c.stream ? c.stream : h->stream;
-    const size_t smem = solve_smem(h, c.w0, n);
-    if (smem > 220 * 1024) return fail(h, PVIO_B200_EINVAL, "reduced system too large for shared memory");
-    // visual-only batches: the lean kernel (no IMU / prior / plane code), a narrow CTA per window so
-    // that many windows are resident per SM; otherwise the full kernel with a wide CTA
-    bool visual = true;
-    for (int i = c.w0; i < c.w0 + n; ++i) {
+    // visual-only batches: the lean kernel (no IMU / prior / plane code, no full staging), a narrow CTA
+    // per window so that many windows are resident per SM; otherwise the full kernel with a wide CTA
+    bool visual = n >= 64;
+    for (int i = c.w0; i < c.w0 + n && visual; ++i) {
         const WinHdr &H = h->hdr.h[i];
-        if (H.use_inertial || H.n_ptracks > 0) { visual = false; break; }
+        if (H.use_inertial || H.n_ptracks > 0) visual = false;
     }
-    if (visual && smem <= 48 * 1024 && n >= 64) solve_kernel_visual<<<n, 64, smem, st>>>(a);
+    size_t smem = solve_smem(h, c.w0, n, visual);
+    if (visual && smem > 48 * 1024) { visual = false; smem = solve_smem(h, c.w0, n, false); }
+    if (smem > 220 * 1024) return fail(h, PVIO_B200_EINVAL, "reduced system too large for shared memory");
+    if (visual) solve_kernel_visual<<<n, 64, smem, st>>>(a);
     else solve_kernel<<<n, 256, smem, st>>>(a);
     ++h->launches;
     CK(h, cudaGetLastError());

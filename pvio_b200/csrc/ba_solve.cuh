@@ -479,7 +479,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     double *xs = hcorr + Dp;                                // [Dp] solution
     double *Linv = xs + Dp;                                 // [nb][16] inverses of the diagonal tiles
     double *T = Linv + nb * 16;                             // [N][36] change of variables
-    double *scr = T + kMaxFrames * 36;                      // scratch: IMU slabs / prior vectors
+    double *scr = T + N * 36;                               // scratch: staging / IMU slabs / prior vectors / reg copy
     __shared__ double cost_sm[4];
     __shared__ int flag_sm;
 
@@ -506,10 +506,76 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     __syncthreads();
 
     STAMP();   // 1: init done
-    // ---- vision blocks: H_delta[f,gf] = T_f^T X T_g.  Stage the xi-coordinate blocks in shared
-    // memory (coalesced), X <- X T_g in place, then T_f^T (X T_g) into the packed system.
     const int npairs = N * (N + 1) / 2;
     const int npairs_cap = a.Ncap * (a.Ncap + 1) / 2;
+    if (!kFull) {
+        // Lean path (batched visual-only windows): no full staging of the xi blocks -- groups of 6 threads
+        // pull one 6x6 block at a time through a small shared buffer, so that ~9 windows fit per SM.
+        const double *Hred = a.Hred + (size_t)w * npairs_cap * 36;
+        const double *Hdd = a.Hdd + (size_t)w * a.Ncap * 36;
+        const double *gdir = a.gdir + (size_t)w * a.Ncap * 6;
+        const double *gred = a.gred + (size_t)w * a.Ncap * 6;
+        double *Ms = scr + Dp;                       // [G][36]
+        for (int e = tid; e < N * 6; e += nt) {      // direct diagonal diag(T_f^T Xd T_f)
+            const int f = e / 6, i = e - f * 6;
+            const double *Tf = T + f * 36, *X = Hdd + f * 36;
+            double sd = 0.0;
+            for (int aa = 0; aa < 6; ++aa) {
+                double t = 0.0;
+                for (int bb = 0; bb < 6; ++bb) t += X[aa * 6 + bb] * Tf[bb * 6 + i];
+                sd += Tf[aa * 6 + i] * t;
+            }
+            hcorr[f * stride + i] = sd;
+        }
+        const int G = nt / 6;
+        const int q = tid / 6, i6 = tid - q * 6;
+        for (int p0 = 0; p0 < npairs; p0 += G) {
+            const int p = p0 + q;
+            const bool act = q < G && p < npairs;
+            int f = 0, gf = 0;
+            if (act) {
+                while ((f + 1) * (f + 2) / 2 <= p) ++f;
+                gf = p - f * (f + 1) / 2;
+                const double *X = Hred + p * 36 + i6 * 6, *Tg = T + gf * 36;
+                double x[6];
+#pragma unroll
+                for (int bb = 0; bb < 6; ++bb) x[bb] = X[bb];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int bb = 0; bb < 6; ++bb) v += x[bb] * Tg[bb * 6 + j];
+                    Ms[q * 36 + i6 * 6 + j] = v;       // M = X T_g, row i6
+                }
+            }
+            __syncthreads();
+            if (act) {
+                const double *Tf = T + f * 36;
+                const int j = i6;                        // this thread produces column j of T_f^T M
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    if (f == gf && j > i) continue;
+                    double sv = 0.0;
+#pragma unroll
+                    for (int aa = 0; aa < 6; ++aa) sv += Tf[aa * 6 + i] * Ms[q * 36 + aa * 6 + j];
+                    const int gi = f * stride + i, gj = gf * stride + j;
+                    A[tri(gi, gj)] = sv;
+                    if (f == gf && i == j) hcorr[gi] -= sv;
+                }
+            }
+            __syncthreads();
+        }
+        for (int e = tid; e < N * 6; e += nt) {
+            const int f = e / 6, i = e - f * 6;
+            const double *Tf = T + f * 36;
+            double sr = 0.0, sd = 0.0;
+            for (int aa = 0; aa < 6; ++aa) { sr += Tf[aa * 6 + i] * gred[f * 6 + aa]; sd += Tf[aa * 6 + i] * gdir[f * 6 + aa]; }
+            g[f * stride + i] = sr;
+            gu[f * stride + i] = sd;
+        }
+    } else
+    // ---- vision blocks: H_delta[f,gf] = T_f^T X T_g.  Stage the xi-coordinate blocks in shared
+    // memory (coalesced), X <- X T_g in place, then T_f^T (X T_g) into the packed system.
     {
         const double *Hred = a.Hred + (size_t)w * npairs_cap * 36;
         const double *Hdd = a.Hdd + (size_t)w * a.Ncap * 36;
