@@ -112,6 +112,8 @@ typedef struct pvio_b200_options {
     int32_t alias_bias;     /* 1: bias linearisation point follows the accepted state (quirk Q1,
                                the reference's behaviour); 0: frozen at solve entry          */
     int32_t run_postpass;   /* 1: run the landmark depth / pixel-error pass :277-296         */
+    double initial_trust_region_radius; /* 0: ceres default 1e4 (PVIO does not override it);
+                               other values exist to exercise the dogleg legs in tests         */
 } pvio_b200_options;
 
 #define PVIO_B200_TERM_CONVERGENCE 0

@@ -392,7 +392,7 @@ def gn_step(win, st, mu=MIN_MU, scale=None, schur=False):
 
 
 # --------------------------------------------------------------- Ceres trust-region loop
-def solve(win, st0, max_iter=10, verbose=False, alias_bias=True):
+def solve(win, st0, max_iter=10, verbose=False, alias_bias=True, radius0=1.0e4):
     """Restatement of ceres::Solve as PVIO configures it (SPARSE_SCHUR is an exact solver,
     so only the minimiser logic matters): TrustRegionMinimizer + TRADITIONAL_DOGLEG,
     jacobi_scaling=true, initial radius 1e4, min_relative_decrease 1e-3, function /
@@ -414,7 +414,7 @@ def solve(win, st0, max_iter=10, verbose=False, alias_bias=True):
     idx = np.where(free)[0]
     H, g, cost = normal_equations(win, st)
     scale = jacobi_scaling(H)
-    radius, mu, reuse = 1.0e4, MIN_MU, False
+    radius, mu, reuse = radius0, MIN_MU, False
     summ = dict(iterations=0, initial_cost=cost, final_cost=cost, termination='NO_CONVERGENCE',
                 usable=True, steps=[], accepted=[])
     if np.max(np.abs(g[idx])) <= 1e-10:

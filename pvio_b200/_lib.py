@@ -45,7 +45,7 @@ class CState(C.Structure):
 
 class COptions(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("max_time", C.c_double), ("alias_bias", C.c_int32),
-                ("run_postpass", C.c_int32)]
+                ("run_postpass", C.c_int32), ("initial_trust_region_radius", C.c_double)]
 
 
 class CSummary(C.Structure):

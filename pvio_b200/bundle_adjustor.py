@@ -47,10 +47,10 @@ class BundleAdjustor:
         return int(self.lib.pvio_b200_kernel_launches(self.h))
 
     # ---- reference-facing calls ------------------------------------------------------
-    def solve(self, win, st, max_iterations=10, max_time=1e6, alias_bias=True, postpass=True):
+    def solve(self, win, st, max_iterations=10, max_time=1e6, alias_bias=True, postpass=True, initial_radius=0.0):
         """BundleAdjustor::solve (bundle_adjustor.cpp:308-319).  Returns (State, summary dict)."""
         pa = _lib.PackedArgs(win, st)
-        opt = _lib.COptions(max_iterations, max_time, 1 if alias_bias else 0, 1 if postpass else 0)
+        opt = _lib.COptions(max_iterations, max_time, 1 if alias_bias else 0, 1 if postpass else 0, initial_radius)
         sm = _lib.CSummary()
         valid = np.zeros(max(win.M, 1), dtype=np.uint8)
         quality = np.zeros(max(win.M, 1))

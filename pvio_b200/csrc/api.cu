@@ -80,7 +80,7 @@ __global__ void finalize_kernel(WinCtrl *ctrl, const double *acc, const double *
                                 const WinHdr *hdr, int Ncap, int Mcap, double beta, int w0) {
     const int w = blockIdx.x + w0;
     WinCtrl &c = ctrl[w];
-    const double *a = acc + (size_t)w * 8;
+    const double *a = acc + (size_t)w * kAcc;
     if (threadIdx.x == 0) {
         c.cand_cost_vis = a[0];
         c.cand_cost = a[0] + aux_cost[w];
@@ -334,7 +334,10 @@ int pack_and_upload(Handle *h, const pvio_b200_window *w, const pvio_b200_state 
 // ------------------------------------------------------------------------ launches
 struct StepCfg {
     double mu = -1.0;          // < 0: per-window ctrl.mu
-    double beta = 1.0;
+    double beta = 1.0;             // truncated Gauss-Newton step: step = beta * dx_gn
+    double step_a = 0.0;           // dogleg: step = step_b * dx_gn - step_a * v  (step_b defaults to beta)
+    double step_b = -1.0;
+    int update_grid = 0;           // > 0: CTAs per window of the update sweep
     int apply = 0;
     int compute_scale = 1;
     int alias_bias = 0;
@@ -408,7 +411,7 @@ static int run_solve(Handle *h, int n, const StepCfg &c) {
     a.prior_x0 = h->prior_x0.d;
     a.plane_param = h->plane_param.d; a.pt_plane = h->pt_plane.d; a.pt_begin = h->pt_begin.d; a.pt_frame = h->pt_frame.d;
     a.pt_z = h->pt_z.d; a.Pcap = h->Pcap; a.Tcap = h->Tcap; a.Ocap = h->Ocap;
-    a.pose_scale = h->pose_scale.d; a.dx_pose = h->dx_pose.d;
+    a.pose_scale = h->pose_scale.d; a.dx_pose = h->dx_pose.d; a.v_pose = h->v_pose.d;
     a.Hfull = c.dump ? h->Hfull.d : nullptr; a.gfull = c.dump ? h->gfull.d : nullptr;
     a.Ncap = h->Ncap; a.compute_scale = c.compute_scale; a.mu_override = c.mu; a.w0 = c.w0;
     a.dbg = nullptr;
@@ -443,18 +446,7 @@ static int run_solve(Handle *h, int n, const StepCfg &c) {
     return 0;
 }
 
-static int run_update(Handle *h, int n, const StepCfg &c) {
-    cudaStream_t st = c.stream ? c.stream : h->stream;
-    CK(h, cudaMemsetAsync(h->acc.d + (size_t)8 * c.w0, 0, sizeof(double) * 8 * n, st));
-    UpdArgs u;
-    u.hdr = h->hdr.d; u.cst = h->cst.d; u.obs = h->obs.d; u.lms = h->lms.d; u.rho = h->rho.d; u.frames = h->frames.d;
-    u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.dx_pose = h->dx_pose.d;
-    u.rho_cand = h->rho_cand.d; u.frames_cand = h->frames_cand.d; u.dx_lm = h->dx_lm.d; u.acc = h->acc.d;
-    u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.beta = c.beta; u.w0 = c.w0;
-    const int gx = lin_grid_x(h, n);
-    if (n * 2 < h->sm_count) update_cost_kernel<true><<<dim3(gx, n), kLinThreads, 0, st>>>(u);
-    else update_tpl_kernel<true><<<dim3(gx, n), kLinThreads, 0, st>>>(u);
-    ++h->launches;
+static CostArgs make_cost_args(Handle *h, const StepCfg &c) {
     CostArgs k;
     memset(&k, 0, sizeof(k));
     k.hdr = h->hdr.d; k.cst = h->cst.d; k.frames_cand = h->frames_cand.d; k.frames_cur = h->frames.d;
@@ -463,6 +455,44 @@ static int run_update(Handle *h, int n, const StepCfg &c) {
     k.plane_param = h->plane_param.d; k.pt_plane = h->pt_plane.d; k.pt_begin = h->pt_begin.d; k.pt_frame = h->pt_frame.d;
     k.pt_z = h->pt_z.d; k.Pcap = h->Pcap; k.Tcap = h->Tcap; k.Ocap = h->Ocap; k.Ncap = h->Ncap; k.out = h->aux_cost.d;
     k.w0 = c.w0;
+    return k;
+}
+
+// |J v|^2 for the Cauchy point of the dogleg step (acc slots 9 and 10); single window path
+static int run_jv(Handle *h, const StepCfg &c) {
+    cudaStream_t st = c.stream ? c.stream : h->stream;
+    CK(h, cudaMemsetAsync(h->acc.d + 9, 0, sizeof(double) * 2, st));
+    UpdArgs u;
+    memset(&u, 0, sizeof(u));
+    u.hdr = h->hdr.d; u.cst = h->cst.d; u.obs = h->obs.d; u.lms = h->lms.d; u.rho = h->rho.d; u.frames = h->frames.d;
+    u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.dx_pose = h->dx_pose.d; u.acc = h->acc.d;
+    u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.w0 = 0; u.v_pose = h->v_pose.d;
+    jv_vision_kernel<true><<<dim3(16, 1), kLinThreads, 0, st>>>(u);
+    JvAuxArgs ja;
+    ja.c = make_cost_args(h, c);
+    ja.v_pose = h->v_pose.d; ja.acc = h->acc.d;
+    jv_aux_kernel<<<1, 64, sizeof(double) * 15 * kMaxFrames, st>>>(ja);
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+static int run_update(Handle *h, int n, const StepCfg &c) {
+    cudaStream_t st = c.stream ? c.stream : h->stream;
+    CK(h, cudaMemsetAsync(h->acc.d + (size_t)kAcc * c.w0, 0, sizeof(double) * kAcc * n, st));
+    UpdArgs u;
+    u.hdr = h->hdr.d; u.cst = h->cst.d; u.obs = h->obs.d; u.lms = h->lms.d; u.rho = h->rho.d; u.frames = h->frames.d;
+    u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.dx_pose = h->dx_pose.d;
+    u.rho_cand = h->rho_cand.d; u.frames_cand = h->frames_cand.d; u.dx_lm = h->dx_lm.d; u.acc = h->acc.d;
+    u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.w0 = c.w0;
+    u.step_a = c.step_a; u.step_b = c.step_b >= 0.0 ? c.step_b : c.beta; u.v_pose = h->v_pose.d;
+    const int gx = lin_grid_x(h, n);
+    // few windows: one chunk per CTA-warp so that a single window spreads over 16 CTAs
+    const int ugx = n * 2 < h->sm_count ? 16 : 1;
+    (void)gx;
+    update_tpl_kernel<true><<<dim3(ugx, n), kLinThreads, 0, st>>>(u);
+    ++h->launches;
+    CostArgs k = make_cost_args(h, c);
     aux_cost_kernel<<<n, 64, sizeof(double) * 15 * kMaxFrames, st>>>(k);
     ++h->launches;
     finalize_kernel<<<n, 128, 0, st>>>(h->ctrl.d, h->acc.d, h->aux_cost.d, c.apply, h->frames.d, h->frames_cand.d,
@@ -540,7 +570,7 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     TRY(alloc(h, h->rho_cand, W * M, false)); TRY(alloc(h, h->frames_cand, W * N * kFrameStride, false));
     TRY(alloc(h, h->lm_scale, W * M, false)); TRY(alloc(h, h->lm_aux, W * M, false));
     TRY(alloc(h, h->dx_lm, W * M, true)); TRY(alloc(h, h->dx_pose, W * N * 15, true));
-    TRY(alloc(h, h->pose_scale, W * N * 15, false));
+    TRY(alloc(h, h->pose_scale, W * N * 15, false)); TRY(alloc(h, h->v_pose, W * N * 15, false));
     {   // the reduced-system outputs of the linearise kernel live in ONE allocation so that the
         // multi-CTA-per-window mode (atomic accumulation) needs a single memset per launch
         const size_t n_sys = W * (npc * 36 + N * 36 + N * 6 + N * 6 + 1);
@@ -549,7 +579,7 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
         h->gdir.d = h->Hdd.d + W * N * 36; h->gdir.n = 0;
         h->gred.d = h->gdir.d + W * N * 6; h->gred.n = 0;
         h->cost_vis.d = h->gred.d + W * N * 6; h->cost_vis.n = 0;
-    } TRY(alloc(h, h->acc, W * 8, true)); TRY(alloc(h, h->aux_cost, W, false));
+    } TRY(alloc(h, h->acc, W * kAcc, true)); TRY(alloc(h, h->aux_cost, W, false));
     TRY(alloc(h, h->Hfull, (15 * N) * (15 * N), true)); TRY(alloc(h, h->gfull, 15 * N, true));
     // unallocated optional buffers still need valid (dummy) device pointers? kernels never touch them
     h->perm.resize(W); h->perm_identity.assign(W, 1); h->slot_M.assign(W, 0); h->slot_N.assign(W, 0); h->slot_K.assign(W, 0);
@@ -573,7 +603,7 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     klt_free(h);
     release(h->hdr); release(h->cst); release(h->obs); release(h->lms); release(h->rho); release(h->frames);
     release(h->ctrl); release(h->rho_cand); release(h->frames_cand); release(h->lm_scale); release(h->lm_aux);
-    release(h->dx_lm); release(h->dx_pose); release(h->pose_scale); release(h->Hred);
+    release(h->dx_lm); release(h->dx_pose); release(h->pose_scale); release(h->v_pose); release(h->Hred);
     release(h->acc); release(h->aux_cost);
     release(h->Hfull); release(h->gfull);
     release(h->imu_idx); release(h->imu_data); release(h->prior_frames); release(h->prior_S); release(h->prior_L);
@@ -775,9 +805,9 @@ int pvio_b200_ba_gn_step(pvio_b200_handle hh, const pvio_b200_window *w, const p
 
 // Trust-region loop: the minimiser logic of ceres::Solve as PVIO configures it
 // (solver_options.h:26-33; TrustRegionMinimizer + dogleg defaults of Ceres 1.14), driven from
-// the host with one small device->host read per iteration.  Step truncation scales the
-// Gauss-Newton step to the trust radius (the Cauchy-point leg of TRADITIONAL_DOGLEG is not
-// implemented yet -- see DESIGN.md "Known deviations").
+// the host with one small device->host read per iteration.  When the Gauss-Newton step leaves the
+// trust region the Cauchy point is computed with one extra J.v sweep and the traditional dogleg
+// interpolation is applied, as dogleg_strategy.cc does.
 int pvio_b200_ba_solve(pvio_b200_handle hh, const pvio_b200_window *w, pvio_b200_state *s,
                        const pvio_b200_options *opt, pvio_b200_summary *summary, uint8_t *valid, double *quality) {
     Handle *h = reinterpret_cast<Handle *>(hh);
@@ -789,7 +819,7 @@ int pvio_b200_ba_solve(pvio_b200_handle hh, const pvio_b200_window *w, pvio_b200
     TRY(pack_window(h, 0, w, s));
     TRY(upload(h, 1));
     CK(h, cudaEventRecord(h->ev0, h->stream));
-    double radius = 1e4, mu = 1e-8;
+    double radius = (opt && opt->initial_trust_region_radius > 0) ? opt->initial_trust_region_radius : 1e4, mu = 1e-8;
     bool reuse = false;
     StepCfg c;
     c.apply = 0; c.alias_bias = alias; c.compute_scale = 1;
@@ -798,14 +828,14 @@ int pvio_b200_ba_solve(pvio_b200_handle hh, const pvio_b200_window *w, pvio_b200
     sm.termination = PVIO_B200_TERM_NO_CONVERGENCE; sm.usable = 1;
     auto read_ctrl = [&](WinCtrl &o, double *acc) -> int {
         CK(h, cudaMemcpyAsync(h->ctrl.h, h->ctrl.d, sizeof(WinCtrl), cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(h->acc.h, h->acc.d, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(h->acc.h, h->acc.d, sizeof(double) * kAcc, cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
         o = h->ctrl.h[0];
-        memcpy(acc, h->acc.h, sizeof(double) * 8);
+        memcpy(acc, h->acc.h, sizeof(double) * kAcc);
         return 0;
     };
     WinCtrl ct;
-    double acc[8];
+    double acc[kAcc];
     int it = 0;
     bool first = true;
     double cost = 0.0;
@@ -829,15 +859,45 @@ int pvio_b200_ba_solve(pvio_b200_handle hh, const pvio_b200_window *w, pvio_b200
             --it;
             continue;
         }
+        // ---- DoglegStrategy::ComputeStep (TRADITIONAL_DOGLEG), all norms in the diag-scaled space
         const double gn_norm = std::sqrt(ct.gn_norm2 + acc[3]);
-        double beta = 1.0, step_norm = gn_norm;
+        const double gdx = ct.g_dot_dx + acc[1];                 // g . dx_gn  (= grad . gn in scaled space)
+        const double rdx = ct.dx_reg_dx + acc[2];                // dx_gn^T (mu D) dx_gn
+        double sa = 0.0, sb = 1.0, step_norm = gn_norm;
+        double grad2 = 0.0, v_rd = 0.0, jv2 = 0.0;
         if (gn_norm > radius) {
-            beta = radius / gn_norm; step_norm = radius;
-            c.beta = beta; c.skip_linearize = true;
+            // Cauchy point: alpha = |grad|^2 / |J S D^-1 grad|^2 needs one J.v sweep
+            TRY(run_jv(h, c));
+            double acc2[kAcc];
+            WinCtrl ct2;
+            TRY(read_ctrl(ct2, acc2));
+            grad2 = ct.grad2 + acc[7];
+            v_rd = ct.v_reg_dx + acc[8];
+            jv2 = acc2[9] + acc2[10];
+            const double g_norm = std::sqrt(grad2);
+            const double alpha = grad2 / jv2;
+            if (g_norm * alpha >= radius) {                       // scaled steepest descent to the boundary
+                sa = radius / g_norm; sb = 0.0;
+            } else {                                              // dogleg interpolation (dogleg_strategy.cc)
+                const double b_dot_a = -alpha * gdx;
+                const double a2 = (alpha * g_norm) * (alpha * g_norm);
+                const double bma2 = a2 - 2.0 * b_dot_a + gn_norm * gn_norm;
+                const double cc = b_dot_a - a2;
+                const double dd = std::sqrt(cc * cc + bma2 * (radius * radius - a2));
+                const double beta = cc <= 0 ? (dd - cc) / bma2 : (radius * radius - a2) / (dd + cc);
+                sa = alpha * (1.0 - beta); sb = beta;
+            }
+            step_norm = radius;
+            c.step_a = sa; c.step_b = sb; c.skip_linearize = true;
             TRY(run_step(h, 1, c));
             TRY(read_ctrl(ct, acc));
+            c.step_a = 0.0; c.step_b = -1.0;
         }
-        const double model_change = ct.model_change;
+        // model cost change -(g.s + s^T H s / 2) of s = sb dx_gn - sa v, using H dx_gn = -g - (mu D) dx_gn
+        const double dHd = -gdx - rdx, vHd = -grad2 - v_rd;
+        const double sHs = sb * sb * dHd - 2.0 * sa * sb * vHd + sa * sa * jv2;
+        const double model_change = -(sb * gdx - sa * grad2) - 0.5 * sHs;
+        const double beta = sb;
         if (!(model_change > 0.0)) { radius *= 0.5; reuse = true; continue; }       // invalid step
         const double x_norm = std::sqrt(ct.xnorm2 + acc[5]);
         const double step_amb = std::sqrt(acc[6] + acc[4]);

@@ -37,7 +37,7 @@ struct Handle {
     DevBuf<LmRec> lms;
     DevBuf<double> rho, frames;
     DevBuf<WinCtrl> ctrl;
-    DevBuf<double> rho_cand, frames_cand, lm_scale, dx_lm, dx_pose, pose_scale;
+    DevBuf<double> rho_cand, frames_cand, lm_scale, dx_lm, dx_pose, pose_scale, v_pose;
     DevBuf<LmAux> lm_aux;
     DevBuf<double> Hred, Hdd, gdir, gred, cost_vis, acc, aux_cost;
     DevBuf<double> Hfull, gfull;                 // debug dump (single window only)

@@ -49,6 +49,7 @@ struct SolveArgs {
     // scaling / outputs
     double *pose_scale;        // [W][15*Ncap]
     double *dx_pose;           // [W][Ncap][15]
+    double *v_pose;            // [W][Ncap][15] scaled steepest-descent direction S^2 g / clamp(S^2 diag H)
     double *Hfull;             // optional [W][(15 Ncap)^2] dump of the reduced system (delta coords, before regularisation)
     double *gfull;             // optional [W][15 Ncap]
     int Ncap;
@@ -835,7 +836,9 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         dxo[i] = (ok && c < stride) ? xs[f * stride + c] : 0.0;
     }
     {
-        double gdx = 0.0, rdx = 0.0, gn2 = 0.0, dx2 = 0.0, gmax = 0.0;
+        double gdx = 0.0, rdx = 0.0, gn2 = 0.0, dx2 = 0.0, gmax = 0.0, g2 = 0.0, vrd = 0.0;
+        double *vpo = a.v_pose + (size_t)w * a.Ncap * 15;
+        for (int i = tid; i < N * 15; i += nt) vpo[i] = 0.0;
         for (int i = tid; i < D; i += nt) {
             const int f = i / stride, c = i - f * stride;
             const bool m = ((fixed_mask >> f) & 1) && c < 6;
@@ -844,23 +847,32 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             const double sc = scale[i];
             double d2 = sc * sc * hcorr[i];
             d2 = fmin(fmax(d2, 1.0e-6), 1.0e32);
+            // NOTE: the reduced gradient g and the unreduced gu differ only through the Schur term;
+            // g . dx over the full system is completed by the landmark sweep (acc[1])
+            const double v = sc * sc * gu[i] / d2;
+            vpo[f * 15 + c] = v;
             gdx += g[i] * dx;
             rdx += reg_keep[i] * dx * dx;
             gn2 += d2 * (dx / sc) * (dx / sc);
             dx2 += dx * dx;
+            g2 += v * gu[i];
+            vrd += v * reg_keep[i] * dx;
             gmax = fmax(gmax, fabs(gu[i]));
         }
         __syncthreads();
         double *red = A;                 // the factor is no longer needed
-        if (tid < D) { red[tid * 5 + 0] = gdx; red[tid * 5 + 1] = rdx; red[tid * 5 + 2] = gn2; red[tid * 5 + 3] = dx2; red[tid * 5 + 4] = gmax; }
+        if (tid < D) { red[tid * 7 + 0] = gdx; red[tid * 7 + 1] = rdx; red[tid * 7 + 2] = gn2; red[tid * 7 + 3] = dx2; red[tid * 7 + 4] = gmax;
+                       red[tid * 7 + 5] = g2; red[tid * 7 + 6] = vrd; }
         __syncthreads();
         if (tid == 0) {
-            gdx = rdx = gn2 = dx2 = gmax = 0.0;
+            gdx = rdx = gn2 = dx2 = gmax = g2 = vrd = 0.0;
             const int nred = min(nt, D);
             for (int t = 0; t < nred; ++t) {
-                gdx += red[t * 5]; rdx += red[t * 5 + 1]; gn2 += red[t * 5 + 2]; dx2 += red[t * 5 + 3];
-                gmax = fmax(gmax, red[t * 5 + 4]);
+                gdx += red[t * 7]; rdx += red[t * 7 + 1]; gn2 += red[t * 7 + 2]; dx2 += red[t * 7 + 3];
+                gmax = fmax(gmax, red[t * 7 + 4]); g2 += red[t * 7 + 5]; vrd += red[t * 7 + 6];
             }
+            ctrl.grad2 = g2;
+            ctrl.v_reg_dx = vrd;
             // |x|^2 over the ambient parameter blocks (ceres takes norms of the 4-vector quaternion)
             double x2 = 0.0;
             for (int f = 0; f < N; ++f) {
@@ -976,6 +988,92 @@ static __global__ void aux_cost_kernel(CostArgs a) {
     }
     __syncthreads();
     if (tid == 0) a.out[w] = acc;
+}
+
+// |J v|^2 over the IMU / prior / plane blocks (loss-corrected), one CTA per window: the non-vision
+// part of the Cauchy-point denominator of the dogleg step.
+struct JvAuxArgs {
+    CostArgs c;               // same inputs as aux_cost_kernel (frames_cand unused; frames_cur = current state)
+    const double *v_pose;     // [W][Ncap][15]
+    double *acc;              // [W][kAcc], slot 10
+};
+
+static __global__ void jv_aux_kernel(JvAuxArgs ja) {
+    const CostArgs &a = ja.c;
+    const int w = blockIdx.x + a.w0;
+    const WinHdr &H = a.hdr[w];
+    const WinConst &wc = a.cst[w];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double *fr = a.frames_cur + (size_t)w * a.Ncap * kFrameStride;
+    const double *v = ja.v_pose + (size_t)w * a.Ncap * 15;
+    __shared__ double acc;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *ev = reinterpret_cast<double *>(smem_raw);      // [15 n_prior] E v
+    if (tid == 0) acc = 0.0;
+    __syncthreads();
+    if (H.use_inertial) {
+        const int32_t *idx = a.imu_idx + (size_t)w * a.Ncap * 2;
+        const double *recs = a.imu_data + (size_t)w * a.Ncap * kImuStride;
+        for (int n = tid; n < H.n_imu; n += nt) {
+            double r[15], J[450], u[15];
+            const double *rec = recs + (size_t)n * kImuStride;
+            const int fi = idx[2 * n], fj = idx[2 * n + 1];
+            imu_factor_raw(fr + fi * kFrameStride, fr + fj * kFrameStride, rec, wc, a.alias_bias, r, J);
+            for (int k = 0; k < 15; ++k) {
+                double s = 0.0;
+                for (int c = 0; c < 15; ++c) s += J[k * 30 + c] * v[fi * 15 + c] + J[k * 30 + 15 + c] * v[fj * 15 + c];
+                u[k] = s;
+            }
+            double c2 = 0.0;
+            for (int i = 0; i < 15; ++i) {
+                double s = 0.0;
+                for (int k = 0; k < 15; ++k) s += rec[11 + i * 15 + k] * u[k];
+                c2 += s * s;
+            }
+            atomicAdd(&acc, c2);
+        }
+        if (H.n_prior > 0) {
+            const int n = H.n_prior, d = 15 * n, dcap = 15 * a.Ncap;
+            const int32_t *pf = a.prior_frames + (size_t)w * a.Ncap;
+            const double *S = a.prior_S + (size_t)w * dcap * dcap;
+            const double *x0 = a.prior_x0 + (size_t)w * a.Ncap * kFrameStride;
+            if (tid < n) {
+                double r15[15], Ji[9];
+                prior_frame_raw(fr + pf[tid] * kFrameStride, x0 + tid * kFrameStride, r15, Ji);
+                const double *vf = v + pf[tid] * 15;
+                for (int k = 0; k < 3; ++k) ev[15 * tid + k] = Ji[3 * k] * vf[0] + Ji[3 * k + 1] * vf[1] + Ji[3 * k + 2] * vf[2];
+                for (int k = 3; k < 15; ++k) ev[15 * tid + k] = vf[k];
+            }
+            __syncthreads();
+            double c2 = 0.0;
+            for (int i = tid; i < d; i += nt) {
+                double s = 0.0;
+                for (int k = 0; k < d; ++k) s += S[(size_t)i * d + k] * ev[k];
+                c2 += s * s;
+            }
+            atomicAdd(&acc, c2);
+        }
+    }
+    if (H.n_ptracks > 0) {
+        const int stride = 15;
+        const double *pl = a.plane_param + (size_t)w * a.Pcap * 4;
+        const int32_t *ptp = a.pt_plane + (size_t)w * a.Tcap;
+        const int32_t *ptb = a.pt_begin + (size_t)w * (a.Tcap + 1);
+        const int32_t *ptf = a.pt_frame + (size_t)w * a.Ocap;
+        const float *ptz = a.pt_z + (size_t)w * a.Ocap * 2;
+        const double cb = wc.cauchy_a * wc.cauchy_a;
+        for (int t = tid; t < H.n_ptracks; t += nt) {
+            const int b0 = ptb[t], K = ptb[t + 1] - b0;
+            double r, J[6 * kMaxFrames];
+            plane_factor(K, ptf + b0, ptz + 2 * b0, fr, wc, pl + 4 * ptp[t], wc.plane_sic, &r, J);
+            const double sc2 = 1.0 / (1.0 + r * r / cb);             // rho'
+            double s = 0.0;
+            for (int i = 0; i < 6 * K; ++i) s += J[i] * v[ptf[b0 + i / 6] * stride + (i % 6)];
+            atomicAdd(&acc, sc2 * s * s);
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && acc != 0.0) atomicAdd(ja.acc + (size_t)w * kAcc + 10, acc);
 }
 
 }  // namespace pvio

@@ -10,7 +10,8 @@ namespace pvio {
 constexpr int kMaxFrames = 16;      // PVIO_B200_MAX_FRAMES
 constexpr int kFrameStride = 16;    // doubles per frame state
 constexpr int kImuStride = 288;     // doubles per IMU factor record
-constexpr int kMaxChunks = 96;      // anchor-homogeneous chunks of <= 32 landmarks per window
+constexpr int kMaxChunks = 96;
+constexpr int kAcc = 16;            // doubles per window accumulated by the update / J.v sweeps      // anchor-homogeneous chunks of <= 32 landmarks per window
 
 struct ObsRec {                     // one reprojection residual block (non-anchor observation), 12 B
     float zx, zy;                   // normalised keypoint in the target frame
@@ -49,6 +50,7 @@ struct WinCtrl {                    // per-window solver state (device resident)
     double cost_vis, cand_cost_vis; // reprojection part accumulated by the sweeps
     double g_dot_dx, dx_reg_dx, gn_norm2, gmax, xnorm2, dxnorm2;
     double model_change;
+    double grad2, v_reg_dx;         // |D^-1 S g|^2 and v^T (mu D) dx over the pose block (dogleg)
     int32_t iteration, accepted, done, termination;
     int32_t solve_failed, have_scale, usable, pad;
 };

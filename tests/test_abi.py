@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported():
 def test_struct_layouts_match_header():
     # sizes that the C compiler produces for the header's structs (LP64)
     assert C.sizeof(_lib.CState) == 16
-    assert C.sizeof(_lib.COptions) == 24
+    assert C.sizeof(_lib.COptions) == 32
     assert C.sizeof(_lib.CSummary) == 56
     assert C.sizeof(_lib.CWindow) == 16 + 8 + 8 * (4 + 3 + 4 + 3 + 4 + 3) + 6 * 8 + 8 + 3 * 8 + 8 + 4 * 8 + 8 + 8 + 8 + 8 + 4 * 8
 

@@ -306,3 +306,22 @@ def test_edge_cases_ragged_and_extreme_sizes(ba):
     with pytest.raises(PvioB200Error):
         small.gn_step(w, st)
     small.close()
+
+
+def test_solve_dogleg_and_rejections_match_oracle(ba):
+    """With a small initial trust radius the Gauss-Newton step leaves the region: the Cauchy point
+    (one extra J.v sweep), the dogleg interpolation, the scaled-gradient leg and the radius updates of
+    TRADITIONAL_DOGLEG are exercised and must reproduce the oracle's iteration history."""
+    for maker, kw, r0 in ((synth.make_cfg2, dict(N=6, M=80, seed=21), 30.0),
+                          (synth.make_cfg2, dict(N=6, M=80, seed=22), 2.0),
+                          (synth.make_cfg3, dict(N=6, M=100, seed=23), 50.0),
+                          (synth.make_cfg4, dict(N=6, M=60, seed=24, tracks_per_plane=20), 20.0)):
+        w, st, _ = maker(**kw)
+        ref_state, ref_sum = bo.solve(w, st, max_iter=8, radius0=r0)
+        out, summ = ba.solve(w, st, max_iterations=8, initial_radius=r0)
+        print(r0, ref_sum['accepted'], ref_sum['iterations'], summ['iterations'], summ['accepted_steps'],
+              ref_sum['final_cost'], summ['final_cost'])
+        assert summ['iterations'] == ref_sum['iterations']
+        assert summ['accepted_steps'] == sum(ref_sum['accepted'])
+        assert abs(summ['final_cost'] - ref_sum['final_cost']) <= 1e-4 * ref_sum['final_cost']
+        assert np.linalg.norm(out.p - ref_state.p) < 2e-4 * max(np.linalg.norm(ref_state.p - st.p), 1e-3)
