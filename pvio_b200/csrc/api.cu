@@ -388,14 +388,13 @@ static int run_linearize(Handle *h, int n, const StepCfg &c) {
         h->kev.resize(1024);
         for (auto &e : h->kev) CK(h, cudaEventCreate(&e));
     }
-    CK(h, cudaEventRecord(h->kev[slot], st));
+    if (!h->capturing) CK(h, cudaEventRecord(h->kev[slot], st));
     // few windows: the group-per-landmark kernel exposes more parallelism per window (latency);
     // many windows: the thread-per-landmark kernel issues ~2x fewer instructions (throughput)
     // (the group kernel owns at most 256 Phase-B tiles: N <= 15)
     if (n * 2 < h->sm_count && h->Ncap * (h->Ncap + 1) <= kLinThreads) lin_schur_kernel<true><<<dim3(gx, n), kLinThreads, lin_smem_bytes(), st>>>(a);
     else lin_tpl_kernel<true><<<dim3(gx, n), kLinThreads, lin2_smem_bytes(h->Ncap), st>>>(a);
-    CK(h, cudaEventRecord(h->kev[slot + 1], st));
-    ++h->kev_count;
+    if (!h->capturing) { CK(h, cudaEventRecord(h->kev[slot + 1], st)); ++h->kev_count; }
     ++h->launches;
     CK(h, cudaGetLastError());
     return 0;
@@ -415,7 +414,7 @@ static int run_solve(Handle *h, int n, const StepCfg &c) {
     a.Hfull = c.dump ? h->Hfull.d : nullptr; a.gfull = c.dump ? h->gfull.d : nullptr;
     a.Ncap = h->Ncap; a.compute_scale = c.compute_scale; a.mu_override = c.mu; a.w0 = c.w0;
     a.dbg = nullptr;
-    if (getenv("PVIO_B200_SOLVE_STAMPS")) {       // profiling aid: clock64 stamps of the solve kernel's phases
+    if (!h->capturing && getenv("PVIO_B200_SOLVE_STAMPS")) {       // profiling aid: clock64 stamps of the solve kernel's phases
         static long long *dbg = nullptr;
         long long hst[16];
         if (!dbg) { cudaMalloc(&dbg, 16 * sizeof(long long)); cudaMemset(dbg, 0, 16 * sizeof(long long)); }
@@ -502,12 +501,47 @@ static int run_update(Handle *h, int n, const StepCfg &c) {
     return 0;
 }
 
-static int run_step(Handle *h, int n, const StepCfg &c) {
+static int run_step_raw(Handle *h, int n, const StepCfg &c, int kind) {
     if (!c.skip_linearize) {
         TRY(run_linearize(h, n, c));
         TRY(run_solve(h, n, c));
     }
-    TRY(run_update(h, n, c));
+    if (kind == 0) TRY(run_update(h, n, c));
+    return 0;
+}
+
+// kind 0: linearise + solve (unless skipped) + update sweep; kind 1: linearise + solve only.
+// Small launches (latency path) are captured once into a CUDA graph and replayed: 6-8 nodes cost one
+// launch instead of 6-8.
+static int run_step(Handle *h, int n, const StepCfg &c, int kind = 0) {
+    const bool graphable = h->use_graphs && n * 2 < h->sm_count && c.w0 == 0 && c.stream == nullptr && !c.dump &&
+                           !getenv("PVIO_B200_SOLVE_STAMPS");
+    if (!graphable) return run_step_raw(h, n, c, kind);
+    const WinHdr &H = h->hdr.h[0];
+    int shape = 0;
+    for (int i = 0; i < n; ++i) shape = shape * 31 + h->hdr.h[i].N * 4 + h->hdr.h[i].use_inertial * 2 + (h->hdr.h[i].n_ptracks > 0);
+    Handle::GraphKey key(n, shape, H.N, kind, c.compute_scale, c.skip_linearize ? 1 : 0, c.apply, c.alias_bias,
+                         (int)(solve_smem(h, 0, n, false) >> 4), c.mu, c.step_a, c.step_b >= 0.0 ? c.step_b : c.beta);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+        const int64_t l0 = h->launches;
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
+        CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        h->capturing = true;
+        const int rc = run_step_raw(h, n, c, kind);
+        h->capturing = false;
+        const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(h, PVIO_B200_ECUDA, "cudaStreamEndCapture", e);
+        CK(h, cudaGraphInstantiate(&ge, g, 0));
+        cudaGraphDestroy(g);
+        const int nl = (int)(h->launches - l0);
+        h->launches = l0;
+        it = h->graphs.emplace(key, std::make_pair(ge, nl)).first;
+    }
+    CK(h, cudaGraphLaunch(it->second.first, h->stream));
+    h->launches += it->second.second;
     return 0;
 }
 
@@ -609,6 +643,7 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     release(h->imu_idx); release(h->imu_data); release(h->prior_frames); release(h->prior_S); release(h->prior_L);
     release(h->prior_e); release(h->prior_x0);
     release(h->plane_param); release(h->pt_plane); release(h->pt_begin); release(h->pt_frame); release(h->pt_z);
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
     for (auto &e : h->kev) cudaEventDestroy(e);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evk0); cudaEventDestroy(h->evk1);
     for (auto &e : h->ev_up) cudaEventDestroy(e);
@@ -655,7 +690,7 @@ int pvio_b200_timer_stop(pvio_b200_handle hh, float *ms) {
 int pvio_b200_last_kernel_ms(pvio_b200_handle hh, int which, float *ms) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (which < 0) { h->kev_count = 0; if (ms) *ms = 0.f; return 0; }
-    if (h->kev_count == 0) return fail(h, PVIO_B200_EINVAL, "no linearise launch recorded");
+    if (h->kev_count == 0) { *ms = 0.f; return 0; }     // graph-replayed launches are not individually timed
     CK(h, cudaStreamSynchronize(h->stream));
     const int n = which == 0 ? 1 : std::min(h->kev_count, 512);
     double tot = 0.0;
@@ -921,8 +956,7 @@ int pvio_b200_ba_solve(pvio_b200_handle hh, const pvio_b200_window *w, pvio_b200
                 g.mu = mu; g.beta = 1.0; g.skip_linearize = false;
                 // peek: linearise + solve only, to read |g|_inf and the re-evaluated cost (ceres re-evaluates
                 // the cost at the accepted point together with the Jacobian)
-                TRY(run_linearize(h, 1, g));
-                TRY(run_solve(h, 1, g));
+                TRY(run_step(h, 1, g, 1));
                 TRY(read_ctrl(ct, acc));
                 cost = ct.cost;
                 reuse = true;                // the next iteration reuses this linearisation

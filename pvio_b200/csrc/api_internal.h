@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 #include "../../include/pvio_b200.h"
 #include "ba_types.h"
@@ -58,6 +60,12 @@ struct Handle {
     // ring of event pairs around every linearise+Schur launch (roofline timing without host syncs)
     std::vector<cudaEvent_t> kev;
     int kev_count = 0;
+    // CUDA graphs of the single-window launch sequences (latency path), keyed by everything that
+    // shapes the launches; replayed on later calls (device buffers are persistent)
+    typedef std::tuple<int, int, int, int, int, int, int, int, int, double, double, double> GraphKey;
+    std::map<GraphKey, std::pair<cudaGraphExec_t, int>> graphs;
+    bool capturing = false;
+    bool use_graphs = true;
     KltState *klt = nullptr;
 };
 

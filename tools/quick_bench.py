@@ -23,7 +23,7 @@ for n in ([1, 8, 64, 512, W] if W >= 512 else [1, W]):
     lin = ba.last_kernel_ms()
     bytes_alg = 16 * w.K + 16 * w.M + 64 * w.N + 4 * (48 * 48 + 48) + 4 * w.M
     print(f"n={n}: {ms*1e3:.1f} us/step, {n/ms*1e3:.0f} window-iters/s, lin kernel {lin*1e3:.1f} us, "
-          f"alg GB/s (whole step) {bytes_alg*n/ms/1e6:.1f}, lin-only {bytes_alg*n/lin/1e6:.1f}")
+          f"alg GB/s (whole step) {bytes_alg*n/ms/1e6:.1f}, lin-only {bytes_alg*n/max(lin,1e-9)/1e6:.1f}")
 t = time.time()
 dx, costs = ba.batch_gn_step_host(W, 15 * w.N + w.M)
 print('e2e host step s', time.time() - t, costs[0])
