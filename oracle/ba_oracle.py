@@ -392,35 +392,26 @@ def gn_step(win, st, mu=MIN_MU, scale=None, schur=False):
 
 
 # --------------------------------------------------------------- Ceres trust-region loop
-def solve(win, st0, max_iter=10, verbose=False, alias_bias=True, radius0=1.0e4):
-    """Restatement of ceres::Solve as PVIO configures it (SPARSE_SCHUR is an exact solver,
-    so only the minimiser logic matters): TrustRegionMinimizer + TRADITIONAL_DOGLEG,
-    jacobi_scaling=true, initial radius 1e4, min_relative_decrease 1e-3, function /
-    gradient / parameter tolerances 1e-6 / 1e-10 / 1e-8, max_num_iterations = max_iter.
-    Quirk Q1 (SURVEY 8a): the IMU bias linearisation point aliases the parameter
-    (preintegration_error_cost.h:57-58 reads frame_i->motion, which ceres refreshes after
-    every successful iteration because update_state_every_iteration=true), so with
-    alias_bias=True bg0/ba0 follow the accepted state and only the current step's bias
-    change is ever applied to the pre-integrated deltas.  alias_bias=False freezes the
-    linearisation point at solve entry (the proper first-order correction).  The exact
-    point inside a ceres iteration at which the user state is refreshed (before or after
-    the re-linearisation of an accepted step) cannot be verified without Ceres; this
-    restatement refreshes BEFORE re-linearising.  PARITY UNPINNED (see module docstring).
-    Returns (state, summary dict)."""
-    st = st0.copy()
-    alias = alias_bias and win.use_inertial
-    win = win.with_bias_lin_point(st) if alias else win
-    free = free_mask(win)
-    idx = np.where(free)[0]
-    H, g, cost = normal_equations(win, st)
+def trust_region(normal, cost_fn, plus, ambient, x0, idx, ndim, max_iter=10, radius0=1.0e4, verbose=False,
+                 on_accept=None):
+    """Generic restatement of ceres' TrustRegionMinimizer + TRADITIONAL_DOGLEG (Ceres 1.14, options as
+    PVIO sets them, estimation/ceres/solver_options.h:26-33): jacobi_scaling=true fixed at iteration
+    0, initial radius 1e4, mu in [1e-8, 1] x10 on linear-solver failure, min_relative_decrease 1e-3,
+    function / gradient / parameter tolerances 1e-6 / 1e-10 / 1e-8.
+      normal(x) -> (H, g, cost) dense local normal equations;  cost_fn(x) -> cost;
+      plus(x, dx) -> x';  ambient(x) -> ambient parameter vector (ceres takes norms of it);
+      idx: free local coordinates;  on_accept(x): hook run before re-linearising an accepted point.
+    PARITY UNPINNED against Ceres itself (not installed); see the module docstring."""
+    x = x0
+    H, g, cost = normal(x)
     scale = jacobi_scaling(H)
     radius, mu, reuse = radius0, MIN_MU, False
     summ = dict(iterations=0, initial_cost=cost, final_cost=cost, termination='NO_CONVERGENCE',
                 usable=True, steps=[], accepted=[])
     if np.max(np.abs(g[idx])) <= 1e-10:
         summ['termination'] = 'CONVERGENCE'
-        return st, summ
-    x_norm = _x_norm(win, st, free)
+        return x, summ
+    x_norm = float(np.linalg.norm(ambient(x)))
     it = 0
     gn_s = None
     while True:
@@ -448,7 +439,7 @@ def solve(win, st0, max_iter=10, verbose=False, alias_bias=True, radius0=1.0e4):
                 if mu > MAX_MU:
                     summ['termination'] = 'FAILURE'
                     summ['usable'] = False
-                    return st, summ
+                    return x, summ
             gn_s = -diag * xs
         gn_norm = float(np.linalg.norm(gn_s))
         g_norm = float(np.linalg.norm(grad))
@@ -467,17 +458,17 @@ def solve(win, st0, max_iter=10, verbose=False, alias_bias=True, radius0=1.0e4):
         step_s = step_s / diag
         # ---- model cost change (trust_region_minimizer.cc ComputeTrustRegionStep)
         model_change = -float(step_s @ gs + 0.5 * step_s @ Hs @ step_s)
-        dx = np.zeros(local_dim(win))
+        dx = np.zeros(ndim)
         dx[idx] = step_s * scale[idx]
         if model_change < 0:                       # invalid step
             radius *= 0.5
             reuse = True
             continue
-        cand = apply_step(win, st, dx)
-        cand_cost = total_cost(win, cand)
+        cand = plus(x, dx)
+        cand_cost = cost_fn(cand)
         summ['steps'].append(dx.copy())
         # parameter tolerance
-        if np.linalg.norm(_x_vec(win, cand, free) - _x_vec(win, st, free)) <= 1e-8 * (x_norm + 1e-8):
+        if np.linalg.norm(ambient(cand) - ambient(x)) <= 1e-8 * (x_norm + 1e-8):
             summ['termination'] = 'CONVERGENCE'
             break
         if abs(cost - cand_cost) <= 1e-6 * cost:
@@ -487,10 +478,11 @@ def solve(win, st0, max_iter=10, verbose=False, alias_bias=True, radius0=1.0e4):
         if verbose:
             print(f"it {it} cost {cost:.6e} -> {cand_cost:.6e} rel {rel:.3f} radius {radius:.3e}")
         if rel > 1e-3:
-            st, cost = cand, cand_cost
-            win = win.with_bias_lin_point(st) if alias else win
-            x_norm = _x_norm(win, st, free)
-            H, g, cost = normal_equations(win, st)
+            x, cost = cand, cand_cost
+            if on_accept is not None:
+                on_accept(x)
+            x_norm = float(np.linalg.norm(ambient(x)))
+            H, g, cost = normal(x)
             summ['accepted'].append(True)
             if rel < 0.25:
                 radius *= 0.5
@@ -510,7 +502,32 @@ def solve(win, st0, max_iter=10, verbose=False, alias_bias=True, radius0=1.0e4):
             break
     summ['iterations'] = it
     summ['final_cost'] = cost
-    return st, summ
+    return x, summ
+
+
+def solve(win, st0, max_iter=10, verbose=False, alias_bias=True, radius0=1.0e4):
+    """ceres::Solve on the sliding window as PVIO configures it (bundle_adjustor.cpp:244-249;
+    SPARSE_SCHUR is an exact solver, so only the minimiser logic of trust_region() matters).
+    Quirk Q1 (SURVEY 8a): the IMU bias linearisation point aliases the parameter
+    (preintegration_error_cost.h:57-58 reads frame_i->motion, which ceres refreshes after
+    every successful iteration because update_state_every_iteration=true), so with
+    alias_bias=True bg0/ba0 follow the accepted state and only the current step's bias
+    change is ever applied to the pre-integrated deltas.  alias_bias=False freezes the
+    linearisation point at solve entry (the proper first-order correction).  The exact
+    point inside a ceres iteration at which the user state is refreshed (before or after
+    the re-linearisation of an accepted step) cannot be verified without Ceres; this
+    restatement refreshes BEFORE re-linearising.  Returns (state, summary dict)."""
+    alias = alias_bias and win.use_inertial
+    box = [win.with_bias_lin_point(st0) if alias else win]
+    free = free_mask(win)
+    idx = np.where(free)[0]
+
+    def on_accept(st):
+        if alias:
+            box[0] = box[0].with_bias_lin_point(st)
+    return trust_region(lambda st: normal_equations(box[0], st), lambda st: total_cost(box[0], st),
+                        lambda st, dx: apply_step(box[0], st, dx), lambda st: _x_vec(box[0], st, free),
+                        st0.copy(), idx, local_dim(win), max_iter, radius0, verbose, on_accept)
 
 
 def _x_vec(win, st, free):

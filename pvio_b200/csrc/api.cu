@@ -365,7 +365,7 @@ static size_t solve_smem(Handle *h, int w0, int n, bool lean) {
         size_t scr = lean ? Dp + 10 * 36 + 36 : std::max<size_t>(Dp, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);
         if (H.use_inertial) scr = std::max<size_t>(scr, 2 * (4 * 450 + 64));
         if (H.n_prior > 0) scr = std::max<size_t>(scr, 3 * 15 * (size_t)H.n_prior + 9 * (size_t)H.n_prior);
-        const size_t bytes = sizeof(double) * (nb * (nb + 1) / 2 * 16 + 4 * Dp + nb * 16 + (size_t)H.N * 36 + scr);
+        const size_t bytes = sizeof(double) * ((nb + 1) * (nb + 2) / 2 * 16 + 4 * Dp + nb * 16 + (size_t)H.N * 36 + scr);
         best = std::max(best, bytes);
     }
     return best;

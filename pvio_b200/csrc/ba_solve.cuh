@@ -309,15 +309,20 @@ __device__ inline void plane_factor(int K, const int32_t *fr, const float *z, co
 }
 
 // Tiled dense Cholesky A = L L^T + solve, all threads of the CTA, fp64, in shared memory.
-// nb block rows of 4 (padding rows carry an identity diagonal).  Per block column kb:
+// nb block rows of 4 (padding rows carry an identity diagonal).  The right-hand side is block row
+// nb of the packed tile array (row 0 of its tiles), so the panel / trailing phases carry out the
+// forward substitution for free.  Per block column kb:
 //   (a) one thread factors the 4x4 diagonal tile and stores inv(L_kk);
-//   (b) one thread per panel tile: A_Ik <- A_Ik L_kk^-T;
+//   (b) one thread per panel tile (incl. the rhs row): A_Ik <- A_Ik L_kk^-T;
 //   (c) one thread per trailing tile: A_IJ -= A_Ik A_Jk^T   (64 independent FMAs).
 // 3 barriers per block column (15 block columns for D = 60) instead of 2-3 per scalar column.
-// Linv: [nb][16] scratch.  Returns false (uniformly) if a pivot is not positive / finite (the
-// system must be positive definite, as for ceres' Cholesky-based SPARSE_SCHUR).
+// The back substitution L^T x = y runs on warp 0 with warp-level barriers only.
+// A must hold (nb+1)(nb+2)/2 tiles; Linv: [nb][16] scratch.  Returns false (uniformly) if a pivot is
+// not positive / finite (the system must be positive definite, as for ceres' Cholesky-based SPARSE_SCHUR).
 __device__ inline bool chol_solve_tiled(double *A, double *x, int nb, double *Linv, int *flag_sm) {
     const int tid = threadIdx.x, nt = blockDim.x;
+    double *R = A + ((nb * (nb + 1) / 2) << 4);          // rhs block row: tiles (nb, J), row 0 used
+    for (int i = tid; i < nb * 16; i += nt) R[i] = ((i & 15) < 4) ? x[(i >> 4) * 4 + (i & 3)] : 0.0;
     if (tid == 0) *flag_sm = 1;
     __syncthreads();
     for (int kb = 0; kb < nb; ++kb) {
@@ -345,7 +350,6 @@ __device__ inline bool chol_solve_tiled(double *A, double *x, int nb, double *Li
                     L[r * 4 + c] = v * id;
                 }
             }
-            // inverse of the lower-triangular 4x4
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 Li[c * 4 + c] = idg[c];
@@ -363,91 +367,61 @@ __device__ inline bool chol_solve_tiled(double *A, double *x, int nb, double *Li
         }
         __syncthreads();
         if (*flag_sm == 0) break;                      // uniform
-        // (b) panel tiles: X <- X * Linv^T   (X L^-T)
-        for (int I = kb + 1 + tid; I < nb; I += nt) {
-            double *X = A + ((I * (I + 1) / 2 + kb) << 4);
+        // (b) panel tiles incl. the rhs block row (I = nb): X <- X * Linv^T, one thread per tile ROW
+        for (int e = tid; e < (nb - kb) * 4; e += nt) {
+            const int I = kb + 1 + (e >> 2), r = e & 3;
+            double *X = A + ((I * (I + 1) / 2 + kb) << 4) + r * 4;
             const double *Li = Linv + kb * 16;
-            double t[16];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int m = 0; m <= c; ++m) v += X[r * 4 + m] * Li[c * 4 + m];
-                    t[r * 4 + c] = v;
-                }
-#pragma unroll
-            for (int e = 0; e < 16; ++e) X[e] = t[e];
+            const double x0 = X[0], x1 = X[1], x2 = X[2], x3 = X[3];
+            X[0] = x0 * Li[0];
+            X[1] = x0 * Li[4] + x1 * Li[5];
+            X[2] = x0 * Li[8] + x1 * Li[9] + x2 * Li[10];
+            X[3] = x0 * Li[12] + x1 * Li[13] + x2 * Li[14] + x3 * Li[15];
         }
         __syncthreads();
-        // (c) trailing tiles (I,J), kb < J <= I
+        // (c) trailing tiles (I,J), kb < J <= I, plus the rhs row (I = nb, kb < J < nb); one thread per tile ROW
         const int n = nb - kb - 1, ntile = n * (n + 1) / 2;
-        for (int e = tid; e < ntile; e += nt) {
-            int ii = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-            while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
-            while (ii * (ii + 1) / 2 > e) --ii;
-            const int jj = e - ii * (ii + 1) / 2;
-            const int I = kb + 1 + ii, J = kb + 1 + jj;
-            const double *P = A + ((I * (I + 1) / 2 + kb) << 4), *Q = A + ((J * (J + 1) / 2 + kb) << 4);
-            double *C = A + ((I * (I + 1) / 2 + J) << 4);
-            double p[16], q[16];
+        for (int e4 = tid; e4 < (ntile + n) * 4; e4 += nt) {
+            const int e = e4 >> 2, r = e4 & 3;
+            int I, J;
+            if (e < ntile) {
+                int ii = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+                while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+                while (ii * (ii + 1) / 2 > e) --ii;
+                I = kb + 1 + ii; J = kb + 1 + (e - ii * (ii + 1) / 2);
+            } else { I = nb; J = kb + 1 + (e - ntile); }
+            const double *P = A + ((I * (I + 1) / 2 + kb) << 4) + r * 4, *Q = A + ((J * (J + 1) / 2 + kb) << 4);
+            double *C = A + ((I * (I + 1) / 2 + J) << 4) + r * 4;
+            const double p0 = P[0], p1 = P[1], p2 = P[2], p3 = P[3];
 #pragma unroll
-            for (int m = 0; m < 16; ++m) { p[m] = P[m]; q[m] = Q[m]; }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    C[r * 4 + c] -= p[r * 4] * q[c * 4] + p[r * 4 + 1] * q[c * 4 + 1] + p[r * 4 + 2] * q[c * 4 + 2] + p[r * 4 + 3] * q[c * 4 + 3];
+            for (int c = 0; c < 4; ++c) C[c] -= p0 * Q[c * 4] + p1 * Q[c * 4 + 1] + p2 * Q[c * 4 + 2] + p3 * Q[c * 4 + 3];
         }
         __syncthreads();
     }
     if (*flag_sm == 0) return false;
-    // forward: y = L^-1 b (block rows), backward: x = L^-T y
-    for (int kb = 0; kb < nb; ++kb) {
-        if (tid == 0) {
+    // y = L^-1 b now sits in row 0 of the rhs tiles; back substitution x = L^-T y on warp 0
+    if (tid < 32) {
+        for (int i = tid; i < nb * 4; i += 32) x[i] = R[(i >> 2) * 16 + (i & 3)];
+        __syncwarp();
+        for (int kb = nb - 1; kb >= 0; --kb) {
             const double *Li = Linv + kb * 16;
-            double v[4], o[4];
+            double o = 0.0;
+            if (tid < 4) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) v[r] = x[kb * 4 + r];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) { o[r] = 0.0;
-#pragma unroll
-                for (int m = 0; m <= r; ++m) o[r] += Li[r * 4 + m] * v[m]; }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) x[kb * 4 + r] = o[r];
+                for (int m = 0; m < 4; ++m) o += (m >= tid) ? Li[m * 4 + tid] * x[kb * 4 + m] : 0.0;   // Linv^T
+            }
+            __syncwarp();
+            if (tid < 4) x[kb * 4 + tid] = o;
+            __syncwarp();
+            for (int e = tid; e < kb * 4; e += 32) {
+                const int J = e >> 2, c = e & 3;
+                const double *X = A + ((kb * (kb + 1) / 2 + J) << 4);      // tile (kb, J)
+                x[e] -= X[c] * x[kb * 4] + X[4 + c] * x[kb * 4 + 1] + X[8 + c] * x[kb * 4 + 2] + X[12 + c] * x[kb * 4 + 3];
+            }
+            __syncwarp();
         }
-        __syncthreads();
-        for (int I = kb + 1 + tid; I < nb; I += nt) {
-            const double *X = A + ((I * (I + 1) / 2 + kb) << 4);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                x[I * 4 + r] -= X[r * 4] * x[kb * 4] + X[r * 4 + 1] * x[kb * 4 + 1] + X[r * 4 + 2] * x[kb * 4 + 2] + X[r * 4 + 3] * x[kb * 4 + 3];
-        }
-        __syncthreads();
     }
-    for (int kb = nb - 1; kb >= 0; --kb) {
-        if (tid == 0) {
-            const double *Li = Linv + kb * 16;
-            double v[4], o[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) v[r] = x[kb * 4 + r];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) { o[r] = 0.0;
-#pragma unroll
-                for (int m = r; m < 4; ++m) o[r] += Li[m * 4 + r] * v[m]; }   // Linv^T
-#pragma unroll
-            for (int r = 0; r < 4; ++r) x[kb * 4 + r] = o[r];
-        }
-        __syncthreads();
-        for (int J = tid; J < kb; J += nt) {
-            const double *X = A + ((kb * (kb + 1) / 2 + J) << 4);      // tile (kb, J): rows of kb, cols of J
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                x[J * 4 + c] -= X[c] * x[kb * 4] + X[4 + c] * x[kb * 4 + 1] + X[8 + c] * x[kb * 4 + 2] + X[12 + c] * x[kb * 4 + 3];
-        }
-        __syncthreads();
-    }
+    __syncthreads();
     return true;
 }
 
@@ -472,7 +446,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nb = (D + 3) >> 2, Dp = nb * 4;               // block rows of 4; rows >= D are identity padding
-    const int nA = nb * (nb + 1) / 2 * 16;
+    const int nA = (nb + 1) * (nb + 2) / 2 * 16;            // + the rhs block row
     double *A = reinterpret_cast<double *>(smem_raw);       // packed lower 4x4 tiles
     double *g = A + nA;                                     // [Dp] reduced gradient
     double *gu = g + Dp;                                    // [Dp] unreduced gradient (for |g|_inf)
