@@ -193,6 +193,29 @@ int pvio_b200_timer_stop(pvio_b200_handle h, float *ms);
 /* device-side time (ms) of the most recent linearise+Schur kernel launch */
 int pvio_b200_last_kernel_ms(pvio_b200_handle h, int which, float *ms);
 
+/* ---- visual-inertial PnP ------------------------------------------------ */
+/* Replaces the ceres::Solve of visual_inertial_pnp, pvio/src/pvio/estimation/pnp.cpp:32-100: the new
+ * frame's pose (and v, bg, ba when use_inertial) against PreIntegrationPriorCost
+ * (ceres/preintegration_error_cost.h:167-206; last_frame is constant) and pose-only reprojection
+ * blocks on constant world points (ceres/reprojection_error_cost.h:128-203, CauchyLoss(1.0)):
+ * Track::get_landmark_point() for ordinary tracks, the plane-cast point for TF_PLANE tracks. */
+typedef struct pvio_b200_pnp_problem {
+    int32_t n_points;
+    int32_t use_inertial;
+    const double *points;        /* [n][3] world points                                        */
+    const double *z;             /* [n][2] normalised keypoints in the new frame               */
+    double cam_q_cs[4], cam_p_cs[3], imu_q_cs[4], imu_p_cs[3];
+    double sqrt_inv_cov[4];
+    double cauchy_a;
+    const double *last_frame;    /* [16] map->last_frame() state (constant)          pnp.cpp:44 */
+    const double *imu_data;      /* [PVIO_B200_IMU_STRIDE] frame->preintegration (bg0/ba0 ignored:
+                                    they alias last_frame's biases)                             */
+} pvio_b200_pnp_problem;
+
+/* frame: [16] in/out (q xyzw, p, v, bg, ba).  One kernel launch runs the whole trust-region solve. */
+int pvio_b200_pnp_solve(pvio_b200_handle h, const pvio_b200_pnp_problem *problem, double *frame,
+                        const pvio_b200_options *opt, pvio_b200_summary *summary);
+
 /* ---- KLT ----------------------------------------------------------------------------- */
 /* Pyramidal Lucas-Kanade with OpenCV's semantics: winSize 21x21, maxLevel levels above
  * level 0, criteria COUNT+EPS (max_iter, eps), OPTFLOW_USE_INITIAL_FLOW (next_pts holds

@@ -54,13 +54,20 @@ class CSummary(C.Structure):
                 ("final_radius", C.c_double), ("final_mu", C.c_double), ("solve_seconds", C.c_double)]
 
 
+class CPnpProblem(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("use_inertial", C.c_int32), ("points", c_f64p), ("z", c_f64p),
+                ("cam_q_cs", C.c_double * 4), ("cam_p_cs", C.c_double * 3), ("imu_q_cs", C.c_double * 4),
+                ("imu_p_cs", C.c_double * 3), ("sqrt_inv_cov", C.c_double * 4), ("cauchy_a", C.c_double),
+                ("last_frame", c_f64p), ("imu_data", c_f64p)]
+
+
 EXPORTS = [
     "pvio_b200_create", "pvio_b200_destroy", "pvio_b200_last_error", "pvio_b200_kernel_launches",
     "pvio_b200_version", "pvio_b200_ba_solve", "pvio_b200_ba_gn_step", "pvio_b200_ba_marginalize",
     "pvio_b200_reprojection_error", "pvio_b200_batch_set_window", "pvio_b200_batch_replicate",
     "pvio_b200_batch_upload", "pvio_b200_batch_gn_step", "pvio_b200_batch_download",
     "pvio_b200_batch_gn_step_host", "pvio_b200_sync", "pvio_b200_timer_start", "pvio_b200_timer_stop",
-    "pvio_b200_last_kernel_ms", "pvio_b200_klt_track",
+    "pvio_b200_last_kernel_ms", "pvio_b200_klt_track", "pvio_b200_pnp_solve",
 ]
 
 _lib = None
@@ -102,6 +109,7 @@ def load():
     lib.pvio_b200_timer_start.argtypes = [vp]
     lib.pvio_b200_timer_stop.argtypes = [vp, c_f32p]
     lib.pvio_b200_last_kernel_ms.argtypes = [vp, C.c_int, c_f32p]
+    lib.pvio_b200_pnp_solve.argtypes = [vp, C.POINTER(CPnpProblem), c_f64p, C.POINTER(COptions), C.POINTER(CSummary)]
     lib.pvio_b200_klt_track.argtypes = [vp, c_u8p, c_u8p, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_u8p, c_f32p,
                                         C.c_int, C.c_int, C.c_int, C.c_double]
     for name in EXPORTS:

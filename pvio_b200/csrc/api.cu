@@ -1029,6 +1029,13 @@ int pvio_b200_ba_marginalize(pvio_b200_handle hh, const pvio_b200_window *w, con
     return marginalize_impl(h, w, s, index, S_out, e_out, H_out, b_out);
 }
 
+int pvio_b200_pnp_solve(pvio_b200_handle hh, const pvio_b200_pnp_problem *problem, double *frame,
+                        const pvio_b200_options *opt, pvio_b200_summary *summary) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !problem || !frame) return PVIO_B200_EINVAL;
+    return pnp_solve_impl(h, problem, frame, opt, summary);
+}
+
 int pvio_b200_klt_track(pvio_b200_handle hh, const uint8_t *prev, const uint8_t *next, int width, int height, int stride,
                         const float *prev_pts, float *next_pts, uint8_t *status, float *err, int n_points,
                         int max_level, int max_iter, double eps) {

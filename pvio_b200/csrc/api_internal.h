@@ -84,6 +84,9 @@ int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int widt
                    const float *prev_pts, float *next_pts, uint8_t *status, float *err, int n_points,
                    int max_level, int max_iter, double eps);
 void klt_free(Handle *h);
+// pnp.cu
+int pnp_solve_impl(Handle *h, const pvio_b200_pnp_problem *pb, double *frame, const pvio_b200_options *opt,
+                   pvio_b200_summary *summary);
 // ba_marg.cu
 int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s, int index,
                      double *S_out, double *e_out, double *H_out, double *b_out);

@@ -368,3 +368,49 @@ def make_klt_pair(seed=648, size=(752, 480), n_points=500, max_shift=8.0):
     sel = rng.permutation(len(pts))[:n_points]
     pts = pts[np.sort(sel)].astype(np.float32)
     return prev8, next8, pts, warp_pts(pts.astype(np.float64)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- PnP inputs
+def make_pnp(seed=651, n_points=150, cal=EUROC, use_inertial=True, kf_dt=0.05, imu_hz=200.0):
+    """Inputs of visual_inertial_pnp (estimation/pnp.cpp:32-100): the last frame (constant), the new
+    frame's predicted state, the IMU pre-integration between them and the world points of the tracks
+    both frames see, with pixel noise.  Returns a dict of arrays (16-vectors: q xyzw, p, v, bg, ba)."""
+    rng = np.random.default_rng(seed)
+    w = _base_window(cal, 2, use_inertial)
+    R_wb0 = R_WC0 @ so3.qmat(w.cam_q_cs).T
+    t0, t1 = 0.4, 0.4 + kf_dt
+    st = []
+    for t in (t0, t1):
+        p, v, _, th, _ = _trajectory(t)
+        st.append((so3.mat2quat(R_wb0 @ so3.qmat(so3.qexp(th))), p, v))
+    bg = rng.normal(0, 2e-3, 3)
+    ba = rng.normal(0, 2e-2, 3)
+    last = np.concatenate([st[0][0], st[0][1], st[0][2], bg, ba])
+    truth = np.concatenate([st[1][0], st[1][1], st[1][2], bg, ba])
+    pre = so3.PreIntegrator(cal['cov_g'], cal['cov_a'], cal['cov_bg'], cal['cov_ba'])
+    dt = 1.0 / imu_hz
+    for s in range(int(round(kf_dt * imu_hz))):
+        t = t0 + s * dt
+        _, _, a, th, thd = _trajectory(t + 0.5 * dt)
+        Rwb = R_wb0 @ so3.qmat(so3.qexp(th))
+        gyro = so3.right_jacobian(th) @ thd + bg + rng.normal(0, np.sqrt(cal['cov_g'] * imu_hz), 3)
+        acc = Rwb.T @ (a - GRAVITY) + ba + rng.normal(0, np.sqrt(cal['cov_a'] * imu_hz), 3)
+        pre.data.append((t, gyro, acc))
+    imu = pre.integrate(t1, bg, ba)
+    q_t = np.stack([st[0][0], st[1][0]])
+    p_t = np.stack([st[0][1], st[1][1]])
+    fx, fy = cal['K'][0], cal['K'][1]
+    s_px = np.sqrt(cal['noise_px2'])
+    pts, zs = [], []
+    for _ in range(n_points):
+        x, _, _ = _sample_landmark(rng, cal, w, q_t, p_t, [0, 1])
+        z, _ = _project(q_t[1], p_t[1], w, x)
+        pts.append(x + rng.normal(0, 0.02, 3))                 # landmark estimate, not the true point
+        zs.append(z + rng.normal(0, s_px, 2) / np.array([fx, fy]))
+    guess = truth.copy()
+    guess[0:4] = so3.qnormalize(so3.qmul(truth[0:4], so3.qexp(rng.normal(0, np.deg2rad(0.7), 3))))
+    guess[4:7] += rng.normal(0, 0.03, 3)
+    guess[7:10] += rng.normal(0, 0.05, 3)
+    return dict(frame=guess, last=last, truth=truth, imu=imu, pts=np.array(pts), zs=np.array(zs),
+                cam_q=w.cam_q_cs, cam_p=w.cam_p_cs, imu_q=w.imu_q_cs, imu_p=w.imu_p_cs, W=w.sqrt_inv_cov,
+                use_inertial=use_inertial)
