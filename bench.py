@@ -141,7 +141,7 @@ def run_gpu(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from pvio_b200 import synth, klt
+    from pvio_b200 import synth, klt, pnp
     from pvio_b200.bundle_adjustor import BundleAdjustor
 
     W = args.windows
@@ -271,6 +271,16 @@ def run_gpu(args):
         klt_info["cv2_tracks_per_s"] = None
         klt_info["cv2_error"] = str(e)
 
+    # ---- visual_inertial_pnp (150 points + IMU prior): one kernel launch per solve, host buffers in/out
+    d = synth.make_pnp()
+    pargs = (d['frame'], d['last'], d['imu'], d['pts'], d['zs'], d['cam_q'], d['cam_p'], d['imu_q'], d['imu_p'], d['W'], True)
+    _, psum = pnp.visual_inertial_pnp(ba1, *pargs)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        _, psum = pnp.visual_inertial_pnp(ba1, *pargs)
+    pnp_info = {"ms_per_solve_e2e": (time.perf_counter() - t0) * 1e3 / 20, "kernel_ms": psum["solve_seconds"] * 1e3,
+                "iterations": int(psum["iterations"]), "points": int(len(d['pts']))}
+
     # ---- CPU baseline beside it (bounded sample, all host threads; plus one thread like num_threads=1)
     ncpu = os.cpu_count() or 1
     n_sample = max(256, 128 * ncpu)
@@ -292,7 +302,7 @@ def run_gpu(args):
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "note": "pvio_b200_batch_gn_step_host: pinned host buffers -> device, one GN iteration, dx back"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "single_window": single, "klt": klt_info,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "single_window": single, "klt": klt_info, "pnp": pnp_info,
     }
     print(json.dumps(line))
     ba.close(); ba1.close()
