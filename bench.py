@@ -202,7 +202,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * W * e2e_steps / e2e_s
-    h2d = W * (12 * 4608 + 16 * 512 + 8 * 512 + 8 * 16 * N + 832 + 224)
+    h2d = W * (8 * 4608 + 16 * 512 + 8 * 512 + 8 * 16 * N + 832 + 224)
     d2h = W * (8 * 15 * N + 8 * 512 + 168)
 
     if rank != 0:

@@ -216,6 +216,14 @@ typedef struct pvio_b200_pnp_problem {
 int pvio_b200_pnp_solve(pvio_b200_handle h, const pvio_b200_pnp_problem *problem, double *frame,
                         const pvio_b200_options *opt, pvio_b200_summary *summary);
 
+/* ---- diagnostics ---------------------------------------------------------------------- */
+/* Self-test of the tcgen05 3xTF32 SYRK block used by the linearise kernel: D[64][64] = sum_k a_k a_k^T
+ * for K rows of 64 floats (A is [K][64]).  Not part of the reference interface. */
+int pvio_b200_selftest_syrk(pvio_b200_handle h, const float *A, int K, double *D);
+/* one pass (K <= 128), raw dump of the 128 x 64 TMEM block + the TMEM base address (tools/tc_debug.py);
+ * mode 0: 3xTF32, 1: unpadded K-major strides, 2: tcgen05.st pattern only, 3: one TF32 pass */
+int pvio_b200_selftest_syrk_raw(pvio_b200_handle h, const float *A, int K, float *out, int mode);
+
 /* ---- KLT ----------------------------------------------------------------------------- */
 /* Pyramidal Lucas-Kanade with OpenCV's semantics: winSize 21x21, maxLevel levels above
  * level 0, criteria COUNT+EPS (max_iter, eps), OPTFLOW_USE_INITIAL_FLOW (next_pts holds

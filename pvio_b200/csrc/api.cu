@@ -10,6 +10,7 @@
 #include "api_internal.h"
 #include "ba_lin.cuh"
 #include "ba_lin2.cuh"
+#include "ba_lin3.cuh"
 #include "ba_solve.cuh"
 #include "ba_update.cuh"
 
@@ -138,18 +139,19 @@ __global__ void postpass_kernel(const WinHdr *hdr, const WinConst *cst, const Ob
         const int l = l0 + gid;
         const bool ok = l < H.M;
         const LmRec lr = lms[(size_t)w * Mcap + (ok ? l : 0)];
-        const int n_obs = ok ? ((lr.meta >> 8) & 0xff) : 0;
-        const int anchor = lr.meta & 0xff;
+        const int n_obs = ok ? lm_nobs(lr.meta) : 0;
+        const int anchor = lm_anchor(lr.meta);
+        const unsigned fmask = ok ? lm_mask(lr.meta) : 0u;
         double x[3];
         float xf[3], cl[3];
         world_point(F[anchor], lr.zrx, lr.zry, ok ? rho[(size_t)w * Mcap + l] : 1.0, x, xf, cl);
-        // lane j < n_obs: observation j; lane n_obs: the anchor observation
+        // lane = frame: its observation is record popc(mask below the lane); the anchor lane uses z_ref
         int frame = -1;
         float zx = 0.f, zy = 0.f;
-        if (lane < n_obs) {
-            const ObsRec o = obs[(size_t)w * Kcap + lr.obs_begin + lane];
-            frame = o.frame; zx = o.zx; zy = o.zy;
-        } else if (lane == n_obs && ok) {
+        if ((fmask >> lane) & 1u) {
+            const ObsRec o = obs[(size_t)w * Kcap + lr.obs_begin + __popc(fmask & ((1u << lane) - 1u))];
+            frame = lane; zx = o.zx; zy = o.zy;
+        } else if (lane == anchor && ok) {
             frame = anchor; zx = lr.zrx; zy = lr.zry;
         }
         double e = 0.0;
@@ -217,20 +219,24 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
         if (a < 0 || a >= N || n < 0 || n >= kGroup) return fail(h, PVIO_B200_EINVAL, "landmark with bad anchor / too many observations");
         lm[lp].zrx = (float)w->lm_z_ref[2 * l];
         lm[lp].zry = (float)w->lm_z_ref[2 * l + 1];
-        lm[lp].meta = a | (n << 8) | ((w->lm_in_victim && w->lm_in_victim[l]) ? (1 << 16) : 0);
         lm[lp].obs_begin = k_out;
         rh[lp] = s->inv_depth[l];
-        unsigned seen = 1u << a;
+        // records in increasing frame order: the frame index lives in the landmark's mask, not in the record
+        unsigned seen = 0;
         for (int k = b0; k < b1; ++k) {
             const int f = w->obs_frame[k];
             if (f <= a || f >= N || (seen >> f) & 1)
                 return fail(h, PVIO_B200_EINVAL, "observation frames must be distinct and later than the anchor (Track::first_frame is the lowest id)");
             seen |= 1u << f;
-            ob[k_out].zx = (float)w->obs_z[2 * k];
-            ob[k_out].zy = (float)w->obs_z[2 * k + 1];
-            ob[k_out].frame = f;
-            ++k_out;
         }
+        for (int k = b0; k < b1; ++k) {
+            const int f = w->obs_frame[k];
+            const int pos = k_out + __builtin_popcount(seen & ((1u << f) - 1u));
+            ob[pos].zx = (float)w->obs_z[2 * k];
+            ob[pos].zy = (float)w->obs_z[2 * k + 1];
+        }
+        k_out += n;
+        lm[lp].meta = lm_meta(a, (w->lm_in_victim && w->lm_in_victim[l]) ? 1 : 0, n, seen);
         // chunks: <= kChunk landmarks of one anchor
         if (nch == 0 || (H.chunk_meta[nch - 1] >> 8) != a || (H.chunk_meta[nch - 1] & 0xff) == kChunk) {
             if (nch == kMaxChunks) return fail(h, PVIO_B200_EINVAL, "too many landmark chunks");
@@ -242,6 +248,7 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
     }
     H.n_chunks = nch;
     h->slot_M[slot] = M; h->slot_N[slot] = N; h->slot_K[slot] = K;
+    h->max_slot_N = std::max(h->max_slot_N, N);
     h->perm_identity[slot] = sorted ? 1 : 0;
     // inertial part
     H.n_imu = w->use_inertial ? w->n_imu : 0;
@@ -392,7 +399,13 @@ static int run_linearize(Handle *h, int n, const StepCfg &c) {
     // few windows: the group-per-landmark kernel exposes more parallelism per window (latency);
     // many windows: the thread-per-landmark kernel issues ~2x fewer instructions (throughput)
     // (the group kernel owns at most 256 Phase-B tiles: N <= 15)
+    // PVIO_B200_TC=1 and windows of <= 10 frames: the Schur SYRK runs on the tensor cores (tcgen05, ba_lin3.cuh).
+    // Opt-in: parity-green but 10 % slower than the CUDA-core SYRK on B200 (profiles/r01c_lin_tc.md)
+    const bool tc_ok = h->max_slot_N <= kTcMaxFrames && h->use_tc;
     if (n * 2 < h->sm_count && h->Ncap * (h->Ncap + 1) <= kLinThreads) lin_schur_kernel<true><<<dim3(gx, n), kLinThreads, lin_smem_bytes(), st>>>(a);
+    else if (tc_ok && h->tc_gs == 4) lin_tc_kernel<true, 4><<<dim3(gx, n), kLinThreads, lin3_smem_bytes(std::min(h->Ncap, kTcMaxFrames)), st>>>(a);
+    else if (tc_ok && h->tc_gs == 2) lin_tc_kernel<true, 2><<<dim3(gx, n), kLinThreads, lin3_smem_bytes(std::min(h->Ncap, kTcMaxFrames)), st>>>(a);
+    else if (tc_ok) lin_tc_kernel<true, 1><<<dim3(gx, n), kLinThreads, lin3_smem_bytes(std::min(h->Ncap, kTcMaxFrames)), st>>>(a);
     else lin_tpl_kernel<true><<<dim3(gx, n), kLinThreads, lin2_smem_bytes(h->Ncap), st>>>(a);
     if (!h->capturing) { CK(h, cudaEventRecord(h->kev[slot + 1], st)); ++h->kev_count; }
     ++h->launches;
@@ -619,6 +632,11 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     h->perm.resize(W); h->perm_identity.assign(W, 1); h->slot_M.assign(W, 0); h->slot_N.assign(W, 0); h->slot_K.assign(W, 0);
     CK(h, cudaFuncSetAttribute(lin_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem_bytes()));
     CK(h, cudaFuncSetAttribute(lin_tpl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin2_smem_bytes(kMaxFrames)));
+    CK(h, cudaFuncSetAttribute(lin_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin3_smem_bytes(kTcMaxFrames)));
+    CK(h, cudaFuncSetAttribute(lin_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin3_smem_bytes(kTcMaxFrames)));
+    CK(h, cudaFuncSetAttribute(lin_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin3_smem_bytes(kTcMaxFrames)));
+    { const char *e = getenv("PVIO_B200_TC_GS"); h->tc_gs = e ? atoi(e) : 2; }
+    { const char *e = getenv("PVIO_B200_TC"); h->use_tc = e && e[0] == '1'; }
     CK(h, cudaFuncSetAttribute(lin_tpl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin2_smem_bytes(kMaxFrames)));
     CK(h, cudaFuncSetAttribute(lin_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem_bytes()));
     CK(h, cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -729,6 +747,13 @@ int pvio_b200_batch_replicate(pvio_b200_handle hh, int n) {
             memcpy(h->prior_S.h + (size_t)i * dcap * dcap, h->prior_S.h, sizeof(double) * dcap * dcap);
             memcpy(h->prior_e.h + (size_t)i * dcap, h->prior_e.h, sizeof(double) * dcap);
             memcpy(h->prior_x0.h + (size_t)i * N * kFrameStride, h->prior_x0.h, sizeof(double) * N * kFrameStride);
+        }
+        if (h->have_planes) {
+            memcpy(h->plane_param.h + (size_t)i * h->Pcap * 4, h->plane_param.h, sizeof(double) * h->Pcap * 4);
+            memcpy(h->pt_plane.h + (size_t)i * h->Tcap, h->pt_plane.h, sizeof(int32_t) * h->Tcap);
+            memcpy(h->pt_begin.h + (size_t)i * (h->Tcap + 1), h->pt_begin.h, sizeof(int32_t) * (h->Tcap + 1));
+            memcpy(h->pt_frame.h + (size_t)i * h->Ocap, h->pt_frame.h, sizeof(int32_t) * h->Ocap);
+            memcpy(h->pt_z.h + (size_t)i * h->Ocap * 2, h->pt_z.h, sizeof(float) * h->Ocap * 2);
         }
     }
     return 0;

@@ -266,21 +266,16 @@ lin_schur_kernel(LinArgs a) {
             const bool lm_ok = s < cnt;
             const int l = lm0 + (lm_ok ? s : 0);
             const LmRec lr = lms[l];
-            int n_obs = lm_ok ? ((lr.meta >> 8) & 0xff) : 0;
-            if (a.victim_only && !((lr.meta >> 16) & 1)) n_obs = 0;
-            // the two groups of a warp must run the same shuffle sequence
-            const int n_max = max(n_obs, __shfl_xor_sync(0xffffffffu, n_obs, 16));
-            ObsRec o;
-            o.frame = -1; o.zx = 0.f; o.zy = 0.f;
-            if (lane < n_obs) o = obs[lr.obs_begin + lane];
-            int src = -1;
-            for (int j = 0; j < n_max; ++j) {
-                const int fj = __shfl_sync(0xffffffffu, o.frame, j, kGroup);
-                if (fj == lane) src = j;
+            int n_obs = lm_ok ? lm_nobs(lr.meta) : 0;
+            if (a.victim_only && !lm_victim(lr.meta)) n_obs = 0;
+            // lane = target frame: its record is number popc(frame mask below the lane)
+            const unsigned fmask = n_obs > 0 ? lm_mask(lr.meta) : 0u;
+            const bool observed = ((fmask >> lane) & 1u) && (lane < N);
+            float zx = 0.f, zy = 0.f;
+            if (observed) {
+                const ObsRec o = obs[lr.obs_begin + __popc(fmask & ((1u << lane) - 1u))];
+                zx = o.zx; zy = o.zy;
             }
-            const float zx = __shfl_sync(0xffffffffu, o.zx, max(src, 0), kGroup);
-            const float zy = __shfl_sync(0xffffffffu, o.zy, max(src, 0), kGroup);
-            const bool observed = (src >= 0) && (lane < N);
 
             double x[3];
             float xf[3], cl[3];

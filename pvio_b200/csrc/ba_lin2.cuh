@@ -78,6 +78,57 @@ __host__ __device__ inline size_t lin2_smem_bytes(int N) {
            + sizeof(double) * 8;
 }
 
+// Epilogue shared by the thread-per-landmark kernels: assemble the direct blocks, subtract the Schur sum.
+// Hdir[t,t] += D(t,a), Hdir[a,a] += D(t,a), Hdir[t,a] = -D(t,a);  g[t] += d(t,a), g[a] -= d(t,a)
+// (target/anchor Jacobians are +-Y).  The pair storage keeps D for the (max,min) frame pair, with
+// the gradient sign relative to the TARGET; a target earlier than its anchor cannot occur in PVIO
+// (the anchor is the lowest-id frame) and is rejected by the packer.
+__device__ __forceinline__ void lin_epilogue(const LinArgs &a, int w, int N, int tid, const double *Ss, const double *Dta, const double *gsc) {
+    const int nsp = N * (N - 1) / 2;
+    const bool exclusive = (gridDim.x == 1);
+    const int npairs_cap = a.Ncap * (a.Ncap + 1) / 2;
+    double *Hred_o = a.Hred + (size_t)w * npairs_cap * 36;
+    double *Hdd_o = a.Hdd + (size_t)w * a.Ncap * 36;
+    double *gdir_o = a.gdir + (size_t)w * a.Ncap * 6;
+    double *gred_o = a.gred + (size_t)w * a.Ncap * 6;
+    // diagonal blocks (direct): thread per (f, i, j)
+    for (int e = tid; e < N * 36; e += kLinThreads) {
+        const int f = e / 36, ij = e - f * 36, i = ij / 6, j = ij - i * 6;
+        const int se = i <= j ? sym6(i, j) : sym6(j, i);
+        double d = 0.0;
+        for (int g = 0; g < N; ++g) {
+            if (g == f) continue;
+            d += Dta[(f > g ? spair(f, g) : spair(g, f)) * 33 + se];
+        }
+        const double red = d - Ss[pair_idx(f, f) * 36 + ij];
+        if (exclusive) { Hdd_o[e] = d; Hred_o[pair_idx(f, f) * 36 + ij] = red; }
+        else { if (d != 0.0) atomicAdd(&Hdd_o[e], d); if (red != 0.0) atomicAdd(&Hred_o[pair_idx(f, f) * 36 + ij], red); }
+    }
+    // off-diagonal blocks (f > g): -D(f,g) - S(f,g)
+    for (int e = tid; e < nsp * 36; e += kLinThreads) {
+        const int sp = e / 36, ij = e - sp * 36, i = ij / 6, j = ij - i * 6;
+        int f = 1;
+        while ((f + 1) * f / 2 <= sp) ++f;
+        const int g = sp - f * (f - 1) / 2;
+        const int se = i <= j ? sym6(i, j) : sym6(j, i);
+        const double v = -Dta[sp * 33 + se] - Ss[pair_idx(f, g) * 36 + ij];
+        if (exclusive) Hred_o[pair_idx(f, g) * 36 + ij] = v; else if (v != 0.0) atomicAdd(&Hred_o[pair_idx(f, g) * 36 + ij], v);
+    }
+    // gradients: the landmarks are sorted by anchor, and a pair (t,a) only ever has t as the target
+    for (int e = tid; e < N * 6; e += kLinThreads) {
+        const int f = e / 6, i = e - f * 6;
+        double d = 0.0;
+        for (int g = 0; g < N; ++g) {
+            if (g == f) continue;
+            const double v = Dta[(f > g ? spair(f, g) : spair(g, f)) * 33 + 21 + i];
+            d += (f > g) ? v : -v;          // f is the target when f > g, the anchor otherwise
+        }
+        const double r = d - gsc[e];
+        if (exclusive) { gdir_o[e] = d; gred_o[e] = r; }
+        else { if (d != 0.0) atomicAdd(&gdir_o[e], d); if (r != 0.0) atomicAdd(&gred_o[e], r); }
+    }
+}
+
 template <bool kLoss>
 __global__ void __launch_bounds__(kLinThreads, 2)
 lin_tpl_kernel(LinArgs a) {
@@ -112,17 +163,23 @@ lin_tpl_kernel(LinArgs a) {
     double *lm_scale = a.lm_scale + (size_t)w * a.Mcap;
     LmAux *aux = a.lm_aux + (size_t)w * a.Mcap;
 
-    // ---- Phase-B task of this thread: one 6x6 block pair x k-split (the k-split lanes are adjacent)
-    const int ntask = npairs;
+    // ---- Phase-B task of this thread: one 6x6 block pair x k-split (the k-split lanes are adjacent).
+    // Pairs are enumerated over the FREE frames only: FF_FIX_POSE frames are constant parameter blocks
+    // (bundle_adjustor.cpp:82-87), their rows of the reduced system are never read by the solve.
+    const unsigned fixed = a.victim_only ? 0u : ((unsigned)H.fixed_mask & ((1u << N) - 1u));
+    const unsigned freem = ~fixed & ((1u << N) - 1u);
+    const int nfree = __popc(freem);
+    const int ntask = nfree * (nfree + 1) / 2;
     const int ksplit = (ntask * 4 <= kLinThreads) ? 4 : ((ntask * 2 <= kLinThreads) ? 2 : 1);
     const int task = tid / ksplit, kk = tid % ksplit;
     const bool b_active = task < ntask;
     int bf = 0, bg = 0;
-    {
+    if (ntask > 0) {
         const int p = min(task, ntask - 1);
         int f = 0;
         while ((f + 1) * (f + 2) / 2 <= p) ++f;
-        bf = f; bg = p - f * (f + 1) / 2;
+        const int g = p - f * (f + 1) / 2;
+        bf = __fns(freem, 0, f + 1); bg = __fns(freem, 0, g + 1);        // f-th / g-th free frame
     }
     const bool b_diag = (bf == bg);
 
@@ -140,8 +197,9 @@ lin_tpl_kernel(LinArgs a) {
             const bool lm_ok = lane < cnt;
             const int l = lm0 + (lm_ok ? lane : 0);
             const LmRec lr = lms[l];
-            int n_obs = lm_ok ? ((lr.meta >> 8) & 0xff) : 0;
-            if (a.victim_only && !((lr.meta >> 16) & 1)) n_obs = 0;
+            int n_obs = lm_ok ? lm_nobs(lr.meta) : 0;
+            if (a.victim_only && !lm_victim(lr.meta)) n_obs = 0;
+            unsigned fm = lm_mask(lr.meta);
             const int n_max = __reduce_max_sync(0xffffffffu, n_obs);
             const double rl = lm_ok ? rho[l] : 1.0;
             double x[3];
@@ -154,9 +212,10 @@ lin_tpl_kernel(LinArgs a) {
             for (int j = 0; j < n_max; ++j) {
                 const bool act = j < n_obs;
                 ObsRec o;
-                o.frame = 0; o.zx = 0.f; o.zy = 0.f;
+                o.zx = 0.f; o.zy = 0.f;
                 if (act) o = obs[lr.obs_begin + j];
-                const int t = o.frame;
+                const int t = act ? __ffs(fm) - 1 : 0;          // j-th set bit of the frame mask
+                fm &= fm - 1;
                 float q[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) q[i] = 0.f;
@@ -186,14 +245,15 @@ lin_tpl_kernel(LinArgs a) {
                     const int leader = __ffs(todo) - 1;
                     const int tf = __shfl_sync(0xffffffffu, t, leader);
                     const unsigned peers = __ballot_sync(0xffffffffu, act && t == tf);
+                    todo &= ~peers;
+                    if ((fixed >> tf) & (fixed >> anchor) & 1u) continue;      // both blocks constant: nothing to assemble
                     const bool mine = act && t == tf;      // q is zero for inactive lanes
-                    const float tot = (peers == todo) ? transpose_reduce32(q, true, lane) : transpose_reduce32(q, mine, lane);
+                    const float tot = (peers == (todo | peers)) ? transpose_reduce32(q, true, lane) : transpose_reduce32(q, mine, lane);
                     if (lane < kDirVals && tf != anchor) {
                         const int sp = tf > anchor ? spair(tf, anchor) : spair(anchor, tf);
                         // sign convention: the block stores +sum Y^T Y; the epilogue applies the signs
                         atomicAdd(&Dta[sp * 33 + lane], (double)tot);
                     }
-                    todo &= ~peers;
                 }
             }
             // per-landmark Schur scalars (thread local)
@@ -267,7 +327,7 @@ lin_tpl_kernel(LinArgs a) {
                 if (ksplit >= 4) v += __shfl_xor_sync(bmask, v, 2);
                 acc[i] = v;
             }
-            double *dst = Ss + task * 36;
+            double *dst = Ss + pair_idx(bf, bg) * 36;
 #pragma unroll
             for (int i = 0; i < 6; ++i)
                 if ((i % ksplit) == kk) {
@@ -287,60 +347,14 @@ lin_tpl_kernel(LinArgs a) {
         __syncthreads();
     }
 
-    // ========================= epilogue: assemble direct blocks, subtract the Schur sum =========================
-    // Hdir[t,t] += D(t,a), Hdir[a,a] += D(t,a), Hdir[t,a] = -D(t,a);  g[t] += d(t,a), g[a] -= d(t,a)
-    // (target/anchor Jacobians are +-Y).  The pair storage keeps D for the (max,min) frame pair, with
-    // the gradient sign relative to the TARGET; a target earlier than its anchor cannot occur in PVIO
-    // (the anchor is the lowest-id frame) and is rejected by the packer.
-    const bool exclusive = (gridDim.x == 1);
-    const int npairs_cap = a.Ncap * (a.Ncap + 1) / 2;
-    double *Hred_o = a.Hred + (size_t)w * npairs_cap * 36;
-    double *Hdd_o = a.Hdd + (size_t)w * a.Ncap * 36;
-    double *gdir_o = a.gdir + (size_t)w * a.Ncap * 6;
-    double *gred_o = a.gred + (size_t)w * a.Ncap * 6;
-    // diagonal blocks (direct): thread per (f, i, j)
-    for (int e = tid; e < N * 36; e += kLinThreads) {
-        const int f = e / 36, ij = e - f * 36, i = ij / 6, j = ij - i * 6;
-        const int se = i <= j ? sym6(i, j) : sym6(j, i);
-        double d = 0.0;
-        for (int g = 0; g < N; ++g) {
-            if (g == f) continue;
-            d += Dta[(f > g ? spair(f, g) : spair(g, f)) * 33 + se];
-        }
-        const double red = d - Ss[pair_idx(f, f) * 36 + ij];
-        if (exclusive) { Hdd_o[e] = d; Hred_o[pair_idx(f, f) * 36 + ij] = red; }
-        else { if (d != 0.0) atomicAdd(&Hdd_o[e], d); if (red != 0.0) atomicAdd(&Hred_o[pair_idx(f, f) * 36 + ij], red); }
-    }
-    // off-diagonal blocks (f > g): -D(f,g) - S(f,g)
-    for (int e = tid; e < nsp * 36; e += kLinThreads) {
-        const int sp = e / 36, ij = e - sp * 36, i = ij / 6, j = ij - i * 6;
-        int f = 1;
-        while ((f + 1) * f / 2 <= sp) ++f;
-        const int g = sp - f * (f - 1) / 2;
-        const int se = i <= j ? sym6(i, j) : sym6(j, i);
-        const double v = -Dta[sp * 33 + se] - Ss[pair_idx(f, g) * 36 + ij];
-        if (exclusive) Hred_o[pair_idx(f, g) * 36 + ij] = v; else if (v != 0.0) atomicAdd(&Hred_o[pair_idx(f, g) * 36 + ij], v);
-    }
-    // gradients: the landmarks are sorted by anchor, and a pair (t,a) only ever has t as the target
-    for (int e = tid; e < N * 6; e += kLinThreads) {
-        const int f = e / 6, i = e - f * 6;
-        double d = 0.0;
-        for (int g = 0; g < N; ++g) {
-            if (g == f) continue;
-            const double v = Dta[(f > g ? spair(f, g) : spair(g, f)) * 33 + 21 + i];
-            d += (f > g) ? v : -v;          // f is the target when f > g, the anchor otherwise
-        }
-        const double r = d - gsc[e];
-        if (exclusive) { gdir_o[e] = d; gred_o[e] = r; }
-        else { if (d != 0.0) atomicAdd(&gdir_o[e], d); if (r != 0.0) atomicAdd(&gred_o[e], r); }
-    }
+    lin_epilogue(a, w, N, tid, Ss, Dta, gsc);
     double cd = (double)cost_acc;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cd += __shfl_xor_sync(0xffffffffu, cd, off);
     if (lane == 0) atomicAdd(&cost_sm[0], cd);
     __syncthreads();
     if (tid == 0) {
-        if (exclusive) a.cost_vis[w] = cost_sm[0]; else atomicAdd(&a.cost_vis[w], cost_sm[0]);
+        if (gridDim.x == 1) a.cost_vis[w] = cost_sm[0]; else atomicAdd(&a.cost_vis[w], cost_sm[0]);
     }
 }
 

@@ -13,17 +13,30 @@ constexpr int kImuStride = 288;     // doubles per IMU factor record
 constexpr int kMaxChunks = 96;
 constexpr int kAcc = 16;            // doubles per window accumulated by the update / J.v sweeps      // anchor-homogeneous chunks of <= 32 landmarks per window
 
-struct ObsRec {                     // one reprojection residual block (non-anchor observation), 12 B
+struct __align__(8) ObsRec {        // one reprojection residual block (non-anchor observation), 8 B
     float zx, zy;                   // normalised keypoint in the target frame
-    int32_t frame;                  // target frame index
-};                                  // (SURVEY's 16-B record also carried the landmark index; the
-                                    //  CSR offsets in LmRec make it redundant: 25 % fewer bytes to move)
+};                                  // SURVEY's 16-B record also carried the landmark and frame indices: the
+                                    // landmark is implied by the CSR offset in LmRec, the frame by the
+                                    // landmark's frame mask (observations are stored in increasing frame
+                                    // order, so record j belongs to the j-th set bit): half the bytes to move
 
 struct __align__(16) LmRec {        // one inverse-depth landmark
     float zrx, zry;                 // normalised keypoint in the anchor frame
-    int32_t meta;                   // anchor | n_obs << 8 | in_victim << 16
+    int32_t meta;                   // anchor | in_victim << 4 | n_obs << 8 | target-frame mask << 16
     int32_t obs_begin;              // first ObsRec of this landmark
 };
+#if defined(__CUDACC__)
+#define PVIO_HD __host__ __device__ __forceinline__
+#else
+#define PVIO_HD inline
+#endif
+PVIO_HD int lm_anchor(int32_t meta) { return meta & 0xf; }
+PVIO_HD int lm_victim(int32_t meta) { return (meta >> 4) & 1; }
+PVIO_HD int lm_nobs(int32_t meta) { return (meta >> 8) & 0x1f; }
+PVIO_HD unsigned lm_mask(int32_t meta) { return (unsigned)meta >> 16; }
+PVIO_HD int32_t lm_meta(int anchor, int victim, int n_obs, unsigned mask) {
+    return (int32_t)((unsigned)anchor | ((unsigned)victim << 4) | ((unsigned)n_obs << 8) | (mask << 16));
+}
 
 struct WinHdr {                     // per-window integers
     int32_t N, M, K, use_inertial;

@@ -112,20 +112,21 @@ update_tpl_kernel(UpdArgs a) {
         if (lane >= cnt) continue;
         const int l = lm0 + lane;
         const LmRec lr = lms[l];
-        const int n_obs = (lr.meta >> 8) & 0xff;
+        const int n_obs = lm_nobs(lr.meta);
         const double rl = rho[l];
         double x[3];
         float xf[3], cl[3];
         world_point(F[anchor], lr.zrx, lr.zry, rl, x, xf, cl);
         double hdx = 0.0, hll = 0.0;
-        for (int j = 0; j < n_obs; ++j) {
+        for (unsigned j = 0, fm = lm_mask(lr.meta); j < (unsigned)n_obs; ++j, fm &= fm - 1) {
             const ObsRec o = obs[lr.obs_begin + j];
+            const int of = __ffs(fm) - 1;
             ObsLin ol;
-            linearize_obs<kLoss>(F[o.frame], x, xf, cl, o.zx, o.zy, W, cb, ol);
+            linearize_obs<kLoss>(F[of], x, xf, cl, o.zx, o.zy, W, cb, ol);
             hll += (double)(ol.j0 * ol.j0 + ol.j1 * ol.j1);
 #pragma unroll
             for (int i = 0; i < 6; ++i)
-                hdx += (double)(ol.j0 * ol.Y0[i] + ol.j1 * ol.Y1[i]) * (dxi[o.frame][i] - dxi[anchor][i]);
+                hdx += (double)(ol.j0 * ol.Y0[i] + ol.j1 * ol.Y1[i]) * (dxi[of][i] - dxi[anchor][i]);
         }
         double drho = 0.0;
         if (n_obs > 0) {
@@ -152,9 +153,10 @@ update_tpl_kernel(UpdArgs a) {
             double xc[3];
             float xcf[3], clc[3];
             world_point(Fc[anchor], lr.zrx, lr.zry, rl + drho, xc, xcf, clc);
-            for (int j = 0; j < n_obs; ++j) {
+            for (unsigned j = 0, fm = lm_mask(lr.meta); j < (unsigned)n_obs; ++j, fm &= fm - 1) {
                 const ObsRec o = obs[lr.obs_begin + j];
-                s_cost += (double)residual_cost<kLoss>(Fc[o.frame], xc, o.zx, o.zy, W, cb);
+                const int of = __ffs(fm) - 1;
+                s_cost += (double)residual_cost<kLoss>(Fc[of], xc, o.zx, o.zy, W, cb);
             }
         }
     }
@@ -215,31 +217,33 @@ jv_vision_kernel(UpdArgs a) {
         if (lane >= cnt) continue;
         const int l = lm0 + lane;
         const LmRec lr = lms[l];
-        const int n_obs = (lr.meta >> 8) & 0xff;
+        const int n_obs = lm_nobs(lr.meta);
         if (n_obs == 0) continue;
         double x[3];
         float xf[3], cl[3];
         world_point(F[anchor], lr.zrx, lr.zry, rho[l], x, xf, cl);
         // first pass: H_ll for the landmark's scaled direction, second pass: the products
         double hll = 0.0;
-        for (int j = 0; j < n_obs; ++j) {
+        for (unsigned j = 0, fm = lm_mask(lr.meta); j < (unsigned)n_obs; ++j, fm &= fm - 1) {
             const ObsRec o = obs[lr.obs_begin + j];
+            const int of = __ffs(fm) - 1;
             ObsLin ol;
-            linearize_obs<kLoss>(F[o.frame], x, xf, cl, o.zx, o.zy, W, cb, ol);
+            linearize_obs<kLoss>(F[of], x, xf, cl, o.zx, o.zy, W, cb, ol);
             hll += (double)(ol.j0 * ol.j0 + ol.j1 * ol.j1);
         }
         const double sc = lm_scale[l];
         double d2 = sc * sc * hll;
         d2 = fmin(fmax(d2, 1.0e-6), 1.0e32);
         const double vl = sc * sc * aux[l].gl / d2;
-        for (int j = 0; j < n_obs; ++j) {
+        for (unsigned j = 0, fm = lm_mask(lr.meta); j < (unsigned)n_obs; ++j, fm &= fm - 1) {
             const ObsRec o = obs[lr.obs_begin + j];
+            const int of = __ffs(fm) - 1;
             ObsLin ol;
-            linearize_obs<kLoss>(F[o.frame], x, xf, cl, o.zx, o.zy, W, cb, ol);
+            linearize_obs<kLoss>(F[of], x, xf, cl, o.zx, o.zy, W, cb, ol);
             double r0 = (double)ol.j0 * vl, r1 = (double)ol.j1 * vl;
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                const double dv = vxi[o.frame][i] - vxi[anchor][i];
+                const double dv = vxi[of][i] - vxi[anchor][i];
                 r0 += (double)ol.Y0[i] * dv; r1 += (double)ol.Y1[i] * dv;
             }
             acc += r0 * r0 + r1 * r1;

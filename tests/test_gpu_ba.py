@@ -64,8 +64,7 @@ def test_gn_step_cfg2b_staggered(ba):
     _check_step(ba, w, st)
 
 
-def test_gn_step_unsorted_landmarks_and_ragged(ba):
-    """Landmarks in arbitrary anchor order, tracks of length 1..N-1, a landmark seen once."""
+def _ragged_window():
     w, st, _ = synth.make_cfg2(N=7, M=90, staggered=True, seed=5)
     rng = np.random.default_rng(1)
     perm = rng.permutation(w.M)
@@ -82,6 +81,12 @@ def test_gn_step_unsorted_landmarks_and_ragged(ba):
     w.K = len(of)
     st.rho = st.rho[perm]
     w.validate()
+    return w, st
+
+
+def test_gn_step_unsorted_landmarks_and_ragged(ba):
+    """Landmarks in arbitrary anchor order, tracks of length 1..N-1, a landmark seen once."""
+    w, st = _ragged_window()
     _check_step(ba, w, st)
 
 
@@ -124,6 +129,47 @@ def test_gn_step_cfg4_planes(ba):
     w, st, _ = synth.make_cfg4()
     assert w.n_ptracks == 80
     _check_step(ba, w, st)
+
+
+@pytest.mark.parametrize("use_tc", ["0", "1"])
+@pytest.mark.parametrize("case", ["cfg2", "cfg2b", "ragged", "cfg3", "cfg4", "cfg2_free"])
+def test_throughput_kernels_match_oracle(case, use_tc, monkeypatch):
+    """Batches of >= 74 windows run the thread-per-landmark linearise kernels: lin_tpl_kernel (CUDA-core
+    Schur SYRK, the default) and, with PVIO_B200_TC=1 and windows of <= 10 frames, lin_tc_kernel (tcgen05
+    3xTF32 Schur SYRK).  Both against the oracle step on the same windows."""
+    monkeypatch.setenv("PVIO_B200_TC", use_tc)
+    if case == "cfg2":
+        w, st, _ = synth.make_cfg2()
+    elif case == "cfg2b":
+        w, st, _ = synth.make_cfg2(staggered=True)
+    elif case == "ragged":
+        w, st = _ragged_window()
+    elif case == "cfg3":
+        w, st, _ = synth.make_cfg3()
+    elif case == "cfg4":
+        w, st, _ = synth.make_cfg4()
+    else:
+        w, st, _ = synth.make_cfg2(N=8, M=200, seed=31)
+        w.frame_fixed[:] = 0
+        w.frame_fixed[0] = 1
+        w.frame_fixed[3] = 1           # non-contiguous fixed frames (free-frame enumeration of the Schur tiles)
+    W = 160
+    b = BundleAdjustor(max_windows=W, max_frames=10, max_landmarks=640, max_obs=6000)
+    b.batch_set(0, w, st)
+    b.batch_replicate(W)
+    b.batch_upload(W)
+    b.batch_gn_step(W, 1e-8, apply=False)
+    stride = 15 * w.N + w.M
+    dx, costs = b.batch_download(W, stride)
+    b.close()
+    ref = bo.gn_step(w, st, schur=True)
+    tol = TOL_DX
+    for i in (0, W - 1):
+        e = _rel(dx[i], ref['dx'])
+        print(case, "use_tc", use_tc, "window", i, "dx rel err", e)
+        assert e < tol
+        assert abs(costs[i, 0] - ref['cost']) <= 2e-6 * ref['cost']
+    assert np.array_equal(dx[0], dx[W - 1])
 
 
 def test_batch_replicas_agree(ba):
