@@ -366,7 +366,11 @@ static size_t solve_smem(Handle *h, int w0, int n, bool lean) {
     size_t best = 0;
     for (int i = w0; i < w0 + n; ++i) {
         const WinHdr &H = h->hdr.h[i];
-        const size_t D = (H.use_inertial ? 15 : 6) * (size_t)H.N;
+        size_t D = (H.use_inertial ? 15 : 6) * (size_t)H.N;
+        if (lean) {                       // the lean kernel drops constant frames from the system
+            const int nfree = H.N - __builtin_popcount((unsigned)H.fixed_mask & ((1u << H.N) - 1u));
+            if (nfree > 0) D = 6 * (size_t)nfree;
+        }
         const size_t nb = (D + 3) / 4, Dp = nb * 4;
         const size_t np_ = (size_t)H.N * (H.N + 1) / 2;
         size_t scr = lean ? Dp + 10 * 36 + 36 : std::max<size_t>(Dp, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);

@@ -435,7 +435,15 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     const int N = H.N;
     const int inertial = H.use_inertial;
     const int stride = inertial ? 15 : 6;
-    const int D = stride * N;
+    // Visual-only windows: FF_FIX_POSE frames are constant parameter blocks (bundle_adjustor.cpp:82-87), so the
+    // lean kernel leaves them out of the system altogether (cfg2: 48 instead of 60 unknowns, half the
+    // factorisation); the full kernel keeps every frame (velocity / bias blocks stay free) and pins the pose rows.
+    const unsigned allm = (1u << N) - 1u;
+    const bool compact = !kFull && ((~(unsigned)H.fixed_mask) & allm) != 0u;
+    const unsigned freem = compact ? (allm & ~(unsigned)H.fixed_mask) : allm;
+    const int nfr = __popc(freem);
+    const int D = stride * nfr;
+    const int mask_c = compact ? 0 : H.fixed_mask;           // pose rows to pin, in the system's own frame numbering
     const int tid = threadIdx.x, nt = blockDim.x;
     const double *frames = a.frames + (size_t)w * a.Ncap * kFrameStride;
     WinCtrl &ctrl = a.ctrl[w];
@@ -491,8 +499,9 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         const double *gdir = a.gdir + (size_t)w * a.Ncap * 6;
         const double *gred = a.gred + (size_t)w * a.Ncap * 6;
         double *Ms = scr + Dp;                       // [G][36]
-        for (int e = tid; e < N * 6; e += nt) {      // direct diagonal diag(T_f^T Xd T_f)
-            const int f = e / 6, i = e - f * 6;
+        for (int e = tid; e < nfr * 6; e += nt) {    // direct diagonal diag(T_f^T Xd T_f)
+            const int cf = e / 6, i = e - cf * 6;
+            const int f = __fns(freem, 0, cf + 1);
             const double *Tf = T + f * 36, *X = Hdd + f * 36;
             double sd = 0.0;
             for (int aa = 0; aa < 6; ++aa) {
@@ -500,18 +509,20 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
                 for (int bb = 0; bb < 6; ++bb) t += X[aa * 6 + bb] * Tf[bb * 6 + i];
                 sd += Tf[aa * 6 + i] * t;
             }
-            hcorr[f * stride + i] = sd;
+            hcorr[cf * stride + i] = sd;
         }
         const int G = nt / 6;
         const int q = tid / 6, i6 = tid - q * 6;
-        for (int p0 = 0; p0 < npairs; p0 += G) {
+        const int npf = nfr * (nfr + 1) / 2;         // block pairs of the free frames
+        for (int p0 = 0; p0 < npf; p0 += G) {
             const int p = p0 + q;
-            const bool act = q < G && p < npairs;
-            int f = 0, gf = 0;
+            const bool act = q < G && p < npf;
+            int f = 0, gf = 0, cf = 0, cg = 0;
             if (act) {
-                while ((f + 1) * (f + 2) / 2 <= p) ++f;
-                gf = p - f * (f + 1) / 2;
-                const double *X = Hred + p * 36 + i6 * 6, *Tg = T + gf * 36;
+                while ((cf + 1) * (cf + 2) / 2 <= p) ++cf;
+                cg = p - cf * (cf + 1) / 2;
+                f = __fns(freem, 0, cf + 1); gf = __fns(freem, 0, cg + 1);
+                const double *X = Hred + (f * (f + 1) / 2 + gf) * 36 + i6 * 6, *Tg = T + gf * 36;
                 double x[6];
 #pragma unroll
                 for (int bb = 0; bb < 6; ++bb) x[bb] = X[bb];
@@ -529,24 +540,25 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
                 const int j = i6;                        // this thread produces column j of T_f^T M
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
-                    if (f == gf && j > i) continue;
+                    if (cf == cg && j > i) continue;
                     double sv = 0.0;
 #pragma unroll
                     for (int aa = 0; aa < 6; ++aa) sv += Tf[aa * 6 + i] * Ms[q * 36 + aa * 6 + j];
-                    const int gi = f * stride + i, gj = gf * stride + j;
+                    const int gi = cf * stride + i, gj = cg * stride + j;
                     A[tri(gi, gj)] = sv;
-                    if (f == gf && i == j) hcorr[gi] -= sv;
+                    if (cf == cg && i == j) hcorr[gi] -= sv;
                 }
             }
             __syncthreads();
         }
-        for (int e = tid; e < N * 6; e += nt) {
-            const int f = e / 6, i = e - f * 6;
+        for (int e = tid; e < nfr * 6; e += nt) {
+            const int cf = e / 6, i = e - cf * 6;
+            const int f = __fns(freem, 0, cf + 1);
             const double *Tf = T + f * 36;
             double sr = 0.0, sd = 0.0;
             for (int aa = 0; aa < 6; ++aa) { sr += Tf[aa * 6 + i] * gred[f * 6 + aa]; sd += Tf[aa * 6 + i] * gdir[f * 6 + aa]; }
-            g[f * stride + i] = sr;
-            gu[f * stride + i] = sd;
+            g[cf * stride + i] = sr;
+            gu[cf * stride + i] = sd;
         }
     } else
     // ---- vision blocks: H_delta[f,gf] = T_f^T X T_g.  Stage the xi-coordinate blocks in shared
@@ -758,10 +770,15 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         double *Ho = a.Hfull + (size_t)w * Df * Df, *go = a.gfull + (size_t)w * Df;
         for (int e = tid; e < D * D; e += nt) {
             const int i = e / D, j = e - i * D;
-            const int fi = i / stride, ci = i - fi * stride, fj = j / stride, cj = j - fj * stride;
+            int fi = i / stride, fj = j / stride;
+            const int ci = i - fi * stride, cj = j - fj * stride;
+            if (compact) { fi = __fns(freem, 0, fi + 1); fj = __fns(freem, 0, fj + 1); }     // back to the window's frame ids
             Ho[(size_t)(fi * 15 + ci) * Df + fj * 15 + cj] = (i >= j) ? A[tri(i, j)] : A[tri(j, i)];
         }
-        for (int i = tid; i < D; i += nt) go[(i / stride) * 15 + (i % stride)] = g[i];
+        for (int i = tid; i < D; i += nt) {
+            const int fi = i / stride;
+            go[(compact ? __fns(freem, 0, fi + 1) : fi) * 15 + (i % stride)] = g[i];
+        }
     }
 
     STAMP();   // 3: factors done
@@ -780,7 +797,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         hcorr[i] = hii;                                       // now holds the unreduced diagonal
     }
     __syncthreads();
-    const int fixed_mask = H.fixed_mask;
+    const int fixed_mask = mask_c;
     for (int e = tid; e < Dp * Dp; e += nt) {
         const int i = e / Dp, j = e - i * Dp;
         if (j > i) continue;
@@ -807,7 +824,8 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     double *dxo = a.dx_pose + (size_t)w * a.Ncap * 15;
     for (int i = tid; i < N * 15; i += nt) {
         const int f = i / 15, c = i - f * 15;
-        dxo[i] = (ok && c < stride) ? xs[f * stride + c] : 0.0;
+        const bool in_sys = (freem >> f) & 1u;               // dropped (constant) frames do not move
+        dxo[i] = (ok && c < stride && in_sys) ? xs[__popc(freem & ((1u << f) - 1u)) * stride + c] : 0.0;
     }
     {
         double gdx = 0.0, rdx = 0.0, gn2 = 0.0, dx2 = 0.0, gmax = 0.0, g2 = 0.0, vrd = 0.0;
@@ -824,7 +842,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             // NOTE: the reduced gradient g and the unreduced gu differ only through the Schur term;
             // g . dx over the full system is completed by the landmark sweep (acc[1])
             const double v = sc * sc * gu[i] / d2;
-            vpo[f * 15 + c] = v;
+            vpo[(compact ? __fns(freem, 0, f + 1) : f) * 15 + c] = v;
             gdx += g[i] * dx;
             rdx += reg_keep[i] * dx * dx;
             gn2 += d2 * (dx / sc) * (dx / sc);
@@ -851,7 +869,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             double x2 = 0.0;
             for (int f = 0; f < N; ++f) {
                 const double *fs = frames + f * kFrameStride;
-                if (!((fixed_mask >> f) & 1)) for (int k = 0; k < 7; ++k) x2 += fs[k] * fs[k];
+                if (!((H.fixed_mask >> f) & 1)) for (int k = 0; k < 7; ++k) x2 += fs[k] * fs[k];
                 if (inertial) for (int k = 7; k < 16; ++k) x2 += fs[k] * fs[k];
             }
             ctrl.g_dot_dx = gdx;

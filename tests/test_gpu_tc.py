@@ -23,5 +23,5 @@ def test_syrk_3xtf32(K):
     # error relative to the magnitude sum |a_m|.|a_n| (what a dot product's rounding is measured against)
     mag = np.abs(A).astype(np.float64).T @ np.abs(A).astype(np.float64) + 1e-300
     err = np.max(np.abs(D - ref) / mag)
-    print('K', K, 'max err / mag', err, 'diag bias', np.mean(np.diag(D - ref) / np.diag(ref)))
+    print('K', K, 'max err / mag', err, 'diag bias', np.mean(np.diag(D - ref)[:61] / np.diag(ref)[:61]))
     assert err < 2e-6, err          # 3xTF32: ~2^-21; one TF32 pass would be ~1e-3
