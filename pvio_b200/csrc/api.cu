@@ -239,7 +239,7 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
         lm[lp].meta = lm_meta(a, (w->lm_in_victim && w->lm_in_victim[l]) ? 1 : 0, n, seen);
         // chunks: <= kChunk landmarks of one anchor
         if (nch == 0 || (H.chunk_meta[nch - 1] >> 8) != a || (H.chunk_meta[nch - 1] & 0xff) == kChunk) {
-            if (nch == kMaxChunks) return fail(h, PVIO_B200_EINVAL, "too many landmark chunks");
+            if (nch == kMaxChunks || nch == h->Mcap / 32 + h->Ncap + 1) return fail(h, PVIO_B200_EINVAL, "too many landmark chunks");
             H.chunk_begin[nch] = lp;
             H.chunk_meta[nch] = (a << 8);
             ++nch;
@@ -390,7 +390,7 @@ static int run_linearize(Handle *h, int n, const StepCfg &c) {
     (void)npc;
     LinArgs a;
     a.hdr = h->hdr.d; a.cst = h->cst.d; a.obs = h->obs.d; a.lms = h->lms.d; a.rho = h->rho.d; a.frames = h->frames.d;
-    a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d;
+    a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d; a.hs_out = h->hs.d; a.hs_stride = h->hs_stride;
     a.Hred = h->Hred.d; a.Hdd = h->Hdd.d; a.gdir = h->gdir.d; a.gred = h->gred.d; a.cost_vis = h->cost_vis.d;
     a.Ncap = h->Ncap; a.Mcap = h->Mcap; a.Kcap = h->Kcap;
     a.compute_scale = c.compute_scale; a.victim_only = 0; a.mu_override = c.mu; a.w0 = c.w0;
@@ -481,7 +481,7 @@ static int run_jv(Handle *h, const StepCfg &c) {
     UpdArgs u;
     memset(&u, 0, sizeof(u));
     u.hdr = h->hdr.d; u.cst = h->cst.d; u.obs = h->obs.d; u.lms = h->lms.d; u.rho = h->rho.d; u.frames = h->frames.d;
-    u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.dx_pose = h->dx_pose.d; u.acc = h->acc.d;
+    u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.hs = h->hs.d; u.hs_stride = h->hs_stride; u.dx_pose = h->dx_pose.d; u.acc = h->acc.d;
     u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.w0 = 0; u.v_pose = h->v_pose.d;
     jv_vision_kernel<true><<<dim3(16, 1), kLinThreads, 0, st>>>(u);
     JvAuxArgs ja;
@@ -498,7 +498,7 @@ static int run_update(Handle *h, int n, const StepCfg &c) {
     CK(h, cudaMemsetAsync(h->acc.d + (size_t)kAcc * c.w0, 0, sizeof(double) * kAcc * n, st));
     UpdArgs u;
     u.hdr = h->hdr.d; u.cst = h->cst.d; u.obs = h->obs.d; u.lms = h->lms.d; u.rho = h->rho.d; u.frames = h->frames.d;
-    u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.dx_pose = h->dx_pose.d;
+    u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.hs = h->hs.d; u.hs_stride = h->hs_stride; u.dx_pose = h->dx_pose.d;
     u.rho_cand = h->rho_cand.d; u.frames_cand = h->frames_cand.d; u.dx_lm = h->dx_lm.d; u.acc = h->acc.d;
     u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.w0 = c.w0;
     u.step_a = c.step_a; u.step_b = c.step_b >= 0.0 ? c.step_b : c.beta; u.v_pose = h->v_pose.d;
@@ -620,6 +620,8 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     TRY(alloc(h, h->ctrl, W, true));
     TRY(alloc(h, h->rho_cand, W * M, false)); TRY(alloc(h, h->frames_cand, W * N * kFrameStride, false));
     TRY(alloc(h, h->lm_scale, W * M, false)); TRY(alloc(h, h->lm_aux, W * M, false));
+    h->hs_stride = (size_t)(M / 32 + N + 1) * 32 * N * 6;
+    TRY(alloc(h, h->hs, W * h->hs_stride, false));
     TRY(alloc(h, h->dx_lm, W * M, true)); TRY(alloc(h, h->dx_pose, W * N * 15, true));
     TRY(alloc(h, h->pose_scale, W * N * 15, false)); TRY(alloc(h, h->v_pose, W * N * 15, false));
     {   // the reduced-system outputs of the linearise kernel live in ONE allocation so that the
@@ -658,7 +660,7 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     cudaStreamSynchronize(h->stream);
     klt_free(h);
     release(h->hdr); release(h->cst); release(h->obs); release(h->lms); release(h->rho); release(h->frames);
-    release(h->ctrl); release(h->rho_cand); release(h->frames_cand); release(h->lm_scale); release(h->lm_aux);
+    release(h->ctrl); release(h->rho_cand); release(h->frames_cand); release(h->lm_scale); release(h->lm_aux); release(h->hs);
     release(h->dx_lm); release(h->dx_pose); release(h->pose_scale); release(h->v_pose); release(h->Hred);
     release(h->acc); release(h->aux_cost);
     release(h->Hfull); release(h->gfull);

@@ -41,6 +41,8 @@ struct Handle {
     DevBuf<WinCtrl> ctrl;
     DevBuf<double> rho_cand, frames_cand, lm_scale, dx_lm, dx_pose, pose_scale, v_pose;
     DevBuf<LmAux> lm_aux;
+    DevBuf<float> hs;                            // [W][hs_stride] sqrt(w_l) h_l records, linearise -> update
+    size_t hs_stride = 0;                        // (Mcap / 32 + Ncap + 1) chunks x 32 slots x 6 Ncap floats
     DevBuf<double> Hred, Hdd, gdir, gred, cost_vis, acc, aux_cost;
     DevBuf<double> Hfull, gfull;                 // debug dump (single window only)
     // inertial / prior / planes (allocated on first use)

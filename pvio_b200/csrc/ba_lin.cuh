@@ -178,6 +178,11 @@ struct LinArgs {
     const WinCtrl *ctrl;     // [W] (mu)
     double *lm_scale;        // [W][Mcap] Jacobi scale of each inverse depth (fixed at iteration 0)
     LmAux *lm_aux;           // [W][Mcap]
+    float *hs_out;           // [W][hs_stride]: sqrt(w_l) h_l for the back-substitution of the update kernel, one
+                             // record of 6 N floats per landmark SLOT (chunk * 32 + lane): the layout of the
+                             // kernels' shared-memory h buffer, so a warp's records leave as one bulk copy.
+                             // nullptr: not wanted (marginaliser)
+    size_t hs_stride;        // floats per window
     double *Hred;            // [W][npairs_cap][36] block-lower-triangular reduced system (xi coords)
     double *Hdd;             // [W][Ncap][36] direct (pre-Schur) diagonal blocks (xi coords)
     double *gdir;            // [W][Ncap][6] direct gradient (xi coords)
@@ -324,8 +329,13 @@ lin_schur_kernel(LinArgs a) {
                 const float wlf = finite ? (float)wl : 0.f;
                 const float sw = sqrtf(wlf);
                 const float wg = wlf * (float)gl_d;
-                if (lane == 0) { aux[l].hll_reg = hreg; aux[l].gl = gl_d; }
+                if (lane == 0) { aux[l].hll_reg = hreg; aux[l].gl = gl_d; aux[l].hll = hll_d; }
                 float *hb = hbuf + (s * kMaxFrames + lane) * 8;
+                if (a.hs_out && (observed || lane == anchor)) {
+                    float *hs = a.hs_out + (size_t)w * a.hs_stride + ((size_t)(ch * 32 + s) * N + lane) * 6;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) hs[i] = (observed ? h[i] : -ha[i]) * sw;
+                }
                 if (observed) {
 #pragma unroll
                     for (int i = 0; i < 6; ++i) hb[i] = h[i] * sw;
@@ -347,7 +357,7 @@ lin_schur_kernel(LinArgs a) {
                 if (lane == 0) msk[s] = finite ? (tmask | (1 << anchor)) : 0;
             } else if (lane == 0) {
                 msk[s] = 0;
-                if (lm_ok && !a.victim_only) { aux[l].hll_reg = 1.0; aux[l].gl = 0.0; }
+                if (lm_ok && !a.victim_only) { aux[l].hll_reg = 1.0; aux[l].gl = 0.0; aux[l].hll = 0.0; }
             }
         }
         // stage the per-group frame accumulators

@@ -75,7 +75,7 @@ __host__ __device__ inline size_t lin2_smem_bytes(int N) {
            + sizeof(float) * ((size_t)kSuper * N * 6)    // scaled h vectors
            + sizeof(float) * kSuper                      // sqrt(w) g_l
            + sizeof(int) * kSuper                        // touched-frame masks
-           + sizeof(double) * 8;
+           + sizeof(double) * 8 + 16;                    // + alignment slack of the h buffer
 }
 
 // Epilogue shared by the thread-per-landmark kernels: assemble the direct blocks, subtract the Schur sum.
@@ -144,7 +144,8 @@ lin_tpl_kernel(LinArgs a) {
     double *Ss = reinterpret_cast<double *>(F + kMaxFrames);        // [npairs][36] Schur sum
     double *Dta = Ss + npairs * 36;                                 // [nsp][33] direct blocks: 21 sym + 6 grad (+6 pad)
     double *gsc = Dta + (nsp + 1) * 33;                             // [N][6] sum_l w g_l h_f
-    float *hbuf = reinterpret_cast<float *>(gsc + N * 6);           // [kSuper][N][6]
+    // [kSuper][N][6], 16-byte aligned (offset arithmetic keeps the shared address space): bulk-copy source
+    float *hbuf = reinterpret_cast<float *>(smem_raw + ((sizeof(FrameSm) * kMaxFrames + sizeof(double) * (npairs * 36 + (nsp + 1) * 33 + N * 6) + 15) & ~(size_t)15));
     float *sgb = hbuf + kSuper * N * 6;                             // [kSuper] sqrt(w) g_l
     int *msk = reinterpret_cast<int *>(sgb + kSuper);               // [kSuper]
     double *cost_sm = reinterpret_cast<double *>(msk + kSuper);     // [8]
@@ -209,6 +210,9 @@ lin_tpl_kernel(LinArgs a) {
             float ha[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             int tmask = 0;
             float *hb = hbuf + (size_t)slot * N * 6;
+            // the previous pass's bulk copy of this warp's records must have read the buffer before it is rewritten
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
             for (int j = 0; j < n_max; ++j) {
                 const bool act = j < n_obs;
                 ObsRec o;
@@ -265,7 +269,7 @@ lin_tpl_kernel(LinArgs a) {
                 const double wl = 1.0 / hreg;
                 const bool finite = isfinite(wl);                 // bundle_adjustor.cpp:538 skip
                 const float sw = finite ? sqrtf((float)wl) : 0.f;
-                aux[l].hll_reg = hreg; aux[l].gl = gl;
+                aux[l].hll_reg = hreg; aux[l].gl = gl; aux[l].hll = hll;
                 int m = tmask;
                 while (m) {
                     const int t = __ffs(m) - 1;
@@ -280,7 +284,20 @@ lin_tpl_kernel(LinArgs a) {
             } else {
                 msk[slot] = 0;
                 sgb[slot] = 0.f;
-                if (lm_ok && !a.victim_only) { aux[l].hll_reg = 1.0; aux[l].gl = 0.0; }
+                if (lm_ok && !a.victim_only) { aux[l].hll_reg = 1.0; aux[l].gl = 0.0; aux[l].hll = 0.0; }
+            }
+            // the warp's 32 records of 6 N floats go to the update kernel as ONE bulk copy (TMA engine, no LSU
+            // instructions): shared -> global, read completion awaited before the next pass reuses the buffer
+            if (a.hs_out && ch_ok) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    float *dst = a.hs_out + (size_t)w * a.hs_stride + (size_t)ch * 32 * N * 6;
+                    const float *src = hbuf + (size_t)wv * 32 * N * 6;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src)), "r"(32 * N * 6 * 4) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             }
         }
         __syncthreads();
@@ -346,6 +363,7 @@ lin_tpl_kernel(LinArgs a) {
         }
         __syncthreads();
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // before the h buffer is freed
 
     lin_epilogue(a, w, N, tid, Ss, Dta, gsc);
     double cd = (double)cost_acc;

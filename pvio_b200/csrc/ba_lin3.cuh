@@ -249,10 +249,11 @@ lin_tc_kernel(LinArgs a) {
             const double wl = 1.0 / hreg;
             const bool finite = isfinite(wl);                       // bundle_adjustor.cpp:538 skip
             sw = finite ? sqrtf((float)wl) : 0.f;
-            if (!h2) { aux[l].hll_reg = hreg; aux[l].gl = gl; }
+            if (!h2) { aux[l].hll_reg = hreg; aux[l].gl = gl; aux[l].hll = hll; }
         } else if (lm_ok && !a.victim_only && !h2) {
-            aux[l].hll_reg = 1.0; aux[l].gl = 0.0;
+            aux[l].hll_reg = 1.0; aux[l].gl = 0.0; aux[l].hll = 0.0;
         }
+        float *hs = (a.hs_out && n_obs > 0) ? a.hs_out + (size_t)w * a.hs_stride + (size_t)(ch * 32 + li) * N * 6 : nullptr;
         __syncwarp();                                               // the partner's unscaled h values
         // ---- column `slot` of A: every row below 6 N + 1 is (re)written, zeros where the landmark is not seen
         for (int f = h2; f < N; f += 2) {
@@ -264,7 +265,13 @@ lin_tc_kernel(LinArgs a) {
             for (int i = 0; i < 6; ++i) {
                 const int off = tc::frame_row_off(rb, cross, i);
                 float hi = 0.f, lo = 0.f;
-                if (live) tc::split_tf32((is_anchor ? ha[i] : a_hi[off]) * sw, hi, lo);
+                if (live) {
+                    const float v = (is_anchor ? ha[i] : a_hi[off]) * sw;
+                    tc::split_tf32(v, hi, lo);
+                    if (hs) hs[f * 6 + i] = v;
+                } else if (hs && (is_anchor || is_seen)) {
+                    hs[f * 6 + i] = 0.f;
+                }
                 a_hi[off] = hi;
                 a_lo[off] = lo;
             }

@@ -336,7 +336,7 @@ int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state
     (void)npc;
     LinArgs a;
     a.hdr = h->hdr.d; a.cst = h->cst.d; a.obs = h->obs.d; a.lms = h->lms.d; a.rho = h->rho.d; a.frames = h->frames.d;
-    a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d;
+    a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d; a.hs_out = nullptr; a.hs_stride = 0;
     a.Hred = h->Hred.d; a.Hdd = h->Hdd.d; a.gdir = h->gdir.d; a.gred = h->gred.d; a.cost_vis = h->cost_vis.d;
     a.Ncap = h->Ncap; a.Mcap = h->Mcap; a.Kcap = h->Kcap;
     a.compute_scale = 1; a.victim_only = 1; a.mu_override = 0.0; a.w0 = 0;

@@ -72,6 +72,8 @@ struct WinCtrl {                    // per-window solver state (device resident)
 struct __align__(16) LmAux {
     double hll_reg;                 // H_ll + mu * clamp(.)  (the pivot the Schur complement divides by)
     double gl;                      // g_l
+    double hll;                     // H_ll
+    double pad;
 };
 
 }  // namespace pvio

@@ -5,9 +5,10 @@
 //   d rho_l = -(g_l + h_l . dxi) / (H_ll + reg)                 back-substitution
 //   candidate = Plus(x, dx)         (quaternion_parameterization.h:28-31, plain + elsewhere)
 //   candidate cost = sum rho(|r|^2)/2 over the reprojection blocks   (step acceptance)
-// and accumulates the scalars the trust-region logic needs.  h_l is recomputed from the
-// observation table (16 B/observation re-read) instead of being stored (6 floats per
-// touched frame per landmark written + read).
+// and accumulates the scalars the trust-region logic needs.  sqrt(w_l) h_l comes from the linearise kernel
+// (LinArgs::hs_out: one record of 6 N floats per landmark slot, written there by bulk copies).  Recomputing it from the observation table costs one full linearisation per observation and was
+// 60 % of this kernel's instructions (profiles/r01d_update.md); the kernels are issue-bound and HBM is at
+// 5 % of its bandwidth, so 2 x 108 KB of extra traffic per window are the cheaper side of the trade.
 #pragma once
 #include "ba_lin.cuh"
 
@@ -23,6 +24,8 @@ struct UpdArgs {
     const WinCtrl *ctrl;
     const double *lm_scale;
     const LmAux *lm_aux;
+    const float *hs;          // [W][hs_stride] from the linearise kernel (LinArgs::hs_out)
+    size_t hs_stride;
     const double *dx_pose;    // [W][Ncap][15] pose/motion step in delta coordinates
     double *rho_cand;         // [W][Mcap]
     double *frames_cand;      // [W][Ncap][16]
@@ -40,7 +43,7 @@ struct UpdArgs {
 
 // Second generation: one LANE per landmark (see ba_lin2.cuh).  Same outputs.
 template <bool kLoss>
-__global__ void __launch_bounds__(kLinThreads, 2)
+__global__ void __launch_bounds__(kLinThreads, 4)
 update_tpl_kernel(UpdArgs a) {
     const int w = blockIdx.y + a.w0;
     const WinHdr &H = a.hdr[w];
@@ -48,7 +51,6 @@ update_tpl_kernel(UpdArgs a) {
     const int N = H.N;
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
 
-    __shared__ FrameSm F[kMaxFrames];      // current state
     __shared__ FrameSm Fc[kMaxFrames];     // candidate state
     __shared__ double dxi[kMaxFrames][6];  // xi = T delta per frame
     __shared__ double red[8];
@@ -56,7 +58,6 @@ update_tpl_kernel(UpdArgs a) {
     if (tid < N) {
         const double *fs = a.frames + ((size_t)w * a.Ncap + tid) * kFrameStride;
         const double *d = a.dx_pose + ((size_t)w * a.Ncap + tid) * 15;
-        make_frame(fs, wc, F[tid]);
         double fc[kFrameStride];
         const double *vp = a.v_pose + ((size_t)w * a.Ncap + tid) * 15;
         double de[15];
@@ -114,23 +115,20 @@ update_tpl_kernel(UpdArgs a) {
         const LmRec lr = lms[l];
         const int n_obs = lm_nobs(lr.meta);
         const double rl = rho[l];
-        double x[3];
-        float xf[3], cl[3];
-        world_point(F[anchor], lr.zrx, lr.zry, rl, x, xf, cl);
         double hdx = 0.0, hll = 0.0;
-        for (unsigned j = 0, fm = lm_mask(lr.meta); j < (unsigned)n_obs; ++j, fm &= fm - 1) {
-            const ObsRec o = obs[lr.obs_begin + j];
-            const int of = __ffs(fm) - 1;
-            ObsLin ol;
-            linearize_obs<kLoss>(F[of], x, xf, cl, o.zx, o.zy, W, cb, ol);
-            hll += (double)(ol.j0 * ol.j0 + ol.j1 * ol.j1);
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-                hdx += (double)(ol.j0 * ol.Y0[i] + ol.j1 * ol.Y1[i]) * (dxi[of][i] - dxi[anchor][i]);
-        }
         double drho = 0.0;
         if (n_obs > 0) {
             const LmAux ax = aux[l];
+            hll = ax.hll;
+            // h_l . dxi = sqrt(H_ll + reg) * sum_f (sqrt(w) h_lf) . dxi_f over the observing frames and the anchor
+            const float2 *hs = reinterpret_cast<const float2 *>(a.hs + (size_t)w * a.hs_stride + (size_t)(ch * 32 + lane) * N * 6);
+            for (unsigned fm = lm_mask(lr.meta) | (1u << anchor); fm; fm &= fm - 1) {
+                const int f = __ffs(fm) - 1;
+                const float2 h01 = hs[f * 3], h23 = hs[f * 3 + 1], h45 = hs[f * 3 + 2];
+                hdx += (double)h01.x * dxi[f][0] + (double)h01.y * dxi[f][1] + (double)h23.x * dxi[f][2] +
+                       (double)h23.y * dxi[f][3] + (double)h45.x * dxi[f][4] + (double)h45.y * dxi[f][5];
+            }
+            hdx *= sqrt(ax.hll_reg);
             const double wl = 1.0 / ax.hll_reg;
             drho = isfinite(wl) ? -(ax.gl + hdx) * wl : 0.0;
             const double sc = lm_scale[l];
