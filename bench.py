@@ -225,7 +225,7 @@ def run_gpu(args):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_alg_per_window": balg, "windows_per_launch": W, "kernel_ms": lin_ms,
                 "kernel_share_of_step": lin_ms / (ms / args.steps),
-                "note": "algorithmic bytes / CUDA-event kernel time; DRAM traffic equals the algorithmic bytes (no re-reads); "
+                "note": "algorithmic bytes / CUDA-event kernel time; DRAM traffic = 56 KB read (8-byte observation records: below the 92 KB algorithmic figure) + 63 KB written, of which ~60 KB are the sqrt(w) h records handed to the update kernel (a deliberate trade: HBM is at 6 % while the SMs are issue-bound); "
                         "arithmetic intensity ~33 flop/B is above the fp32 ridge (11.5 flop/B), so on CUDA cores the kernel is "
                         "FP32-issue bound, see DESIGN.md 4.1"}
 
