@@ -141,7 +141,7 @@ def run_gpu(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from pvio_b200 import synth, klt, pnp
+    from pvio_b200 import synth, klt, pnp, imu
     from pvio_b200.bundle_adjustor import BundleAdjustor
 
     W = args.windows
@@ -281,6 +281,37 @@ def run_gpu(args):
     pnp_info = {"ms_per_solve_e2e": (time.perf_counter() - t0) * 1e3 / 20, "kernel_ms": psum["solve_seconds"] * 1e3,
                 "iterations": int(psum["iterations"]), "points": int(len(d['pts']))}
 
+    # ---- IMU pre-integration (PreIntegrator::integrate): 8 factors x 4096 windows, 40 samples each, host buffers in/out
+    rng = np.random.default_rng(648)
+    nf, ks = 32768, 40
+    tt = np.arange(ks) / 200.0
+    base = np.c_[tt, rng.normal(0, 0.3, (ks, 3)), rng.normal(0, 1.0, (ks, 3)) + np.array([0.0, 0.0, 9.81])]
+    factors = [(base, tt[-1] + 0.004, np.zeros(3), np.zeros(3))] * nf
+    noise = (np.eye(3) * 2.8791e-8, np.eye(3) * 4.0e-6, np.eye(3) * 3.7608e-10, np.eye(3) * 9.0e-6)
+    begin = np.arange(nf + 1, dtype=np.int32) * ks
+    samples = np.ascontiguousarray(np.tile(base, (nf, 1)))
+    t_end = np.full(nf, tt[-1] + 0.004); bias = np.zeros((nf, 6)); rec = np.zeros((nf, 288))
+    noise_a = np.ascontiguousarray(np.array([c.reshape(9) for c in noise]))
+    import ctypes as C
+    from pvio_b200 import _lib as L
+    fn = ba1.lib.pvio_b200_preintegrate
+    fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                   C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    call = lambda: fn(ba1.h, nf, L._ptr(begin, C.c_int32), L._ptr(samples, C.c_double), L._ptr(t_end, C.c_double),
+                      L._ptr(bias, C.c_double), L._ptr(noise_a, C.c_double), L._ptr(rec, C.c_double))
+    call()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        call()
+    imu_s = (time.perf_counter() - t0) / 3
+    from oracle import imu_oracle
+    t0 = time.perf_counter()
+    for _ in range(20):
+        imu_oracle.integrate(base, tt[-1] + 0.004, np.zeros(3), np.zeros(3), *noise)
+    imu_cpu = 20 / (time.perf_counter() - t0)
+    imu_info = {"factors_per_s_e2e": nf / imu_s, "factors": nf, "samples_per_factor": ks,
+                "numpy_oracle_factors_per_s_1core": imu_cpu}
+
     # ---- CPU baseline beside it (bounded sample, all host threads; plus one thread like num_threads=1)
     ncpu = os.cpu_count() or 1
     n_sample = max(256, 128 * ncpu)
@@ -302,7 +333,7 @@ def run_gpu(args):
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "note": "pvio_b200_batch_gn_step_host: pinned host buffers -> device, one GN iteration, dx back"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "single_window": single, "klt": klt_info, "pnp": pnp_info,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "single_window": single, "klt": klt_info, "pnp": pnp_info, "imu_preintegration": imu_info,
     }
     print(json.dumps(line))
     ba.close(); ba1.close()

@@ -216,6 +216,16 @@ typedef struct pvio_b200_pnp_problem {
 int pvio_b200_pnp_solve(pvio_b200_handle h, const pvio_b200_pnp_problem *problem, double *frame,
                         const pvio_b200_options *opt, pvio_b200_summary *summary);
 
+/* ---- IMU pre-integration ---------------------------------------------------------------- */
+/* PreIntegrator::integrate(t, bg, ba, true, true) (pvio/src/pvio/estimation/preintegrator.cpp:85-98) for
+ * n_factors independent factors, one warp each.  samples: rows (t, w xyz, a xyz) of every factor back to
+ * back, begin[n_factors + 1] the CSR offsets; the last sample of a factor is integrated up to t_end[i].
+ * bias: [n_factors][6] (bg, ba) -- the biases of the factor's FIRST frame (bundle_adjustor.cpp:228).
+ * noise_cov: [4][9] row-major 3x3 cov_w, cov_a, cov_bg, cov_ba (preintegrator.h:63-66).
+ * records: [n_factors][PVIO_B200_IMU_STRIDE], the layout pvio_b200_window::imu_data takes. */
+int pvio_b200_preintegrate(pvio_b200_handle h, int n_factors, const int32_t *begin, const double *samples,
+                           const double *t_end, const double *bias, const double *noise_cov, double *records);
+
 /* ---- diagnostics ---------------------------------------------------------------------- */
 /* Self-test of the tcgen05 3xTF32 SYRK block used by the linearise kernel: D[64][64] = sum_k a_k a_k^T
  * for K rows of 64 floats (A is [K][64]).  Not part of the reference interface. */

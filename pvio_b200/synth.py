@@ -234,6 +234,7 @@ def make_cfg3(seed=649, N=9, M=300, cal=EUROC, planes=0, tracks_per_plane=40, pr
     w.imu_frame_i = np.arange(0, N - 1, dtype=np.int32)
     w.imu_frame_j = np.arange(1, N, dtype=np.int32)
     recs = []
+    raw_factors = []            # (samples [K][7], t_end, bg, ba) per factor, for the device pre-integrator
     dt = 1.0 / imu_hz
     for j in range(1, N):
         pre = so3.PreIntegrator(cal['cov_g'], cal['cov_a'], cal['cov_bg'], cal['cov_ba'])
@@ -249,6 +250,9 @@ def make_cfg3(seed=649, N=9, M=300, cal=EUROC, planes=0, tracks_per_plane=40, pr
             acc = a_true + ba_t[j - 1] + rng.normal(0, np.sqrt(cal['cov_a'] * imu_hz), 3)
             pre.data.append((t, gyro, acc))
         recs.append(pre.integrate(t1, st.bg[j - 1], st.ba[j - 1]))
+        raw_factors.append((np.array([np.r_[t_, g_, a_] for t_, g_, a_ in pre.data]), t1, st.bg[j - 1].copy(), st.ba[j - 1].copy()))
+    truth.imu_factors = raw_factors
+    truth.imu_noise = tuple(np.eye(3) * cal[k] for k in ('cov_g', 'cov_a', 'cov_bg', 'cov_ba'))
     w.imu_dt = np.array([r['dt'] for r in recs])
     w.imu_dq = np.array([r['dq'] for r in recs])
     w.imu_dp = np.array([r['dp'] for r in recs])
