@@ -226,6 +226,17 @@ int pvio_b200_pnp_solve(pvio_b200_handle h, const pvio_b200_pnp_problem *problem
 int pvio_b200_preintegrate(pvio_b200_handle h, int n_factors, const int32_t *begin, const double *samples,
                            const double *t_end, const double *bias, const double *noise_cov, double *records);
 
+/* ---- triangulation of new tracks ---------------------------------------------------------- */
+/* Track::triangulate (pvio/src/pvio/map/track.cpp:83-106): multi-view DLT (stereo.h:67-75) and the parallax /
+ * depth checks of triangulate_point_scored (stereo.h:104-128), one thread per track.
+ * P: [n_frames][12] row-major 3x4 [R | T] of the CAMERA in each frame (R = q_wc^-1, T = -R p_wc, track.cpp:90-95).
+ * begin / obs_frame / obs_z: CSR list of ALL keypoints of each track (>= 2 views).
+ * points: [n_tracks][3] (q.hnormalized() when valid; otherwise the unit direction, whose sign is that of the
+ * singular vector and as unspecified as in the reference, stereo.h:122-126);
+ * valid: has_parallax; score: mean squared reprojection error in normalised coordinates. */
+int pvio_b200_triangulate(pvio_b200_handle h, int n_frames, const double *P, int n_tracks, const int32_t *begin,
+                          const int32_t *obs_frame, const double *obs_z, double *points, uint8_t *valid, double *score);
+
 /* ---- diagnostics ---------------------------------------------------------------------- */
 /* Self-test of the tcgen05 3xTF32 SYRK block used by the linearise kernel: D[64][64] = sum_k a_k a_k^T
  * for K rows of 64 floats (A is [K][64]).  Not part of the reference interface. */
