@@ -23,4 +23,27 @@ print('reproj err', ba.compute_reprojection_error(w, st))
 prev, nxt, pts, _ = synth.make_klt_pair(size=(160, 120), n_points=20)
 p, s_, e_ = klt.track_keypoints(ba, prev, nxt, pts)
 print('klt', int(s_.sum()))
+# newer kernels: PnP, IMU pre-integration, triangulation, tensor-core SYRK (self-test and opt-in lin kernel)
+from pvio_b200 import pnp, imu, triangulate as tri
+from oracle import tri_oracle, lie
+d = synth.make_pnp()
+_, ps = pnp.visual_inertial_pnp(ba, d['frame'], d['last'], d['imu'], d['pts'], d['zs'], d['cam_q'], d['cam_p'], d['imu_q'], d['imu_p'], d['W'], True)
+print('pnp', ps['iterations'])
+_, _, truth = synth.make_cfg3(N=4, M=30)
+print('imu', np.linalg.norm(imu.preintegrate(ba, truth.imu_factors, truth.imu_noise)[:, :11]))
+P = np.array([tri_oracle.projection_matrix(lie.expmap(np.zeros(3)), np.array([0.3 * i, 0, 0])) for i in range(4)])
+X = np.array([0.2, 0.1, 5.0])
+zz = np.array([(P[f] @ np.r_[X, 1])[:2] / (P[f] @ np.r_[X, 1])[2] for f in range(4)])
+print('tri', tri.triangulate(ba, P, [0, 4], [0, 1, 2, 3], zz)[0])
+import ctypes as C
+A = np.random.default_rng(0).standard_normal((200, 64)).astype(np.float32); D = np.zeros((64, 64))
+ba.lib.pvio_b200_selftest_syrk.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_double)]
+print('syrk', ba.lib.pvio_b200_selftest_syrk(ba.h, A.ctypes.data_as(C.POINTER(C.c_float)), 200, D.ctypes.data_as(C.POINTER(C.c_double))), D[0, 0])
+ba.close()
+os.environ['PVIO_B200_TC'] = '1'
+ba = BundleAdjustor(max_windows=80, max_frames=8, max_landmarks=96, max_obs=800)
+for i in range(80):
+    ba.batch_set(i, w, st)
+ba.batch_upload(80); ba.batch_gn_step(80, 1e-8, apply=False); dx2, _ = ba.batch_download(80, 15 * 6 + 70)
+print('batch 80 (tcgen05 lin kernel)', np.linalg.norm(dx2[79]))
 ba.close()
