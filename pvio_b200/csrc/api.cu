@@ -790,8 +790,19 @@ int pvio_b200_batch_download(pvio_b200_handle hh, int n, double *dx, int64_t dx_
 int pvio_b200_batch_gn_step_host(pvio_b200_handle hh, int n, double mu, double *dx, int64_t dx_stride, double *costs) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (n < 1 || n > h->W) return fail(h, PVIO_B200_EINVAL, "bad window count");
-    const int sub = n >= 1024 ? 512 : n;
-    const int nsub = (n + sub - 1) / sub;
+    // sub-batch schedule: small batches first and last (the first upload and the last kernels + download are the
+    // only parts of the pipeline that nothing overlaps), 512-window batches in between
+    static const int sub_env = getenv("PVIO_B200_SUB") ? atoi(getenv("PVIO_B200_SUB")) : 0;     // uniform size (experiments)
+    std::vector<int> sizes;
+    if (n < 1024) sizes.push_back(n);
+    else if (sub_env > 0) { for (int r = n; r > 0; r -= sub_env) sizes.push_back(std::min(sub_env, r)); }
+    else {
+        int mid = n - 2 * (128 + 256);
+        sizes.push_back(128); sizes.push_back(256);
+        while (mid > 0) { const int m = std::min(512, mid); sizes.push_back(m); mid -= m; }
+        sizes.push_back(256); sizes.push_back(128);
+    }
+    const int nsub = (int)sizes.size();
     if (nsub == 1) {
         TRY(upload(h, n));
         StepCfg c;
@@ -799,6 +810,8 @@ int pvio_b200_batch_gn_step_host(pvio_b200_handle hh, int n, double mu, double *
         TRY(run_step(h, n, c));
         return download_dx(h, n, dx, dx_stride, costs);
     }
+    std::vector<int> starts(nsub, 0);
+    for (int i = 1; i < nsub; ++i) starts[i] = starts[i - 1] + sizes[i - 1];
     if (!h->stream_up) {
         CK(h, cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
         CK(h, cudaStreamCreateWithFlags(&h->stream_down, cudaStreamNonBlocking));
@@ -813,7 +826,7 @@ int pvio_b200_batch_gn_step_host(pvio_b200_handle hh, int n, double mu, double *
         h->ev_down.push_back(c_);
     }
     for (int i = 0; i < nsub; ++i) {
-        const int w0 = i * sub, m = std::min(sub, n - w0);
+        const int w0 = starts[i], m = sizes[i];
         TRY(upload_range(h, w0, m, h->stream_up));
         CK(h, cudaEventRecord(h->ev_up[i], h->stream_up));
         CK(h, cudaStreamWaitEvent(h->stream, h->ev_up[i], 0));
@@ -832,7 +845,7 @@ int pvio_b200_batch_gn_step_host(pvio_b200_handle hh, int n, double mu, double *
     h->n_uploaded = n;
     // scatter each sub-batch as soon as it has landed, while the GPU works on the later ones
     for (int i = 0; i < nsub; ++i) {
-        const int w0 = i * sub, m = std::min(sub, n - w0);
+        const int w0 = starts[i], m = sizes[i];
         CK(h, cudaEventSynchronize(h->ev_down[i]));
         TRY(scatter_dx(h, w0, m, dx, dx_stride, costs));
     }
