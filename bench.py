@@ -254,6 +254,14 @@ def run_gpu(args):
         klt.track_keypoints(ba1, prev, nxt, pts)
     klt_s = (time.perf_counter() - t0) / 20
     klt_info = {"tracks_per_s_e2e": len(pts) / klt_s, "ms_per_frame_pair": klt_s * 1e3, "points": int(len(pts))}
+    # from the RAW frames: CLAHE(6, 8x8) on the device + pyramids + LK (OpenCvImage::preprocess + track_keypoints)
+    klt.track_keypoints(ba1, prev, nxt, pts, clahe_clip=6.0)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        klt.track_keypoints(ba1, prev, nxt, pts, clahe_clip=6.0)
+    raw_s = (time.perf_counter() - t0) / 20
+    klt_info["raw_frames_tracks_per_s_e2e"] = len(pts) / raw_s
+    klt_info["raw_frames_ms_per_frame_pair"] = raw_s * 1e3
     try:
         import cv2
         crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
@@ -267,6 +275,13 @@ def run_gpu(args):
         cv_s = (time.perf_counter() - t0) / 10
         klt_info["cv2_tracks_per_s"] = len(pts) / cv_s
         klt_info["cv2_threads"] = cv2.getNumThreads()
+        cl = cv2.createCLAHE(6.0, (8, 8))
+        t0 = time.perf_counter()
+        for _ in range(10):
+            a_, b_ = cl.apply(prev), cl.apply(nxt)
+            cv2.calcOpticalFlowPyrLK(a_, b_, p0.copy(), p0.copy(), winSize=(21, 21), maxLevel=3, criteria=crit,
+                                     flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        klt_info["cv2_raw_frames_tracks_per_s"] = len(pts) / ((time.perf_counter() - t0) / 10)
     except Exception as e:      # cv2 is the reference's KLT; report if it is unavailable
         klt_info["cv2_tracks_per_s"] = None
         klt_info["cv2_error"] = str(e)

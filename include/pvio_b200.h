@@ -216,6 +216,20 @@ typedef struct pvio_b200_pnp_problem {
 int pvio_b200_pnp_solve(pvio_b200_handle h, const pvio_b200_pnp_problem *problem, double *frame,
                         const pvio_b200_options *opt, pvio_b200_summary *summary);
 
+/* Same, from the RAW 8-bit frames: CLAHE (cv::createCLAHE(clahe_clip, Size(tiles_x, tiles_y))->apply,
+ * pvio-extra/src/pvio/extra/opencv_image.cpp:138-143: clip 6.0, 8 x 8 tiles) runs on the device between the upload and
+ * the pyramid build, bit-exact with OpenCV.  width / height must be multiples of tiles_x / tiles_y (752x480 and
+ * 512x512 are).  prev_eq / next_eq (optional, [height][width]): the equalised frames, e.g. to hand to GFTT. */
+int pvio_b200_klt_track_raw(pvio_b200_handle h, const uint8_t *prev, const uint8_t *next,
+                            int width, int height, int stride, const float *prev_pts,
+                            float *next_pts, uint8_t *status, float *err, int n_points,
+                            int max_level, int max_iter, double eps, double clahe_clip, int tiles_x, int tiles_y,
+                            uint8_t *prev_eq, uint8_t *next_eq);
+
+/* CLAHE of one frame (same kernels); dst is [height][width]. */
+int pvio_b200_clahe(pvio_b200_handle h, const uint8_t *src, int width, int height, int stride, double clip_limit,
+                    int tiles_x, int tiles_y, uint8_t *dst);
+
 /* ---- IMU pre-integration ---------------------------------------------------------------- */
 /* PreIntegrator::integrate(t, bg, ba, true, true) (pvio/src/pvio/estimation/preintegrator.cpp:85-98) for
  * n_factors independent factors, one warp each.  samples: rows (t, w xyz, a xyz) of every factor back to

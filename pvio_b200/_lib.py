@@ -67,7 +67,7 @@ EXPORTS = [
     "pvio_b200_reprojection_error", "pvio_b200_batch_set_window", "pvio_b200_batch_replicate",
     "pvio_b200_batch_upload", "pvio_b200_batch_gn_step", "pvio_b200_batch_download",
     "pvio_b200_batch_gn_step_host", "pvio_b200_sync", "pvio_b200_timer_start", "pvio_b200_timer_stop",
-    "pvio_b200_last_kernel_ms", "pvio_b200_klt_track", "pvio_b200_pnp_solve", "pvio_b200_selftest_syrk", "pvio_b200_selftest_syrk_raw", "pvio_b200_preintegrate", "pvio_b200_triangulate",
+    "pvio_b200_last_kernel_ms", "pvio_b200_klt_track", "pvio_b200_pnp_solve", "pvio_b200_selftest_syrk", "pvio_b200_selftest_syrk_raw", "pvio_b200_preintegrate", "pvio_b200_triangulate", "pvio_b200_klt_track_raw", "pvio_b200_clahe",
 ]
 
 _lib = None

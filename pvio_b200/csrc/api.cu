@@ -1089,4 +1089,22 @@ int pvio_b200_klt_track(pvio_b200_handle hh, const uint8_t *prev, const uint8_t 
                           max_iter, eps);
 }
 
+int pvio_b200_klt_track_raw(pvio_b200_handle hh, const uint8_t *prev, const uint8_t *next, int width, int height, int stride,
+                            const float *prev_pts, float *next_pts, uint8_t *status, float *err, int n_points,
+                            int max_level, int max_iter, double eps, double clahe_clip, int tiles_x, int tiles_y,
+                            uint8_t *prev_eq, uint8_t *next_eq) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !prev || !next || !prev_pts || !next_pts || !status) return PVIO_B200_EINVAL;
+    if (!(clahe_clip > 0.0)) return fail(h, PVIO_B200_EINVAL, "klt_track_raw: clahe_clip must be positive");
+    return klt_track_impl(h, prev, next, width, height, stride, prev_pts, next_pts, status, err, n_points, max_level,
+                          max_iter, eps, clahe_clip, tiles_x, tiles_y, prev_eq, next_eq);
+}
+
+int pvio_b200_clahe(pvio_b200_handle hh, const uint8_t *src, int width, int height, int stride, double clip_limit,
+                    int tiles_x, int tiles_y, uint8_t *dst) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !src || !dst) return PVIO_B200_EINVAL;
+    return clahe_impl(h, src, width, height, stride, clip_limit, tiles_x, tiles_y, dst);
+}
+
 }  // extern "C"

@@ -28,6 +28,9 @@ struct KltState {
     int lw[kMaxLevels], lh[kMaxLevels];
     float *d_prev = nullptr, *d_next = nullptr, *d_err = nullptr;
     uint8_t *d_status = nullptr;
+    uint8_t *raw[2] = {nullptr, nullptr};     // pre-CLAHE level-0 images (raw entry point only)
+    uint8_t *lut = nullptr;                   // [2][tiles][256] CLAHE look-up tables
+    int lut_tiles = 0;
     uint8_t *h_img = nullptr;                 // pinned staging for both level-0 images
     float *h_pts = nullptr;                   // pinned: prev | next | err
     uint8_t *h_status = nullptr;
@@ -43,6 +46,86 @@ struct KltLevels {
 __device__ __forceinline__ int reflect101(int i, int n) {
     i = i < 0 ? -i : i;
     return i >= n ? 2 * (n - 1) - i : i;
+}
+
+// ---- CLAHE (cv::createCLAHE(clip, tiles)->apply, opencv_image.cpp:138-143; algorithm: OpenCV imgproc/clahe.cpp,
+// restated in oracle/clahe_oracle.py which is pinned bit for bit against cv2).  Image sizes that are multiples
+// of the tile grid only.  Kernel 1: one CTA per tile -- histogram in shared memory, clip + redistribute, prefix
+// sum, LUT = cvRound(cdf * 255 / area).  Kernel 2: one thread per pixel, bilinear blend of the four neighbouring
+// tiles' LUTs in OpenCV's float32 operation order (explicit _rn intrinsics: no FMA contraction).
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t *src, int w, int tw, int th, int tiles_x,
+                                                        int clip, float lut_scale, uint8_t *lut) {
+    __shared__ int hist[256];
+    __shared__ int wsum[8];
+    __shared__ int total_clipped;
+    const int t = blockIdx.x, tx = t % tiles_x, ty = t / tiles_x, tid = threadIdx.x;
+    hist[tid] = 0;
+    __syncthreads();
+    const uint8_t *base = src + (size_t)ty * th * w + (size_t)tx * tw;
+    for (int i = tid; i < tw * th; i += 256) atomicAdd(&hist[base[(size_t)(i / tw) * w + (i % tw)]], 1);
+    __syncthreads();
+    int hv = hist[tid];
+    int excess = max(hv - clip, 0);
+    hv = min(hv, clip);
+    int e = excess;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    if ((tid & 31) == 0) wsum[tid >> 5] = e;
+    __syncthreads();
+    if (tid == 0) { int s = 0; for (int k = 0; k < 8; ++k) s += wsum[k]; total_clipped = s; }
+    __syncthreads();
+    const int clipped = total_clipped;
+    const int batch = clipped / 256;
+    int residual = clipped - batch * 256;
+    hv += batch;
+    if (residual != 0) {
+        const int step = max(256 / residual, 1);
+        if (tid % step == 0 && tid / step < residual) hv += 1;       // bins 0, step, 2 step, ... (residual of them)
+    }
+    // inclusive prefix sum over the 256 bins
+    int v = hv;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int n = __shfl_up_sync(0xffffffffu, v, off); if ((tid & 31) >= off) v += n; }
+    __syncthreads();
+    if ((tid & 31) == 31) wsum[tid >> 5] = v;
+    __syncthreads();
+    int pre = 0;
+    for (int k = 0; k < (tid >> 5); ++k) pre += wsum[k];
+    const float f = __fmul_rn((float)(v + pre), lut_scale);
+    lut[(size_t)t * 256 + tid] = (uint8_t)min(max(__float2int_rn(f), 0), 255);
+}
+
+__global__ void clahe_apply_kernel(const uint8_t *src, int w, int h, int tw, int th, int tiles_x, int tiles_y,
+                                   const uint8_t *lut, uint8_t *dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float inv_tw = __fdiv_rn(1.0f, (float)tw), inv_th = __fdiv_rn(1.0f, (float)th);
+    const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f), tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+    int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+    const float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
+    const float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
+    const int tx2 = min(tx1 + 1, tiles_x - 1), ty2 = min(ty1 + 1, tiles_y - 1);
+    tx1 = max(tx1, 0); ty1 = max(ty1, 0);
+    const int v = src[(size_t)y * w + x];
+    const float l11 = (float)lut[((size_t)ty1 * tiles_x + tx1) * 256 + v], l12 = (float)lut[((size_t)ty1 * tiles_x + tx2) * 256 + v];
+    const float l21 = (float)lut[((size_t)ty2 * tiles_x + tx1) * 256 + v], l22 = (float)lut[((size_t)ty2 * tiles_x + tx2) * 256 + v];
+    const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+    const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+    const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+    dst[(size_t)y * w + x] = (uint8_t)min(max(__float2int_rn(res), 0), 255);
+}
+
+// device-resident CLAHE of a w x h image (row stride w)
+static int clahe_device(Handle *h, const uint8_t *src, uint8_t *dst, uint8_t *lut, int w, int hgt, double clip_limit,
+                        int tiles_x, int tiles_y) {
+    const int tw = w / tiles_x, th = hgt / tiles_y, area = tw * th;
+    const int clip = std::max((int)(clip_limit * area / 256), 1);
+    const float lut_scale = 255.0f / (float)area;
+    clahe_lut_kernel<<<tiles_x * tiles_y, 256, 0, h->stream>>>(src, w, tw, th, tiles_x, clip, lut_scale, lut);
+    dim3 b(32, 8), g((w + 31) / 32, (hgt + 7) / 8);
+    clahe_apply_kernel<<<g, b, 0, h->stream>>>(src, w, hgt, tw, th, tiles_x, tiles_y, lut, dst);
+    h->launches += 2;
+    return 0;
 }
 
 __global__ void pyrdown_kernel(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh) {
@@ -222,6 +305,8 @@ void klt_free(Handle *h) {
     if (k->d_next) cudaFree(k->d_next);
     if (k->d_err) cudaFree(k->d_err);
     if (k->d_status) cudaFree(k->d_status);
+    for (int i = 0; i < 2; ++i) if (k->raw[i]) cudaFree(k->raw[i]);
+    if (k->lut) cudaFree(k->lut);
     if (k->h_img) cudaFreeHost(k->h_img);
     if (k->h_pts) cudaFreeHost(k->h_pts);
     if (k->h_status) cudaFreeHost(k->h_status);
@@ -257,9 +342,13 @@ static int klt_prepare(Handle *h, int w, int hgt, int max_level, int n_points) {
 
 int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int width, int height, int stride,
                    const float *prev_pts, float *next_pts, uint8_t *status, float *err, int n_points,
-                   int max_level, int max_iter, double eps) {
+                   int max_level, int max_iter, double eps, double clahe_clip, int tiles_x, int tiles_y,
+                   uint8_t *prev_eq, uint8_t *next_eq) {
     if (width < 2 || height < 2 || stride < width || n_points < 0 || max_level < 0 || max_level >= kMaxLevels)
         return fail(h, PVIO_B200_EINVAL, "klt: bad arguments");
+    const bool do_clahe = clahe_clip > 0.0;
+    if (do_clahe && (tiles_x < 1 || tiles_y < 1 || width % tiles_x || height % tiles_y))
+        return fail(h, PVIO_B200_EINVAL, "clahe: the image size must be a multiple of the tile grid");
     if (n_points == 0) return 0;
     // buildOpticalFlowPyramid stops adding levels once a level is not larger than the window
     int levels = 1, lw = width, lh = height;
@@ -279,8 +368,22 @@ int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int widt
     }
     memcpy(k->h_pts, prev_pts, sizeof(float) * 2 * n_points);
     memcpy(k->h_pts + 2 * k->cap_pts, next_pts, sizeof(float) * 2 * n_points);
-    CK(h, cudaMemcpyAsync(k->pyr[0], k->h_img, img_bytes, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaMemcpyAsync(k->pyr[1], k->h_img + img_bytes, img_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (do_clahe) {
+        // raw frames -> device, CLAHE on the device into level 0 of the pyramids (opencv_image.cpp:138-143)
+        if (!k->raw[0]) for (int i = 0; i < 2; ++i) CK(h, cudaMalloc(&k->raw[i], img_bytes));
+        if (k->lut_tiles < tiles_x * tiles_y) {
+            if (k->lut) cudaFree(k->lut);
+            CK(h, cudaMalloc(&k->lut, (size_t)tiles_x * tiles_y * 256));
+            k->lut_tiles = tiles_x * tiles_y;
+        }
+        for (int i = 0; i < 2; ++i) {
+            CK(h, cudaMemcpyAsync(k->raw[i], k->h_img + i * img_bytes, img_bytes, cudaMemcpyHostToDevice, h->stream));
+            clahe_device(h, k->raw[i], k->pyr[i], k->lut, width, height, clahe_clip, tiles_x, tiles_y);
+        }
+    } else {
+        CK(h, cudaMemcpyAsync(k->pyr[0], k->h_img, img_bytes, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(k->pyr[1], k->h_img + img_bytes, img_bytes, cudaMemcpyHostToDevice, h->stream));
+    }
     CK(h, cudaMemcpyAsync(k->d_prev, k->h_pts, sizeof(float) * 2 * n_points, cudaMemcpyHostToDevice, h->stream));
     CK(h, cudaMemcpyAsync(k->d_next, k->h_pts + 2 * k->cap_pts, sizeof(float) * 2 * n_points, cudaMemcpyHostToDevice, h->stream));
     KltLevels L;
@@ -305,11 +408,33 @@ int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int widt
     CK(h, cudaMemcpyAsync(k->h_pts + 2 * k->cap_pts, k->d_next, sizeof(float) * 2 * n_points, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaMemcpyAsync(k->h_pts + 4 * k->cap_pts, k->d_err, sizeof(float) * n_points, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaMemcpyAsync(k->h_status, k->d_status, n_points, cudaMemcpyDeviceToHost, h->stream));
+    if (do_clahe && (prev_eq || next_eq)) {
+        CK(h, cudaMemcpyAsync(k->h_img, k->pyr[0], img_bytes, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(k->h_img + img_bytes, k->pyr[1], img_bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaGetLastError());
     memcpy(next_pts, k->h_pts + 2 * k->cap_pts, sizeof(float) * 2 * n_points);
     if (err) memcpy(err, k->h_pts + 4 * k->cap_pts, sizeof(float) * n_points);
     memcpy(status, k->h_status, n_points);
+    if (do_clahe && prev_eq) memcpy(prev_eq, k->h_img, img_bytes);
+    if (do_clahe && next_eq) memcpy(next_eq, k->h_img + img_bytes, img_bytes);
+    return 0;
+}
+
+// stand-alone CLAHE of one host image (dst row stride = width)
+int clahe_impl(Handle *h, const uint8_t *src, int width, int height, int stride, double clip, int tiles_x, int tiles_y, uint8_t *dst) {
+    if (width < 1 || height < 1 || stride < width || clip <= 0.0 || tiles_x < 1 || tiles_y < 1 || width % tiles_x || height % tiles_y)
+        return fail(h, PVIO_B200_EINVAL, "clahe: bad arguments (the image size must be a multiple of the tile grid)");
+    const size_t bytes = (size_t)width * height;
+    uint8_t *d = nullptr;
+    CK(h, cudaMalloc(&d, 2 * bytes + (size_t)tiles_x * tiles_y * 256));
+    cudaError_t e = cudaMemcpy2DAsync(d, width, src, stride, width, height, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) { clahe_device(h, d, d + bytes, d + 2 * bytes, width, height, clip, tiles_x, tiles_y); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, d + bytes, bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { h->err = std::string("clahe: ") + cudaGetErrorString(e); return PVIO_B200_ECUDA; }
     return 0;
 }
 

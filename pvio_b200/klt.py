@@ -9,9 +9,21 @@ import numpy as np
 from . import _lib
 
 
+def clahe(ba, img, clip_limit=6.0, tiles=(8, 8)):
+    """cv::createCLAHE(clip_limit, tiles)->apply on the device (opencv_image.cpp:138-143); bit-exact with OpenCV."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    out = np.zeros_like(img)
+    fn = ba.lib.pvio_b200_clahe
+    fn.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    ba._ck(fn(ba.h, _lib._ptr(img, C.c_uint8), w, h, w, float(clip_limit), tiles[0], tiles[1], _lib._ptr(out, C.c_uint8)))
+    return out
+
+
 def track_keypoints(ba, prev_img, next_img, curr_keypoints, next_keypoints=None, max_level=3, max_iter=30,
-                    eps=0.01, border=20, raw=False):
+                    eps=0.01, border=20, raw=False, clahe_clip=0.0, clahe_tiles=(8, 8)):
     """ba: a BundleAdjustor (owns the device handle).  Images: uint8 [h, w].  Keypoints in pixels.
+    clahe_clip > 0: the images are the RAW frames and CLAHE runs on the device first (OpenCvImage::preprocess).
     Returns (next_keypoints float32 [n,2], status uint8 [n], err float32 [n])."""
     prev_img = np.ascontiguousarray(prev_img, dtype=np.uint8)
     next_img = np.ascontiguousarray(next_img, dtype=np.uint8)
@@ -22,9 +34,18 @@ def track_keypoints(ba, prev_img, next_img, curr_keypoints, next_keypoints=None,
     n = len(cur)
     status = np.zeros(max(n, 1), dtype=np.uint8)
     err = np.zeros(max(n, 1), dtype=np.float32)
-    rc = ba.lib.pvio_b200_klt_track(ba.h, _lib._ptr(prev_img, C.c_uint8), _lib._ptr(next_img, C.c_uint8), w, h, w,
-                                    _lib._ptr(cur, C.c_float), _lib._ptr(nxt, C.c_float), _lib._ptr(status, C.c_uint8),
-                                    _lib._ptr(err, C.c_float), n, max_level, max_iter, eps)
+    if clahe_clip > 0:
+        fn = ba.lib.pvio_b200_klt_track_raw
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                       C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_double,
+                       C.c_double, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
+        rc = fn(ba.h, _lib._ptr(prev_img, C.c_uint8), _lib._ptr(next_img, C.c_uint8), w, h, w,
+                _lib._ptr(cur, C.c_float), _lib._ptr(nxt, C.c_float), _lib._ptr(status, C.c_uint8),
+                _lib._ptr(err, C.c_float), n, max_level, max_iter, eps, float(clahe_clip), clahe_tiles[0], clahe_tiles[1], None, None)
+    else:
+        rc = ba.lib.pvio_b200_klt_track(ba.h, _lib._ptr(prev_img, C.c_uint8), _lib._ptr(next_img, C.c_uint8), w, h, w,
+                                        _lib._ptr(cur, C.c_float), _lib._ptr(nxt, C.c_float), _lib._ptr(status, C.c_uint8),
+                                        _lib._ptr(err, C.c_float), n, max_level, max_iter, eps)
     ba._ck(rc)
     status, err = status[:n], err[:n]
     if not raw:

@@ -56,3 +56,29 @@ def test_klt_border_rule_and_empty(ba):
     assert st[-1] == 0                      # inside 20 px of the border: opencv_image.cpp:106
     nxt0, st0, _ = klt.track_keypoints(ba, prev, nxt_img, np.zeros((0, 2), dtype=np.float32))
     assert len(nxt0) == 0 and len(st0) == 0
+
+
+def test_clahe_bit_exact_with_oracle_and_cv2(ba):
+    """Device CLAHE (opencv_image.cpp:138-143) against the cv2-pinned oracle and cv2 itself: every pixel equal."""
+    from oracle import clahe_oracle
+    rng = np.random.default_rng(5)
+    for shape in [(480, 752), (512, 512), (64, 96)]:
+        img = np.clip(np.linspace(20, 230, shape[1])[None, :] + rng.normal(0, 25, shape), 0, 255).astype(np.uint8)
+        out = klt.clahe(ba, img)
+        assert np.array_equal(out, clahe_oracle.clahe(img))
+        try:
+            import cv2
+            assert np.array_equal(out, cv2.createCLAHE(6.0, (8, 8)).apply(img))
+        except ImportError:
+            pass
+    flat = np.full((64, 64), 200, dtype=np.uint8)
+    assert np.array_equal(klt.clahe(ba, flat), clahe_oracle.clahe(flat))
+
+
+def test_track_from_raw_frames_equals_track_of_equalised_frames(ba):
+    """pvio_b200_klt_track_raw = CLAHE on the device + the same tracker: identical to tracking host-equalised frames."""
+    from oracle import clahe_oracle
+    prev, nxt, pts, _ = synth.make_klt_pair(size=(752, 480), n_points=300)
+    a = klt.track_keypoints(ba, prev, nxt, pts, clahe_clip=6.0)
+    b = klt.track_keypoints(ba, clahe_oracle.clahe(prev), clahe_oracle.clahe(nxt), pts)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
