@@ -221,11 +221,11 @@ def run_gpu(args):
             traffic = json.load(open(tp))["dram_bytes_per_window"] * W
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "lin_tpl_kernel (linearise + Schur)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "lin_a_kernel + schur_kernel (linearise + Schur stage, timed together)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_alg_per_window": balg, "windows_per_launch": W, "kernel_ms": lin_ms,
                 "kernel_share_of_step": lin_ms / (ms / args.steps),
-                "note": "algorithmic bytes / CUDA-event kernel time; DRAM traffic = 56 KB read (8-byte observation records: below the 92 KB algorithmic figure) + 63 KB written, of which ~60 KB are the sqrt(w) h records handed to the update kernel (a deliberate trade: HBM is at 6 % while the SMs are issue-bound); "
+                "note": "algorithmic bytes / CUDA-event time of the stage (two launches: linearisation 0.49 ms, Schur sum 0.34 ms; SURVEY's byte figure covers both); DRAM traffic = 56 KB read (8-byte observation records: below the 92 KB algorithmic figure) + 63 KB written, of which ~60 KB are the sqrt(w) h records handed to the update kernel (a deliberate trade: HBM is at 6 % while the SMs are issue-bound); "
                         "arithmetic intensity ~33 flop/B is above the fp32 ridge (11.5 flop/B), so on CUDA cores the kernel is "
                         "FP32-issue bound, see DESIGN.md 4.1"}
 

@@ -11,6 +11,7 @@
 #include "ba_lin.cuh"
 #include "ba_lin2.cuh"
 #include "ba_lin3.cuh"
+#include "ba_schur.cuh"
 #include "ba_solve.cuh"
 #include "ba_update.cuh"
 
@@ -249,6 +250,7 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
     H.n_chunks = nch;
     h->slot_M[slot] = M; h->slot_N[slot] = N; h->slot_K[slot] = K;
     h->max_slot_N = std::max(h->max_slot_N, N);
+    h->max_slot_free = std::max(h->max_slot_free, N - __builtin_popcount((unsigned)H.fixed_mask & ((1u << N) - 1u)));
     h->perm_identity[slot] = sorted ? 1 : 0;
     // inertial part
     H.n_imu = w->use_inertial ? w->n_imu : 0;
@@ -410,6 +412,22 @@ static int run_linearize(Handle *h, int n, const StepCfg &c) {
     else if (tc_ok && h->tc_gs == 4) lin_tc_kernel<true, 4><<<dim3(gx, n), kLinThreads, lin3_smem_bytes(std::min(h->Ncap, kTcMaxFrames)), st>>>(a);
     else if (tc_ok && h->tc_gs == 2) lin_tc_kernel<true, 2><<<dim3(gx, n), kLinThreads, lin3_smem_bytes(std::min(h->Ncap, kTcMaxFrames)), st>>>(a);
     else if (tc_ok) lin_tc_kernel<true, 1><<<dim3(gx, n), kLinThreads, lin3_smem_bytes(std::min(h->Ncap, kTcMaxFrames)), st>>>(a);
+    else if (h->split_schur && gx == 1) {
+        // split stage (default for whole-window CTAs): Phase A (records + direct blocks, ba_lin4.cuh), then the Schur
+        // sum as its own kernel at ~3x the occupancy (ba_schur.cuh): 0.83 ms instead of 0.90 ms per 4096 cfg2 windows
+        switch (h->split_shape) {
+            case 1: lin_a_kernel<true, 6, 3><<<dim3(1, n), 192, lin4_smem_bytes<6>(h->Ncap), st>>>(a); break;
+            case 2: lin_a_kernel<true, 4, 4><<<dim3(1, n), 128, lin4_smem_bytes<4>(h->Ncap), st>>>(a); break;
+            case 3: lin_a_kernel<true, 4, 5><<<dim3(1, n), 128, lin4_smem_bytes<4>(h->Ncap), st>>>(a); break;
+            default: lin_a_kernel<true, 8, 2><<<dim3(1, n), 256, lin4_smem_bytes<8>(h->Ncap), st>>>(a); break;
+        }
+        // CTA = the tiles of the free-frame pairs x 4 k-split lanes (x 2 / x 1 when that exceeds 256 threads)
+        const int nfree = std::max(1, h->max_slot_free), ntask = nfree * (nfree + 1) / 2;
+        const int ks = ntask * 4 <= kSchurThreads ? 4 : (ntask * 2 <= kSchurThreads ? 2 : 1);
+        const int nthr = std::min(kSchurThreads, ((ntask * ks + 31) / 32) * 32);
+        schur_kernel<<<n, nthr, schur_smem_bytes(h->Ncap), st>>>(a);
+        ++h->launches;
+    }
     else lin_tpl_kernel<true><<<dim3(gx, n), kLinThreads, lin2_smem_bytes(h->Ncap), st>>>(a);
     if (!h->capturing) { CK(h, cudaEventRecord(h->kev[slot + 1], st)); ++h->kev_count; }
     ++h->launches;
@@ -620,7 +638,7 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     TRY(alloc(h, h->ctrl, W, true));
     TRY(alloc(h, h->rho_cand, W * M, false)); TRY(alloc(h, h->frames_cand, W * N * kFrameStride, false));
     TRY(alloc(h, h->lm_scale, W * M, false)); TRY(alloc(h, h->lm_aux, W * M, false));
-    h->hs_stride = (size_t)(M / 32 + N + 1) * 32 * N * 6;
+    h->hs_stride = (size_t)(M / 32 + N + 1) * 32 * hs_rec(N);
     TRY(alloc(h, h->hs, W * h->hs_stride, false));
     TRY(alloc(h, h->dx_lm, W * M, true)); TRY(alloc(h, h->dx_pose, W * N * 15, true));
     TRY(alloc(h, h->pose_scale, W * N * 15, false)); TRY(alloc(h, h->v_pose, W * N * 15, false));
@@ -643,6 +661,13 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     CK(h, cudaFuncSetAttribute(lin_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin3_smem_bytes(kTcMaxFrames)));
     { const char *e = getenv("PVIO_B200_TC_GS"); h->tc_gs = e ? atoi(e) : 2; }
     { const char *e = getenv("PVIO_B200_TC"); h->use_tc = e && e[0] == '1'; }
+    CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<8>(kMaxFrames)));
+    CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<6>(kMaxFrames)));
+    CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<4>(kMaxFrames)));
+    CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<4>(kMaxFrames)));
+    { const char *e = getenv("PVIO_B200_SPLIT_SHAPE"); h->split_shape = e ? atoi(e) : 2; }    // 4 warps x 4 CTAs per SM measured best
+    CK(h, cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem_bytes(kMaxFrames)));
+    { const char *e = getenv("PVIO_B200_SPLIT"); h->split_schur = !(e && e[0] == '0'); }     // default on; 0: the fused kernel
     CK(h, cudaFuncSetAttribute(lin_tpl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin2_smem_bytes(kMaxFrames)));
     CK(h, cudaFuncSetAttribute(lin_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem_bytes()));
     CK(h, cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

@@ -58,8 +58,11 @@ struct Handle {
     std::vector<int> slot_M, slot_N, slot_K;
     std::vector<uint8_t> perm_identity;
     int n_uploaded = 0;
+    int max_slot_free = 0;        // most free (non FF_FIX_POSE) frames of any window packed so far
     int max_slot_N = 0;           // largest window packed so far (selects the tensor-core linearise kernel)
     int tc_gs = 1;                // k-steps per TMEM partial sum (PVIO_B200_TC_GS, experiments)
+    int split_shape = 2;          // CTA shape of lin_a_kernel (experiments)
+    bool split_schur = true;      // PVIO_B200_SPLIT=1: linearise stage as two kernels (Phase A, then schur_kernel)
     bool use_tc = false;          // PVIO_B200_TC=1: tcgen05 Schur SYRK (lin_tc_kernel) instead of the CUDA-core one
     float last_lin_ms = 0.f;
     // ring of event pairs around every linearise+Schur launch (roofline timing without host syncs)

@@ -168,6 +168,8 @@ __device__ __forceinline__ double lm_reg(double hii, double scale, double mu) {
     return mu * d2 / s2;
 }
 
+__host__ __device__ __forceinline__ int hs_rec(int N) { return 6 * N + 2; }
+
 struct LinArgs {
     const WinHdr *hdr;
     const WinConst *cst;
@@ -183,6 +185,8 @@ struct LinArgs {
                              // kernels' shared-memory h buffer, so a warp's records leave as one bulk copy.
                              // nullptr: not wanted (marginaliser)
     size_t hs_stride;        // floats per window
+    // one record = hs_rec(N) floats: [0, 6N) sqrt(w) h per frame, [6N] sqrt(w) g_l, [6N + 1] the bit pattern of the
+    // frame mask (observing frames | anchor; 0 for an empty slot or a non-finite pivot)
     double *Hred;            // [W][npairs_cap][36] block-lower-triangular reduced system (xi coords)
     double *Hdd;             // [W][Ncap][36] direct (pre-Schur) diagonal blocks (xi coords)
     double *gdir;            // [W][Ncap][6] direct gradient (xi coords)
@@ -332,9 +336,10 @@ lin_schur_kernel(LinArgs a) {
                 if (lane == 0) { aux[l].hll_reg = hreg; aux[l].gl = gl_d; aux[l].hll = hll_d; }
                 float *hb = hbuf + (s * kMaxFrames + lane) * 8;
                 if (a.hs_out && (observed || lane == anchor)) {
-                    float *hs = a.hs_out + (size_t)w * a.hs_stride + ((size_t)(ch * 32 + s) * N + lane) * 6;
+                    float *hs = a.hs_out + (size_t)w * a.hs_stride + (size_t)(ch * 32 + s) * hs_rec(N);
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) hs[i] = (observed ? h[i] : -ha[i]) * sw;
+                    for (int i = 0; i < 6; ++i) hs[lane * 6 + i] = (observed ? h[i] : -ha[i]) * sw;
+                    if (lane == anchor) { hs[6 * N] = sw * (float)gl_d; hs[6 * N + 1] = __int_as_float(finite ? (tmask | (1 << anchor)) : 0); }
                 }
                 if (observed) {
 #pragma unroll

@@ -72,9 +72,7 @@ __host__ __device__ inline size_t lin2_smem_bytes(int N) {
            + sizeof(double) * (npairs * 36)              // Schur sum (block lower triangular)
            + sizeof(double) * (nsp + 1) * 33             // direct (target, anchor) blocks + gradients
            + sizeof(double) * (size_t)N * 6              // Schur gradient correction
-           + sizeof(float) * ((size_t)kSuper * N * 6)    // scaled h vectors
-           + sizeof(float) * kSuper                      // sqrt(w) g_l
-           + sizeof(int) * kSuper                        // touched-frame masks
+           + sizeof(float) * ((size_t)kSuper * (N * 6 + 2))   // records: scaled h vectors, sqrt(w) g_l, frame mask
            + sizeof(double) * 8 + 16;                    // + alignment slack of the h buffer
 }
 
@@ -146,9 +144,8 @@ lin_tpl_kernel(LinArgs a) {
     double *gsc = Dta + (nsp + 1) * 33;                             // [N][6] sum_l w g_l h_f
     // [kSuper][N][6], 16-byte aligned (offset arithmetic keeps the shared address space): bulk-copy source
     float *hbuf = reinterpret_cast<float *>(smem_raw + ((sizeof(FrameSm) * kMaxFrames + sizeof(double) * (npairs * 36 + (nsp + 1) * 33 + N * 6) + 15) & ~(size_t)15));
-    float *sgb = hbuf + kSuper * N * 6;                             // [kSuper] sqrt(w) g_l
-    int *msk = reinterpret_cast<int *>(sgb + kSuper);               // [kSuper]
-    double *cost_sm = reinterpret_cast<double *>(msk + kSuper);     // [8]
+    const int R = hs_rec(N);                                        // record stride (LinArgs::hs_out layout)
+    double *cost_sm = reinterpret_cast<double *>(hbuf + kSuper * R);   // [8]  (kSuper * R floats is a multiple of 8 bytes)
 
     if (tid < N) make_frame(a.frames + ((size_t)w * a.Ncap + tid) * kFrameStride, wc, F[tid]);
     for (int i = tid; i < npairs * 36 + (nsp + 1) * 33 + N * 6; i += kLinThreads) Ss[i] = 0.0;   // Ss, Dta, gsc contiguous
@@ -209,7 +206,7 @@ lin_tpl_kernel(LinArgs a) {
             double hll = 0.0, gl = 0.0;
             float ha[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             int tmask = 0;
-            float *hb = hbuf + (size_t)slot * N * 6;
+            float *hb = hbuf + (size_t)slot * R;
             // the previous pass's bulk copy of this warp's records must have read the buffer before it is rewritten
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
@@ -279,11 +276,11 @@ lin_tpl_kernel(LinArgs a) {
                 }
 #pragma unroll
                 for (int i = 0; i < 6; ++i) hb[anchor * 6 + i] = ha[i] * sw;
-                sgb[slot] = sw * (float)gl;
-                msk[slot] = finite ? (tmask | (1 << anchor)) : 0;
+                hb[6 * N] = sw * (float)gl;
+                hb[6 * N + 1] = __int_as_float(finite ? (tmask | (1 << anchor)) : 0);
             } else {
-                msk[slot] = 0;
-                sgb[slot] = 0.f;
+                hb[6 * N] = 0.f;
+                hb[6 * N + 1] = __int_as_float(0);
                 if (lm_ok && !a.victim_only) { aux[l].hll_reg = 1.0; aux[l].gl = 0.0; aux[l].hll = 0.0; }
             }
             // the warp's 32 records of 6 N floats go to the update kernel as ONE bulk copy (TMA engine, no LSU
@@ -292,10 +289,10 @@ lin_tpl_kernel(LinArgs a) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
-                    float *dst = a.hs_out + (size_t)w * a.hs_stride + (size_t)ch * 32 * N * 6;
-                    const float *src = hbuf + (size_t)wv * 32 * N * 6;
+                    float *dst = a.hs_out + (size_t)w * a.hs_stride + (size_t)ch * 32 * R;
+                    const float *src = hbuf + (size_t)wv * 32 * R;
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src)), "r"(32 * N * 6 * 4) : "memory");
+                                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src)), "r"(32 * R * 4) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -314,10 +311,10 @@ lin_tpl_kernel(LinArgs a) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) accg[i] = 0.f;
             for (int s = kk; s < kSuper; s += ksplit) {
-                const int m = msk[s];
+                const int m = __float_as_int(hbuf[(size_t)s * R + 6 * N + 1]);
                 if (((m >> bf) & (m >> bg) & 1) == 0) continue;
-                const float *hf = hbuf + (size_t)s * N * 6 + bf * 6;
-                const float *hg = hbuf + (size_t)s * N * 6 + bg * 6;
+                const float *hf = hbuf + (size_t)s * R + bf * 6;
+                const float *hg = hbuf + (size_t)s * R + bg * 6;
                 const float2 f01 = *reinterpret_cast<const float2 *>(hf);
                 const float2 f23 = *reinterpret_cast<const float2 *>(hf + 2);
                 const float2 f45 = *reinterpret_cast<const float2 *>(hf + 4);
@@ -331,7 +328,7 @@ lin_tpl_kernel(LinArgs a) {
 #pragma unroll
                     for (int j = 0; j < 6; ++j) acc[i * 6 + j] += hfv[i] * hgv[j];
                 if (b_diag) {
-                    const float sg = sgb[s];
+                    const float sg = hbuf[(size_t)s * R + 6 * N];
 #pragma unroll
                     for (int j = 0; j < 6; ++j) accg[j] += hgv[j] * sg;
                 }

@@ -253,7 +253,8 @@ lin_tc_kernel(LinArgs a) {
         } else if (lm_ok && !a.victim_only && !h2) {
             aux[l].hll_reg = 1.0; aux[l].gl = 0.0; aux[l].hll = 0.0;
         }
-        float *hs = (a.hs_out && n_obs > 0) ? a.hs_out + (size_t)w * a.hs_stride + (size_t)(ch * 32 + li) * N * 6 : nullptr;
+        float *hs = (a.hs_out && lm_ok) ? a.hs_out + (size_t)w * a.hs_stride + (size_t)(ch * 32 + li) * hs_rec(N) : nullptr;
+        if (hs && !h2) { hs[6 * N] = sw * (float)gl; hs[6 * N + 1] = __int_as_float(sw != 0.f ? (int)(seen | (1u << anchor)) : 0); }
         __syncwarp();                                               // the partner's unscaled h values
         // ---- column `slot` of A: every row below 6 N + 1 is (re)written, zeros where the landmark is not seen
         for (int f = h2; f < N; f += 2) {

@@ -121,7 +121,7 @@ update_tpl_kernel(UpdArgs a) {
             const LmAux ax = aux[l];
             hll = ax.hll;
             // h_l . dxi = sqrt(H_ll + reg) * sum_f (sqrt(w) h_lf) . dxi_f over the observing frames and the anchor
-            const float2 *hs = reinterpret_cast<const float2 *>(a.hs + (size_t)w * a.hs_stride + (size_t)(ch * 32 + lane) * N * 6);
+            const float2 *hs = reinterpret_cast<const float2 *>(a.hs + (size_t)w * a.hs_stride + (size_t)(ch * 32 + lane) * hs_rec(N));
             for (unsigned fm = lm_mask(lr.meta) | (1u << anchor); fm; fm &= fm - 1) {
                 const int f = __ffs(fm) - 1;
                 const float2 h01 = hs[f * 3], h23 = hs[f * 3 + 1], h45 = hs[f * 3 + 2];

@@ -131,13 +131,15 @@ def test_gn_step_cfg4_planes(ba):
     _check_step(ba, w, st)
 
 
-@pytest.mark.parametrize("use_tc", ["0", "1"])
+@pytest.mark.parametrize("mode", ["fused", "tc", "split"])
 @pytest.mark.parametrize("case", ["cfg2", "cfg2b", "ragged", "cfg3", "cfg4", "cfg2_free"])
-def test_throughput_kernels_match_oracle(case, use_tc, monkeypatch):
+def test_throughput_kernels_match_oracle(case, mode, monkeypatch):
     """Batches of >= 74 windows run the thread-per-landmark linearise kernels: lin_tpl_kernel (CUDA-core
     Schur SYRK, the default) and, with PVIO_B200_TC=1 and windows of <= 10 frames, lin_tc_kernel (tcgen05
     3xTF32 Schur SYRK).  Both against the oracle step on the same windows."""
-    monkeypatch.setenv("PVIO_B200_TC", use_tc)
+    # "split": Phase A (lin_tpl_kernel<.., false>) + schur_kernel streaming the records through a bulk-copy ring
+    monkeypatch.setenv("PVIO_B200_TC", "1" if mode == "tc" else "0")
+    monkeypatch.setenv("PVIO_B200_SPLIT", "1" if mode == "split" else "0")
     if case == "cfg2":
         w, st, _ = synth.make_cfg2()
     elif case == "cfg2b":
@@ -166,7 +168,7 @@ def test_throughput_kernels_match_oracle(case, use_tc, monkeypatch):
     tol = TOL_DX
     for i in (0, W - 1):
         e = _rel(dx[i], ref['dx'])
-        print(case, "use_tc", use_tc, "window", i, "dx rel err", e)
+        print(case, "mode", mode, "window", i, "dx rel err", e)
         assert e < tol
         assert abs(costs[i, 0] - ref['cost']) <= 2e-6 * ref['cost']
     assert np.array_equal(dx[0], dx[W - 1])
