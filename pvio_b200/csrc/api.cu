@@ -425,7 +425,8 @@ static int run_linearize(Handle *h, int n, const StepCfg &c) {
         const int nfree = std::max(1, h->max_slot_free), ntask = nfree * (nfree + 1) / 2;
         const int ks = ntask * 4 <= kSchurThreads ? 4 : (ntask * 2 <= kSchurThreads ? 2 : 1);
         const int nthr = std::min(kSchurThreads, ((ntask * ks + 31) / 32) * 32);
-        schur_kernel<<<n, nthr, schur_smem_bytes(h->Ncap), st>>>(a);
+        if (nthr <= 160) schur_kernel<160, 4><<<n, nthr, schur_smem_bytes(h->Ncap), st>>>(a);
+        else schur_kernel<256, 2><<<n, nthr, schur_smem_bytes(h->Ncap), st>>>(a);
         ++h->launches;
     }
     else lin_tpl_kernel<true><<<dim3(gx, n), kLinThreads, lin2_smem_bytes(h->Ncap), st>>>(a);
@@ -666,7 +667,8 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<4>(kMaxFrames)));
     CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<4>(kMaxFrames)));
     { const char *e = getenv("PVIO_B200_SPLIT_SHAPE"); h->split_shape = e ? atoi(e) : 2; }    // 4 warps x 4 CTAs per SM measured best
-    CK(h, cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem_bytes(kMaxFrames)));
+    CK(h, cudaFuncSetAttribute(schur_kernel<160, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem_bytes(kMaxFrames)));
+    CK(h, cudaFuncSetAttribute(schur_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem_bytes(kMaxFrames)));
     { const char *e = getenv("PVIO_B200_SPLIT"); h->split_schur = !(e && e[0] == '0'); }     // default on; 0: the fused kernel
     CK(h, cudaFuncSetAttribute(lin_tpl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin2_smem_bytes(kMaxFrames)));
     CK(h, cudaFuncSetAttribute(lin_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem_bytes()));

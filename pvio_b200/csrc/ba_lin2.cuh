@@ -302,59 +302,64 @@ lin_tpl_kernel(LinArgs a) {
         // ========================= Phase B: Schur sum over the super-chunk =========================
         // fp32 accumulation over the <= kSuper / ksplit landmarks of this thread (<= 64 terms: relative
         // error of the partial ~ 3e-7, averaged down over the partials), then ONE fp64 flush.
-        const unsigned bmask = __ballot_sync(0xffffffffu, b_active);
-        const unsigned dmask = __ballot_sync(0xffffffffu, b_active && b_diag);
-        if (b_active) {
+        {
             float acc[36], accg[6];
 #pragma unroll
             for (int i = 0; i < 36; ++i) acc[i] = 0.f;
 #pragma unroll
             for (int i = 0; i < 6; ++i) accg[i] = 0.f;
-            for (int s = kk; s < kSuper; s += ksplit) {
-                const int m = __float_as_int(hbuf[(size_t)s * R + 6 * N + 1]);
-                if (((m >> bf) & (m >> bg) & 1) == 0) continue;
-                const float *hf = hbuf + (size_t)s * R + bf * 6;
-                const float *hg = hbuf + (size_t)s * R + bg * 6;
-                const float2 f01 = *reinterpret_cast<const float2 *>(hf);
-                const float2 f23 = *reinterpret_cast<const float2 *>(hf + 2);
-                const float2 f45 = *reinterpret_cast<const float2 *>(hf + 4);
-                const float2 g01 = *reinterpret_cast<const float2 *>(hg);
-                const float2 g23 = *reinterpret_cast<const float2 *>(hg + 2);
-                const float2 g45 = *reinterpret_cast<const float2 *>(hg + 4);
-                const float hfv[6] = {f01.x, f01.y, f23.x, f23.y, f45.x, f45.y};
-                const float hgv[6] = {g01.x, g01.y, g23.x, g23.y, g45.x, g45.y};
+            if (b_active) {
+                for (int s = kk; s < kSuper; s += ksplit) {
+                    const int m = __float_as_int(hbuf[(size_t)s * R + 6 * N + 1]);
+                    if (((m >> bf) & (m >> bg) & 1) == 0) continue;
+                    const float *hf = hbuf + (size_t)s * R + bf * 6;
+                    const float *hg = hbuf + (size_t)s * R + bg * 6;
+                    const float2 f01 = *reinterpret_cast<const float2 *>(hf);
+                    const float2 f23 = *reinterpret_cast<const float2 *>(hf + 2);
+                    const float2 f45 = *reinterpret_cast<const float2 *>(hf + 4);
+                    const float2 g01 = *reinterpret_cast<const float2 *>(hg);
+                    const float2 g23 = *reinterpret_cast<const float2 *>(hg + 2);
+                    const float2 g45 = *reinterpret_cast<const float2 *>(hg + 4);
+                    const float hfv[6] = {f01.x, f01.y, f23.x, f23.y, f45.x, f45.y};
+                    const float hgv[6] = {g01.x, g01.y, g23.x, g23.y, g45.x, g45.y};
 #pragma unroll
-                for (int i = 0; i < 6; ++i)
+                    for (int i = 0; i < 6; ++i)
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) acc[i * 6 + j] += hfv[i] * hgv[j];
-                if (b_diag) {
-                    const float sg = hbuf[(size_t)s * R + 6 * N];
+                        for (int j = 0; j < 6; ++j) acc[i * 6 + j] += hfv[i] * hgv[j];
+                    if (b_diag) {
+                        const float sg = hbuf[(size_t)s * R + 6 * N];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) accg[j] += hgv[j] * sg;
+                        for (int j = 0; j < 6; ++j) accg[j] += hgv[j] * sg;
+                    }
                 }
             }
-            // flush: sum over the k-split lanes (butterfly), lane kk adds rows kk, kk + ksplit, ... in fp64
+            // flush: sum over the k-split lanes (butterfly; ALL lanes run it, idle ones carry zeros, so the shuffles are
+            // plain full-mask SHFL), lane kk adds rows kk, kk + ksplit, ... in fp64
 #pragma unroll
             for (int i = 0; i < 36; ++i) {
                 float v = acc[i];
-                if (ksplit >= 2) v += __shfl_xor_sync(bmask, v, 1);
-                if (ksplit >= 4) v += __shfl_xor_sync(bmask, v, 2);
+                if (ksplit >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (ksplit >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
                 acc[i] = v;
             }
-            double *dst = Ss + pair_idx(bf, bg) * 36;
 #pragma unroll
-            for (int i = 0; i < 6; ++i)
-                if ((i % ksplit) == kk) {
+            for (int j = 0; j < 6; ++j) {
+                float v = accg[j];
+                if (ksplit >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (ksplit >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
+                accg[j] = v;
+            }
+            if (b_active) {
+                double *dst = Ss + pair_idx(bf, bg) * 36;
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) dst[i * 6 + j] += (double)acc[i * 6 + j];
-                }
-            if (b_diag) {
+                for (int i = 0; i < 6; ++i)
+                    if ((i % ksplit) == kk) {
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    float v = accg[j];
-                    if (ksplit >= 2) v += __shfl_xor_sync(dmask, v, 1);     // the lanes of a task share b_diag
-                    if (ksplit >= 4) v += __shfl_xor_sync(dmask, v, 2);
-                    if (kk == 0) gsc[bf * 6 + j] += (double)v;
+                        for (int j = 0; j < 6; ++j) dst[i * 6 + j] += (double)acc[i * 6 + j];
+                    }
+                if (b_diag && kk == 0) {
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) gsc[bf * 6 + j] += (double)accg[j];
                 }
             }
         }

@@ -22,7 +22,10 @@ __host__ __device__ inline size_t schur_smem_bytes(int N) {
     return sizeof(double) * (npairs * 36 + (size_t)N * 6) + 32 + 16 + sizeof(float) * 2 * kSlab * (6 * N + 2);
 }
 
-__global__ void __launch_bounds__(kSchurThreads, 3)
+// kMaxThreads / kMinBlocks: <160, 4> covers up to 36 tiles x 4 lanes (8 free frames, cfg2) at 4 CTAs per SM,
+// <256, 2> everything else
+template <int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 schur_kernel(LinArgs a) {
     const int w = blockIdx.x + a.w0;
     const WinHdr &H = a.hdr[w];
@@ -74,8 +77,6 @@ schur_kernel(LinArgs a) {
     __syncthreads();
     if (tid == 0) { if (n_slab > 0) issue(0); if (n_slab > 1) issue(1); }
 
-    const unsigned bmask = __ballot_sync(0xffffffffu, b_active);
-    const unsigned dmask = __ballot_sync(0xffffffffu, b_active && b_diag);
     float acc[36], accg[6];
 #pragma unroll
     for (int i = 0; i < 36; ++i) acc[i] = 0.f;
@@ -115,15 +116,25 @@ schur_kernel(LinArgs a) {
                     for (int j = 0; j < 6; ++j) accg[j] += hgv[j] * sg;
                 }
             }
-            // every 4 slabs (256 records: <= 64 fp32 terms per lane, like the fused kernel) and at the end: fp64 flush
-            if ((i & 3) == 3 || i == n_slab - 1) {
+        }
+        // every 4 slabs (256 records: <= 64 fp32 terms per lane, like the fused kernel) and at the end: fp64 flush.
+        // ALL lanes run the shuffles (idle lanes carry zeros) so that they compile to plain full-mask SHFL.
+        if ((i & 3) == 3 || i == n_slab - 1) {
 #pragma unroll
-                for (int e = 0; e < 36; ++e) {
-                    float v = acc[e];
-                    if (ksplit >= 2) v += __shfl_xor_sync(bmask, v, 1);
-                    if (ksplit >= 4) v += __shfl_xor_sync(bmask, v, 2);
-                    acc[e] = v;
-                }
+            for (int e = 0; e < 36; ++e) {
+                float v = acc[e];
+                if (ksplit >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (ksplit >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
+                acc[e] = v;
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                float v = accg[j];
+                if (ksplit >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (ksplit >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
+                accg[j] = v;
+            }
+            if (b_active) {
                 double *dst = Ss + pair_idx(bf, bg) * 36;
 #pragma unroll
                 for (int ii = 0; ii < 6; ++ii)
@@ -131,19 +142,15 @@ schur_kernel(LinArgs a) {
 #pragma unroll
                         for (int j = 0; j < 6; ++j) dst[ii * 6 + j] += (double)acc[ii * 6 + j];
                     }
-                if (b_diag) {
+                if (b_diag && kk == 0) {
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        float v = accg[j];
-                        if (ksplit >= 2) v += __shfl_xor_sync(dmask, v, 1);
-                        if (ksplit >= 4) v += __shfl_xor_sync(dmask, v, 2);
-                        if (kk == 0) gsc[bf * 6 + j] += (double)v;
-                        accg[j] = 0.f;
-                    }
+                    for (int j = 0; j < 6; ++j) gsc[bf * 6 + j] += (double)accg[j];
                 }
-#pragma unroll
-                for (int e = 0; e < 36; ++e) acc[e] = 0.f;
             }
+#pragma unroll
+            for (int e = 0; e < 36; ++e) acc[e] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) accg[j] = 0.f;
         }
         __syncthreads();                                            // slab i consumed by everybody
         if (tid == 0 && i + 2 < n_slab) issue(i + 2);
