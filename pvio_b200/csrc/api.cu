@@ -12,6 +12,7 @@
 #include "ba_lin2.cuh"
 #include "ba_lin3.cuh"
 #include "ba_schur.cuh"
+#include "ba_schur_tc.cuh"
 #include "ba_solve.cuh"
 #include "ba_update.cuh"
 
@@ -425,7 +426,8 @@ static int run_linearize(Handle *h, int n, const StepCfg &c) {
         const int nfree = std::max(1, h->max_slot_free), ntask = nfree * (nfree + 1) / 2;
         const int ks = ntask * 4 <= kSchurThreads ? 4 : (ntask * 2 <= kSchurThreads ? 2 : 1);
         const int nthr = std::min(kSchurThreads, ((ntask * ks + 31) / 32) * 32);
-        if (nthr <= 160) schur_kernel<160, 4><<<n, nthr, schur_smem_bytes(h->Ncap), st>>>(a);
+        if (h->tc_mode == 2 && h->max_slot_N <= kTcMaxFrames) schur_tc_kernel<<<n, 128, schur_tc_smem_bytes(std::min(h->Ncap, kTcMaxFrames)), st>>>(a);
+        else if (nthr <= 160) schur_kernel<160, 4><<<n, nthr, schur_smem_bytes(h->Ncap), st>>>(a);
         else schur_kernel<256, 2><<<n, nthr, schur_smem_bytes(h->Ncap), st>>>(a);
         ++h->launches;
     }
@@ -661,7 +663,8 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     CK(h, cudaFuncSetAttribute(lin_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin3_smem_bytes(kTcMaxFrames)));
     CK(h, cudaFuncSetAttribute(lin_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin3_smem_bytes(kTcMaxFrames)));
     { const char *e = getenv("PVIO_B200_TC_GS"); h->tc_gs = e ? atoi(e) : 2; }
-    { const char *e = getenv("PVIO_B200_TC"); h->use_tc = e && e[0] == '1'; }
+    { const char *e = getenv("PVIO_B200_TC"); h->use_tc = e && e[0] == '1'; h->tc_mode = e ? atoi(e) : 0; }
+    CK(h, cudaFuncSetAttribute(schur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_tc_smem_bytes(kTcMaxFrames)));
     CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<8>(kMaxFrames)));
     CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<6>(kMaxFrames)));
     CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<4>(kMaxFrames)));

@@ -131,15 +131,16 @@ def test_gn_step_cfg4_planes(ba):
     _check_step(ba, w, st)
 
 
-@pytest.mark.parametrize("mode", ["fused", "tc", "split"])
+@pytest.mark.parametrize("mode", ["fused", "tc", "split", "split_tc"])
 @pytest.mark.parametrize("case", ["cfg2", "cfg2b", "ragged", "cfg3", "cfg4", "cfg2_free"])
 def test_throughput_kernels_match_oracle(case, mode, monkeypatch):
     """Batches of >= 74 windows run the thread-per-landmark linearise kernels: lin_tpl_kernel (CUDA-core
     Schur SYRK, the default) and, with PVIO_B200_TC=1 and windows of <= 10 frames, lin_tc_kernel (tcgen05
     3xTF32 Schur SYRK).  Both against the oracle step on the same windows."""
     # "split": Phase A (lin_tpl_kernel<.., false>) + schur_kernel streaming the records through a bulk-copy ring
-    monkeypatch.setenv("PVIO_B200_TC", "1" if mode == "tc" else "0")
-    monkeypatch.setenv("PVIO_B200_SPLIT", "1" if mode == "split" else "0")
+    # "split_tc": the same split with the Schur sum on the tensor cores (schur_tc_kernel)
+    monkeypatch.setenv("PVIO_B200_TC", {"tc": "1", "split_tc": "2"}.get(mode, "0"))
+    monkeypatch.setenv("PVIO_B200_SPLIT", "1" if mode in ("split", "split_tc") else "0")
     if case == "cfg2":
         w, st, _ = synth.make_cfg2()
     elif case == "cfg2b":
