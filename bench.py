@@ -225,7 +225,7 @@ def run_gpu(args):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_alg_per_window": balg, "windows_per_launch": W, "kernel_ms": lin_ms,
                 "kernel_share_of_step": lin_ms / (ms / args.steps),
-                "note": "algorithmic bytes / CUDA-event time of the stage (two launches: linearisation 0.49 ms, Schur sum 0.34 ms; SURVEY's byte figure covers both); DRAM traffic = 56 KB read (8-byte observation records: below the 92 KB algorithmic figure) + 63 KB written, of which ~60 KB are the sqrt(w) h records handed to the update kernel (a deliberate trade: HBM is at 6 % while the SMs are issue-bound); "
+                "note": "algorithmic bytes / CUDA-event time of the stage (two launches: linearisation 0.49 ms, Schur sum 0.34 ms; SURVEY's byte figure covers both); DRAM traffic of the stage = 264 KB per window: 55 KB of inputs (8-byte observation records: below the 92 KB algorithmic figure), 65 KB of sqrt(w) h records written, 139 KB read back by the Schur kernel, 5 KB of outputs (a deliberate compute-for-bandwidth trade: the records also save the update kernel one linearisation per observation, and HBM is at 7 % while the SMs are latency-bound); "
                         "arithmetic intensity ~33 flop/B is above the fp32 ridge (11.5 flop/B), so on CUDA cores the kernel is "
                         "FP32-issue bound, see DESIGN.md 4.1"}
 
