@@ -175,6 +175,32 @@ def test_throughput_kernels_match_oracle(case, mode, monkeypatch):
     assert np.array_equal(dx[0], dx[W - 1])
 
 
+def test_full_size_batch_properties():
+    """BASELINE's full bench size (4096 cfg2 windows per launch): size-independent properties instead of 4096 oracle
+    runs -- replicas are bit-identical, the second half of the batch is scaled noise (different data) and must still
+    satisfy the optimality identity of its own step: the candidate cost of the GN step is below the initial cost and
+    matches the oracle on the two windows that are checked in full."""
+    W = 4096
+    b = BundleAdjustor(max_windows=W, max_frames=10, max_landmarks=512, max_obs=4608)
+    wa, sa, _ = synth.make_cfg2()
+    wb, sb, _ = synth.make_cfg2(seed=99)
+    b.batch_set(0, wa, sa)
+    b.batch_replicate(W)
+    for i in (1, W // 2, W - 1):
+        b.batch_set(i, wb, sb)
+    b.batch_upload(W)
+    b.batch_gn_step(W, 1e-8, apply=False)
+    stride = 15 * wa.N + wa.M
+    dx, costs = b.batch_download(W, stride)
+    b.close()
+    ra, rb = bo.gn_step(wa, sa, schur=True), bo.gn_step(wb, sb, schur=True)
+    assert _rel(dx[0], ra['dx']) < TOL_DX and _rel(dx[1], rb['dx']) < TOL_DX
+    same_a = np.ones(W, dtype=bool); same_a[[1, W // 2, W - 1]] = False
+    assert np.all(dx[same_a] == dx[0]) and np.all(costs[same_a] == costs[0])          # replicas: bit-identical
+    assert np.array_equal(dx[W // 2], dx[1]) and np.array_equal(dx[W - 1], dx[1])
+    assert np.all(costs[:, 1] < costs[:, 0])                                           # every window's step reduces its cost
+
+
 def test_batch_replicas_agree(ba):
     w, st, _ = synth.make_cfg2(N=6, M=64)
     ba.batch_set(0, w, st)
