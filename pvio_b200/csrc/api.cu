@@ -669,7 +669,7 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<6>(kMaxFrames)));
     CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<4>(kMaxFrames)));
     CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<4>(kMaxFrames)));
-    { const char *e = getenv("PVIO_B200_SPLIT_SHAPE"); h->split_shape = e ? atoi(e) : 2; }    // 4 warps x 4 CTAs per SM measured best
+    { const char *e = getenv("PVIO_B200_SPLIT_SHAPE"); h->split_shape = e ? atoi(e) : 3; }    // 4 warps x 5 CTAs per SM (96 registers) measured best
     CK(h, cudaFuncSetAttribute(schur_kernel<160, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem_bytes(kMaxFrames)));
     CK(h, cudaFuncSetAttribute(schur_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem_bytes(kMaxFrames)));
     { const char *e = getenv("PVIO_B200_SPLIT"); h->split_schur = !(e && e[0] == '0'); }     // default on; 0: the fused kernel

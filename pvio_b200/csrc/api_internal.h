@@ -61,7 +61,7 @@ struct Handle {
     int max_slot_free = 0;        // most free (non FF_FIX_POSE) frames of any window packed so far
     int max_slot_N = 0;           // largest window packed so far (selects the tensor-core linearise kernel)
     int tc_gs = 1;                // k-steps per TMEM partial sum (PVIO_B200_TC_GS, experiments)
-    int split_shape = 2;          // CTA shape of lin_a_kernel (experiments)
+    int split_shape = 3;          // CTA shape of lin_a_kernel (experiments)
     bool split_schur = true;      // PVIO_B200_SPLIT=1: linearise stage as two kernels (Phase A, then schur_kernel)
     int tc_mode = 0;              // PVIO_B200_TC: 1 = fused tcgen05 linearise kernel, 2 = split stage with the tcgen05 Schur kernel
     bool use_tc = false;          // PVIO_B200_TC=1: tcgen05 Schur SYRK (lin_tc_kernel) instead of the CUDA-core one

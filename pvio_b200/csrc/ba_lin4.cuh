@@ -8,10 +8,12 @@
 
 namespace pvio {
 
+constexpr int kDta = 28;                        // doubles per (target, anchor) block: 21 sym + 6 grad + 1 pad
+
 template <int kWarps>
 __host__ __device__ inline size_t lin4_smem_bytes(int N) {
     const size_t nsp = (size_t)N * (N - 1) / 2;
-    return sizeof(FrameSm) * kMaxFrames + sizeof(double) * ((nsp + 1) * 33 + 8) + 16 + sizeof(float) * (size_t)kWarps * 32 * (6 * N + 2);
+    return sizeof(FrameSm) * N + sizeof(double) * ((nsp + 1) * kDta + 8) + 16 + sizeof(float) * (size_t)kWarps * 32 * (6 * N + 2);
 }
 
 template <bool kLoss, int kWarps, int kMinBlocks>
@@ -28,12 +30,12 @@ lin_a_kernel(LinArgs a) {
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameSm *F = reinterpret_cast<FrameSm *>(smem_raw);
-    double *Dta = reinterpret_cast<double *>(F + kMaxFrames);       // [nsp + 1][33] direct blocks: 21 sym + 6 grad (+6 pad)
-    double *cost_sm = Dta + (nsp + 1) * 33;                         // [8]
-    float *hbuf = reinterpret_cast<float *>(smem_raw + ((sizeof(FrameSm) * kMaxFrames + sizeof(double) * ((nsp + 1) * 33 + 8) + 15) & ~(size_t)15));
+    double *Dta = reinterpret_cast<double *>(F + N);                // [nsp + 1][kDta] direct blocks (sized by the window: 5 CTAs per SM)
+    double *cost_sm = Dta + (nsp + 1) * kDta;                       // [8]
+    float *hbuf = reinterpret_cast<float *>(smem_raw + ((sizeof(FrameSm) * N + sizeof(double) * ((nsp + 1) * kDta + 8) + 15) & ~(size_t)15));
 
     if (tid < N) make_frame(a.frames + ((size_t)w * a.Ncap + tid) * kFrameStride, wc, F[tid]);
-    for (int i = tid; i < (nsp + 1) * 33 + 8; i += kThreads) Dta[i] = 0.0;
+    for (int i = tid; i < (nsp + 1) * kDta + 8; i += kThreads) Dta[i] = 0.0;
     __syncthreads();
 
     const float W[4] = {(float)wc.sic[0], (float)wc.sic[1], (float)wc.sic[2], (float)wc.sic[3]};
@@ -110,7 +112,7 @@ lin_a_kernel(LinArgs a) {
                 const float tot = (peers == (todo | peers)) ? transpose_reduce32(q, true, lane) : transpose_reduce32(q, mine, lane);
                 if (lane < kDirVals && tf != anchor) {
                     const int sp = tf > anchor ? spair(tf, anchor) : spair(anchor, tf);
-                    atomicAdd(&Dta[sp * 33 + lane], (double)tot);              // +sum Y^T Y; the epilogue applies the signs
+                    atomicAdd(&Dta[sp * kDta + lane], (double)tot);              // +sum Y^T Y; the epilogue applies the signs
                 }
             }
         }
@@ -167,7 +169,7 @@ lin_a_kernel(LinArgs a) {
         double d = 0.0;
         for (int g = 0; g < N; ++g) {
             if (g == f) continue;
-            d += Dta[(f > g ? spair(f, g) : spair(g, f)) * 33 + se];
+            d += Dta[(f > g ? spair(f, g) : spair(g, f)) * kDta + se];
         }
         if (exclusive) { Hdd_o[e] = d; Hred_o[pair_idx(f, f) * 36 + ij] = d; }
         else if (d != 0.0) { atomicAdd(&Hdd_o[e], d); atomicAdd(&Hred_o[pair_idx(f, f) * 36 + ij], d); }
@@ -178,7 +180,7 @@ lin_a_kernel(LinArgs a) {
         while ((f + 1) * f / 2 <= sp) ++f;
         const int g = sp - f * (f - 1) / 2;
         const int se = i <= j ? sym6(i, j) : sym6(j, i);
-        const double v = -Dta[sp * 33 + se];
+        const double v = -Dta[sp * kDta + se];
         if (exclusive) Hred_o[pair_idx(f, g) * 36 + ij] = v; else if (v != 0.0) atomicAdd(&Hred_o[pair_idx(f, g) * 36 + ij], v);
     }
     for (int e = tid; e < N * 6; e += kThreads) {                   // gradients (f is the target when f > g)
@@ -186,7 +188,7 @@ lin_a_kernel(LinArgs a) {
         double d = 0.0;
         for (int g = 0; g < N; ++g) {
             if (g == f) continue;
-            const double v = Dta[(f > g ? spair(f, g) : spair(g, f)) * 33 + 21 + i];
+            const double v = Dta[(f > g ? spair(f, g) : spair(g, f)) * kDta + 21 + i];
             d += (f > g) ? v : -v;
         }
         if (exclusive) { gdir_o[e] = d; gred_o[e] = d; }

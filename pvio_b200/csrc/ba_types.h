@@ -10,8 +10,8 @@ namespace pvio {
 constexpr int kMaxFrames = 16;      // PVIO_B200_MAX_FRAMES
 constexpr int kFrameStride = 16;    // doubles per frame state
 constexpr int kImuStride = 288;     // doubles per IMU factor record
-constexpr int kMaxChunks = 96;
-constexpr int kAcc = 16;            // doubles per window accumulated by the update / J.v sweeps      // anchor-homogeneous chunks of <= 32 landmarks per window
+constexpr int kMaxChunks = 96;      // anchor-homogeneous chunks of <= 32 landmarks per window
+constexpr int kAcc = 16;            // doubles per window accumulated by the update / J.v sweeps
 
 struct __align__(8) ObsRec {        // one reprojection residual block (non-anchor observation), 8 B
     float zx, zy;                   // normalised keypoint in the target frame
