@@ -175,6 +175,36 @@ def test_throughput_kernels_match_oracle(case, mode, monkeypatch):
     assert np.array_equal(dx[0], dx[W - 1])
 
 
+@pytest.mark.parametrize("split", ["1", "0"])
+@pytest.mark.parametrize("mixed_inertial", [False, True])
+def test_throughput_heterogeneous_batch(split, mixed_inertial, monkeypatch):
+    """One launch over windows of different sizes, anchors, visibility patterns and fixed-frame sets (and, in the
+    second variant, visual-only and inertial windows side by side): every window against its own oracle step."""
+    monkeypatch.setenv("PVIO_B200_SPLIT", split)
+    monkeypatch.setenv("PVIO_B200_TC", "0")
+    kinds = [synth.make_cfg2(N=10, M=120, seed=41)[:2], synth.make_cfg2(N=6, M=80, staggered=True, seed=42)[:2], _ragged_window()]
+    w3, s3, _ = synth.make_cfg2(N=8, M=100, seed=43)
+    w3.frame_fixed[:] = 0; w3.frame_fixed[0] = 1; w3.frame_fixed[5] = 1
+    kinds.append((w3, s3))
+    if mixed_inertial:
+        kinds.append(synth.make_cfg3(N=6, M=60, seed=44)[:2])
+    W = 150
+    b = BundleAdjustor(max_windows=W, max_frames=10, max_landmarks=160, max_obs=1500)
+    for i in range(W):
+        b.batch_set(i, *kinds[i % len(kinds)])
+    b.batch_upload(W)
+    b.batch_gn_step(W, 1e-8, apply=False)
+    stride = 15 * 10 + 160
+    dx, costs = b.batch_download(W, stride)
+    b.close()
+    for k, (w, st) in enumerate(kinds):
+        ref = bo.gn_step(w, st, schur=True)
+        n = 15 * w.N + w.M
+        for i in (k, k + len(kinds) * ((W - 1 - k) // len(kinds))):        # first and last window of this kind
+            assert _rel(dx[i, :n], ref['dx']) < TOL_DX, (k, i)
+            assert abs(costs[i, 0] - ref['cost']) <= 2e-6 * ref['cost']
+
+
 def test_full_size_batch_properties():
     """BASELINE's full bench size (4096 cfg2 windows per launch): size-independent properties instead of 4096 oracle
     runs -- replicas are bit-identical, the second half of the batch is scaled noise (different data) and must still
