@@ -688,6 +688,8 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->pnp_dev) cudaFree(h->pnp_dev);
+    if (h->pnp_host) cudaFreeHost(h->pnp_host);
     klt_free(h);
     release(h->hdr); release(h->cst); release(h->obs); release(h->lms); release(h->rho); release(h->frames);
     release(h->ctrl); release(h->rho_cand); release(h->frames_cand); release(h->lm_scale); release(h->lm_aux); release(h->hs);

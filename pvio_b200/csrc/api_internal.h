@@ -76,6 +76,8 @@ struct Handle {
     bool capturing = false;
     bool use_graphs = true;
     KltState *klt = nullptr;
+    double *pnp_dev = nullptr, *pnp_host = nullptr;   // pnp.cu: device buffer + pinned staging, grown on demand
+    size_t pnp_words = 0;
 };
 
 int fail(Handle *h, int code, const char *what, cudaError_t e = cudaSuccess);

@@ -287,14 +287,22 @@ int pnp_solve_impl(Handle *h, const pvio_b200_pnp_problem *pb, double *frame, co
     const int n = pb->n_points;
     if (n < 0 || !frame || !pb->last_frame || (pb->use_inertial && !pb->imu_data))
         return fail(h, PVIO_B200_EINVAL, "pnp: bad arguments");
-    double *d = nullptr;
     const size_t words = (size_t)5 * n + 16 + 8 + kImuStride;
-    CK(h, cudaMalloc(&d, sizeof(double) * words));
-    std::vector<double> stage(words, 0.0);
-    if (n > 0) { memcpy(stage.data(), pb->points, sizeof(double) * 3 * n); memcpy(stage.data() + 3 * n, pb->z, sizeof(double) * 2 * n); }
-    memcpy(stage.data() + 5 * n, frame, sizeof(double) * 16);
-    if (pb->use_inertial) memcpy(stage.data() + 5 * n + 24, pb->imu_data, sizeof(double) * kImuStride);
-    CK(h, cudaMemcpyAsync(d, stage.data(), sizeof(double) * words, cudaMemcpyHostToDevice, h->stream));
+    if (words > h->pnp_words) {                       // this runs on every frame: no allocation in the steady state
+        if (h->pnp_dev) cudaFree(h->pnp_dev);
+        if (h->pnp_host) cudaFreeHost(h->pnp_host);
+        h->pnp_dev = nullptr; h->pnp_host = nullptr; h->pnp_words = 0;
+        const size_t cap = std::max<size_t>(words, (size_t)5 * 512 + 16 + 8 + kImuStride);
+        CK(h, cudaMalloc(&h->pnp_dev, sizeof(double) * cap));
+        CK(h, cudaMallocHost(&h->pnp_host, sizeof(double) * cap));
+        h->pnp_words = cap;
+    }
+    double *d = h->pnp_dev, *stage = h->pnp_host;
+    memset(stage, 0, sizeof(double) * words);
+    if (n > 0) { memcpy(stage, pb->points, sizeof(double) * 3 * n); memcpy(stage + 3 * n, pb->z, sizeof(double) * 2 * n); }
+    memcpy(stage + 5 * n, frame, sizeof(double) * 16);
+    if (pb->use_inertial) memcpy(stage + 5 * n + 24, pb->imu_data, sizeof(double) * kImuStride);
+    CK(h, cudaMemcpyAsync(d, stage, sizeof(double) * words, cudaMemcpyHostToDevice, h->stream));
     PnpArgs a;
     memset(&a, 0, sizeof(a));
     a.pts = d; a.z = d + 3 * n; a.frame = d + 5 * n; a.out = d + 5 * n + 16; a.imu_rec = d + 5 * n + 24;
@@ -310,11 +318,10 @@ int pnp_solve_impl(Handle *h, const pvio_b200_pnp_problem *pb, double *frame, co
     pnp_kernel<<<1, kPnpThreads, 0, h->stream>>>(a);
     CK(h, cudaEventRecord(h->ev1, h->stream));
     ++h->launches;
-    double back[24];
+    double *back = stage + 5 * n;                     // the frame + summary words come back into the pinned staging
     CK(h, cudaMemcpyAsync(back, d + 5 * n, sizeof(double) * 24, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaGetLastError());
-    cudaFree(d);
     memcpy(frame, back, sizeof(double) * 16);
     if (summary) {
         memset(summary, 0, sizeof(*summary));
