@@ -132,7 +132,7 @@ def test_gn_step_cfg4_planes(ba):
 
 
 @pytest.mark.parametrize("mode", ["fused", "tc", "split", "split_tc"])
-@pytest.mark.parametrize("case", ["cfg2", "cfg2b", "ragged", "cfg3", "cfg4", "cfg2_free"])
+@pytest.mark.parametrize("case", ["cfg2", "cfg2b", "ragged", "cfg3", "cfg4", "cfg2_free", "cfg2_n16"])
 def test_throughput_kernels_match_oracle(case, mode, monkeypatch):
     """Batches of >= 74 windows run the thread-per-landmark linearise kernels: lin_tpl_kernel (CUDA-core
     Schur SYRK, the default) and, with PVIO_B200_TC=1 and windows of <= 10 frames, lin_tc_kernel (tcgen05
@@ -151,13 +151,15 @@ def test_throughput_kernels_match_oracle(case, mode, monkeypatch):
         w, st, _ = synth.make_cfg3()
     elif case == "cfg4":
         w, st, _ = synth.make_cfg4()
+    elif case == "cfg2_n16":           # the largest window of the ABI: the tensor-core variants must fall back by themselves
+        w, st, _ = synth.make_cfg2(N=16, M=240, staggered=True, seed=12)
     else:
         w, st, _ = synth.make_cfg2(N=8, M=200, seed=31)
         w.frame_fixed[:] = 0
         w.frame_fixed[0] = 1
         w.frame_fixed[3] = 1           # non-contiguous fixed frames (free-frame enumeration of the Schur tiles)
     W = 160
-    b = BundleAdjustor(max_windows=W, max_frames=10, max_landmarks=640, max_obs=6000)
+    b = BundleAdjustor(max_windows=W, max_frames=16 if case == "cfg2_n16" else 10, max_landmarks=640, max_obs=6000)
     b.batch_set(0, w, st)
     b.batch_replicate(W)
     b.batch_upload(W)
