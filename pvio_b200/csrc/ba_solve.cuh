@@ -69,8 +69,9 @@ __device__ __forceinline__ int tri(int i, int j) {   // element (i,j), j <= i
 // ---- IMU factor: raw residual and Jacobian (before whitening); J is [15][30] row-major.
 __device__ inline void imu_factor_raw(const double *fi, const double *fj, const double *rec,
                                       const WinConst &wc, int alias_bias, double *r, double *J) {
+    // J == nullptr: residual only (candidate-cost evaluations)
     const double g[3] = {0.0, 0.0, -9.80665};                 // preintegration_error_cost.h:41
-    for (int i = 0; i < 450; ++i) J[i] = 0.0;
+    if (J) for (int i = 0; i < 450; ++i) J[i] = 0.0;
     const double *qic = fi, *pic = fi + 4, *vi = fi + 7, *bgi = fi + 10, *bai = fi + 13;
     const double *qjc = fj, *pjc = fj + 4, *vj = fj + 7, *bgj = fj + 10, *baj = fj + 13;
     const double dt = rec[0];
@@ -115,6 +116,7 @@ __device__ inline void imu_factor_raw(const double *fi, const double *fj, const 
     mat3_vec(dv_dba, dba, d_);
     for (int k = 0; k < 3; ++k) r[6 + k] = b3[k] - (dv[k] + c_[k] + d_[k]);   // :81
     for (int k = 0; k < 3; ++k) { r[9 + k] = bgj[k] - bgi[k]; r[12 + k] = baj[k] - bai[k]; }  // :82-83
+    if (!J) return;
 
     double Jr[9], Jri[9], Rimu[9], Rj[9];
     right_jacobian(r, Jr);
@@ -927,7 +929,7 @@ static __global__ void aux_cost_kernel(CostArgs a) {
         const double *recs = a.imu_data + (size_t)w * a.Ncap * kImuStride;
         for (int n = tid; n < H.n_imu; n += nt) {
             // residual only: reuse the raw evaluator (Jacobian discarded)
-            double r[15], J[450];
+            double r[15];
             double rec_local[kImuStride];
             const double *rec = recs + (size_t)n * kImuStride;
             for (int k = 0; k < kImuStride; ++k) rec_local[k] = rec[k];
@@ -937,7 +939,7 @@ static __global__ void aux_cost_kernel(CostArgs a) {
                     rec_local[284 + k] = fcur[idx[2 * n] * kFrameStride + 13 + k];
                 }
             }
-            imu_factor_raw(fc + idx[2 * n] * kFrameStride, fc + idx[2 * n + 1] * kFrameStride, rec_local, wc, 0, r, J);
+            imu_factor_raw(fc + idx[2 * n] * kFrameStride, fc + idx[2 * n + 1] * kFrameStride, rec_local, wc, 0, r, nullptr);
             double c = 0.0;
             for (int i = 0; i < 15; ++i) {
                 double s = 0.0;

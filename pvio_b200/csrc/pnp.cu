@@ -101,7 +101,7 @@ __device__ void pnp_evaluate(const PnpArgs &a, PnpShared &S, const double *xs, b
     }
     // IMU prior factor: frame_i = last frame (constant), Jacobian columns of frame_j only
     if (a.inertial) {
-        if (tid == 32) imu_factor_raw(a.last, xs, a.imu_rec, a.wc, 1, S.rraw, S.Jraw);
+        if (tid == 32) imu_factor_raw(a.last, xs, a.imu_rec, a.wc, 1, S.rraw, jac ? S.Jraw : nullptr);
         __syncthreads();
         for (int e = tid; e < 15 * 16; e += kPnpThreads) {
             const int row = e / 16, col = e - row * 16;
