@@ -107,7 +107,8 @@ __global__ void prior_lambda_kernel(const WinHdr *hdr, const double *S, double *
     const int d = 15 * hdr[w].n_prior, dcap = 15 * Ncap;
     const double *Sw = S + (size_t)w * dcap * dcap;
     double *Lw = L + (size_t)w * dcap * dcap;
-    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    // gridDim.y CTAs share a window (a single window would otherwise leave 147 SMs idle for 0.29 ms)
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < d * d; e += blockDim.x * gridDim.y) {
         const int i = e / d, j = e - i * d;
         double s = 0.0;
         for (int k = 0; k < d; ++k) s += Sw[(size_t)k * d + i] * Sw[(size_t)k * d + j];
@@ -316,7 +317,7 @@ static int upload_range(Handle *h, int w0, int n, cudaStream_t st) {
         TRY(h2d(h, h->prior_x0, N * kFrameStride, w0, n, st));
         for (int i = w0; i < w0 + n; ++i) any_prior |= h->hdr.h[i].n_prior > 0;
         if (any_prior) {
-            prior_lambda_kernel<<<n, 256, 0, st>>>(h->hdr.d, h->prior_S.d, h->prior_L.d, h->Ncap, w0);
+            prior_lambda_kernel<<<dim3(n, n < 64 ? 32 : 1), 256, 0, st>>>(h->hdr.d, h->prior_S.d, h->prior_L.d, h->Ncap, w0);
             ++h->launches;
         }
     }
