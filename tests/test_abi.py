@@ -42,3 +42,40 @@ def test_no_cpu_fallback():
     from pvio_b200.bundle_adjustor import BundleAdjustor, PvioB200Error
     with pytest.raises(PvioB200Error):
         BundleAdjustor()
+
+
+def test_header_is_plain_c_and_cxx():
+    """The boundary must be bindable from cgo-style C as well as from PVIO's C++17: the header compiles alone in both."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "pvio_b200.h")
+    for cc, std, lang in (("gcc", "-std=c99", "c"), ("g++", "-std=c++17", "c++")):
+        if shutil.which(cc) is None:
+            pytest.skip(cc + " not installed")
+        r = subprocess.run([cc, std, "-Wall", "-Werror", "-fsyntax-only", "-x", lang, hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_integration_shim_compiles_against_the_header(tmp_path):
+    """A minimal C caller (what a cgo / FFI stub would generate) links against the built library without a GPU:
+    create() must fail cleanly with ENODEV here, never crash."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not installed")
+    from pvio_b200 import build
+    lib = build.build()
+    src = tmp_path / "caller.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "pvio_b200.h"\n'
+        'int main(void) { pvio_b200_handle h = 0; int rc = pvio_b200_create(0, 1, 8, 64, 512, &h);\n'
+        '  printf("%d %s\\n", rc, pvio_b200_version()); if (h) pvio_b200_destroy(h); return 0; }\n')
+    exe = tmp_path / "caller"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), lib,
+                        "-Wl,-rpath," + os.path.dirname(lib), "-L/usr/local/cuda/lib64", "-lcudart", "-lstdc++"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    rc = int(out.stdout.split()[0])
+    assert rc in (0, -1, -4), out.stdout          # 0 on a GPU box; ENODEV / ECUDA here
