@@ -1,3 +1,6 @@
+"""Diagnostic script (not collected by pytest; run by hand on a GPU box): where the dx difference of the gauge-prior
+window lives -- conditioning of the reduced system, eigen-direction of the error.  Lives under tests/ because it
+uses the oracle."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

@@ -25,13 +25,12 @@ p, s_, e_ = klt.track_keypoints(ba, prev, nxt, pts)
 print('klt', int(s_.sum()))
 # newer kernels: PnP, IMU pre-integration, triangulation, tensor-core SYRK (self-test and opt-in lin kernel)
 from pvio_b200 import pnp, imu, triangulate as tri
-from oracle import tri_oracle, lie
 d = synth.make_pnp()
 _, ps = pnp.visual_inertial_pnp(ba, d['frame'], d['last'], d['imu'], d['pts'], d['zs'], d['cam_q'], d['cam_p'], d['imu_q'], d['imu_p'], d['W'], True)
 print('pnp', ps['iterations'])
 _, _, truth = synth.make_cfg3(N=4, M=30)
 print('imu', np.linalg.norm(imu.preintegrate(ba, truth.imu_factors, truth.imu_noise)[:, :11]))
-P = np.array([tri_oracle.projection_matrix(lie.expmap(np.zeros(3)), np.array([0.3 * i, 0, 0])) for i in range(4)])
+P = np.array([np.c_[np.eye(3), -np.array([0.3 * i, 0, 0])] for i in range(4)])      # identity rotation, camera at (0.3 i, 0, 0)
 X = np.array([0.2, 0.1, 5.0])
 zz = np.array([(P[f] @ np.r_[X, 1])[:2] / (P[f] @ np.r_[X, 1])[2] for f in range(4)])
 print('tri', tri.triangulate(ba, P, [0, 4], [0, 1, 2, 3], zz)[0])
