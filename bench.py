@@ -357,7 +357,7 @@ def run_gpu(args):
         "dtype": "f32 Jacobians + f64 residuals/accumulation/solve", "data": "synthetic",
         "config": {"workload": f"cfg2 (10 KF x 500 landmarks, K_res=4500, reprojection-only GN, frames 0-1 fixed) x {W} "
                                "independent windows per GPU per step",
-                   "windows_per_gpu": W, "l2_policy": f"inputs {balg * W / 1e6:.0f} MB per step exceed the 126 MB L2",
+                   "windows_per_gpu": W, "l2_policy": f"device-resident inputs {(8 * K + 24 * M + 128 * N + 1056) * W / 1e6:.0f} MB + {(M // 32 + 1) * 32 * (6 * N + 2) * 4 * W / 1e6:.0f} MB of intermediate records per step exceed the 126 MB L2",
                    "parallelism": f"independent windows, {world} GPU(s), no data-path collective"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
