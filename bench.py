@@ -105,7 +105,7 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return 0
-    from pvio_b200 import synth
+    from synthetic import synth
     win, st, _ = synth.make_cfg2()
     ncpu = os.cpu_count() or 1
     n_sample = max(64, min(args.windows, 128 * ncpu))     # ~10-30 s of CPU work in total over the run
@@ -141,7 +141,8 @@ def run_gpu(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from pvio_b200 import synth, klt, pnp, imu
+    from pvio_b200 import klt, pnp, imu
+    from synthetic import synth
     from pvio_b200.bundle_adjustor import BundleAdjustor
 
     W = args.windows

@@ -186,11 +186,24 @@ int pvio_b200_batch_download(pvio_b200_handle h, int n, double *dx, int64_t dx_s
 /* upload + gn_step + download in one call: the end-to-end path bench.py times. */
 int pvio_b200_batch_gn_step_host(pvio_b200_handle h, int n, double mu, double *dx,
                                  int64_t dx_stride, double *costs);
+/* Full trust-region solve (ceres::Solve semantics per window: dogleg, per-window termination, at most
+ * opt->max_iterations iterations) of the first n uploaded windows, entirely on the device: no host round trip per
+ * iteration.  The device-resident states are overwritten with the solutions (BASELINE config 5: independent windows). */
+int pvio_b200_batch_solve(pvio_b200_handle h, int n, const pvio_b200_options *opt);
+/* Device -> host: solved states frames [n][frames_stride] (16 doubles per frame), inv_depth [n][inv_depth_stride] in
+ * the caller's landmark order, one summary per window (solve_seconds is not filled).  Any pointer may be NULL. */
+int pvio_b200_batch_download_state(pvio_b200_handle h, int n, double *frames, int64_t frames_stride, double *inv_depth,
+                                   int64_t inv_depth_stride, pvio_b200_summary *summaries);
+/* upload + batch_solve + download_state in one call with HOST buffers, pipelined over sub-batches: one host -> device
+ * copy buys up to max_iterations iterations per window. */
+int pvio_b200_batch_solve_host(pvio_b200_handle h, int n, const pvio_b200_options *opt, double *frames, int64_t frames_stride,
+                               double *inv_depth, int64_t inv_depth_stride, pvio_b200_summary *summaries);
 int pvio_b200_sync(pvio_b200_handle h);
 /* CUDA-event timing on the handle's stream (bench.py): start / stop return ms. */
 int pvio_b200_timer_start(pvio_b200_handle h);
 int pvio_b200_timer_stop(pvio_b200_handle h, float *ms);
-/* device-side time (ms) of the most recent linearise+Schur kernel launch */
+/* device-side time (ms) of the linearise + Schur stage from CUDA events around its launches: which = 0 the most recent
+ * stage, 1 the mean stage since the last reset, 2 / 3 the mean of the linearise / Schur kernel alone, -1 reset */
 int pvio_b200_last_kernel_ms(pvio_b200_handle h, int which, float *ms);
 
 /* ---- visual-inertial PnP ------------------------------------------------ */
@@ -252,12 +265,11 @@ int pvio_b200_triangulate(pvio_b200_handle h, int n_frames, const double *P, int
                           const int32_t *obs_frame, const double *obs_z, double *points, uint8_t *valid, double *score);
 
 /* ---- diagnostics ---------------------------------------------------------------------- */
-/* Self-test of the tcgen05 3xTF32 SYRK block used by the linearise kernel: D[64][64] = sum_k a_k a_k^T
- * for K rows of 64 floats (A is [K][64]).  Not part of the reference interface. */
-int pvio_b200_selftest_syrk(pvio_b200_handle h, const float *A, int K, double *D);
-/* one pass (K <= 128), raw dump of the 128 x 64 TMEM block + the TMEM base address (tools/tc_debug.py);
- * mode 0: 3xTF32, 1: unpadded K-major strides, 2: tcgen05.st pattern only, 3: one TF32 pass */
-int pvio_b200_selftest_syrk_raw(pvio_b200_handle h, const float *A, int K, float *out, int mode);
+/* Device self-test of the Lie-group helpers (geometry/lie_algebra.h:25-42, lie_algebra.cpp:22-59,
+ * quaternion_parameterization.h:28-31): w [n][3] rotation vectors; out [n][32] = expmap(w) (4, xyzw),
+ * logmap(expmap(w)) (3), right_jacobian(w) (9, row-major), its inverse (9), Plus(expmap(w), w) (4), 3 spare.
+ * Not part of the reference interface. */
+int pvio_b200_selftest_lie(pvio_b200_handle h, int n, const double *w, double *out);
 
 /* ---- KLT ----------------------------------------------------------------------------- */
 /* Pyramidal Lucas-Kanade with OpenCV's semantics: winSize 21x21, maxLevel levels above

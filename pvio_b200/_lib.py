@@ -10,6 +10,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpvio_b200.so")
+if os.environ.get("PVIO_B200_TUNE_LIB"):        # tools/ only: a tuning build of the same sources (pvio_b200.build, defines=...)
+    LIB_PATH = os.environ["PVIO_B200_TUNE_LIB"]
 
 IMU_STRIDE = 288
 FRAME_STRIDE = 16
@@ -67,7 +69,9 @@ EXPORTS = [
     "pvio_b200_reprojection_error", "pvio_b200_batch_set_window", "pvio_b200_batch_replicate",
     "pvio_b200_batch_upload", "pvio_b200_batch_gn_step", "pvio_b200_batch_download",
     "pvio_b200_batch_gn_step_host", "pvio_b200_sync", "pvio_b200_timer_start", "pvio_b200_timer_stop",
-    "pvio_b200_last_kernel_ms", "pvio_b200_klt_track", "pvio_b200_pnp_solve", "pvio_b200_selftest_syrk", "pvio_b200_selftest_syrk_raw", "pvio_b200_preintegrate", "pvio_b200_triangulate", "pvio_b200_klt_track_raw", "pvio_b200_clahe",
+    "pvio_b200_last_kernel_ms", "pvio_b200_klt_track", "pvio_b200_pnp_solve", "pvio_b200_preintegrate",
+    "pvio_b200_triangulate", "pvio_b200_klt_track_raw", "pvio_b200_clahe", "pvio_b200_batch_solve",
+    "pvio_b200_batch_download_state", "pvio_b200_batch_solve_host", "pvio_b200_selftest_lie",
 ]
 
 _lib = None
@@ -105,6 +109,11 @@ def load():
     lib.pvio_b200_batch_gn_step.argtypes = [vp, C.c_int, C.c_double, C.c_int]
     lib.pvio_b200_batch_download.argtypes = [vp, C.c_int, c_f64p, C.c_int64, c_f64p]
     lib.pvio_b200_batch_gn_step_host.argtypes = [vp, C.c_int, C.c_double, c_f64p, C.c_int64, c_f64p]
+    lib.pvio_b200_batch_solve.argtypes = [vp, C.c_int, C.POINTER(COptions)]
+    lib.pvio_b200_batch_download_state.argtypes = [vp, C.c_int, c_f64p, C.c_int64, c_f64p, C.c_int64, C.POINTER(CSummary)]
+    lib.pvio_b200_batch_solve_host.argtypes = [vp, C.c_int, C.POINTER(COptions), c_f64p, C.c_int64, c_f64p, C.c_int64,
+                                               C.POINTER(CSummary)]
+    lib.pvio_b200_selftest_lie.argtypes = [vp, C.c_int, c_f64p, c_f64p]
     lib.pvio_b200_sync.argtypes = [vp]
     lib.pvio_b200_timer_start.argtypes = [vp]
     lib.pvio_b200_timer_stop.argtypes = [vp, c_f32p]

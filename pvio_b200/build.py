@@ -20,7 +20,10 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: tuning builds (tools/tune_build.py) -- objects go to a side directory, the product .so is untouched."""
+    if defines or out:
+        return _build_variant(list(defines), out)
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "pvio_b200.h"))
@@ -54,6 +57,30 @@ def build(force=False, verbose=False):
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
     return OUT
+
+
+def _build_variant(defines, out):
+    odir = os.path.join(HERE, "csrc", "_variants", os.path.basename(out))
+    os.makedirs(odir, exist_ok=True)
+    objs = []
+    for s in sorted(f for f in os.listdir(CSRC) if f.endswith(".cu")):
+        obj = os.path.join(odir, s[:-3] + ".o")
+        extra = ["-fmad=false"] if s == "klt.cu" else []
+        ref = os.path.join(CSRC, s[:-3] + ".o")
+        if s != "api.cu" and os.path.exists(ref):      # only api.cu depends on the tuning defines
+            objs.append(ref)
+            continue
+        r = subprocess.run([NVCC] + [f for f in FLAGS if f not in ("-Xptxas", "-v")] + extra + ["-D" + d for d in defines] +
+                           ["-c", os.path.join(CSRC, s), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed on " + s)
+        objs.append(obj)
+    r = subprocess.run([NVCC, "-shared", "-o", out] + objs + ["-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return out
 
 
 if __name__ == "__main__":

@@ -128,6 +128,37 @@ class BundleAdjustor:
                                                        _lib._ptr(costs, C.c_double)))
         return dx, costs
 
+    def batch_solve(self, n, max_iterations=10, max_time=0.0, alias_bias=True, initial_radius=0.0):
+        """Full trust-region solve of the first n uploaded windows, device-side loop with per-window termination."""
+        opt = _lib.COptions(max_iterations, max_time, 1 if alias_bias else 0, 0, initial_radius)
+        self._ck(self.lib.pvio_b200_batch_solve(self.h, n, C.byref(opt)))
+
+    def batch_download_state(self, n, N, M):
+        """Solved states of the first n windows: (frames [n, N, 16], inv_depth [n, M], list of summary dicts)."""
+        frames = np.zeros((n, N * 16))
+        rho = np.zeros((n, max(M, 1)))
+        sm = (_lib.CSummary * n)()
+        self._ck(self.lib.pvio_b200_batch_download_state(self.h, n, _lib._ptr(frames, C.c_double), N * 16,
+                                                         _lib._ptr(rho, C.c_double), max(M, 1), sm))
+        return frames.reshape(n, N, 16), rho[:, :M], [{k: getattr(x, k) for k, _ in _lib.CSummary._fields_} for x in sm]
+
+    def batch_solve_host(self, n, N, M, max_iterations=10, alias_bias=True, frames=None, rho=None):
+        """upload + solve + download through host buffers (the end-to-end call bench.py times)."""
+        frames = np.zeros((n, N * 16)) if frames is None else frames
+        rho = np.zeros((n, max(M, 1))) if rho is None else rho
+        opt = _lib.COptions(max_iterations, 0.0, 1 if alias_bias else 0, 0, 0.0)
+        sm = (_lib.CSummary * n)()
+        self._ck(self.lib.pvio_b200_batch_solve_host(self.h, n, C.byref(opt), _lib._ptr(frames, C.c_double), N * 16,
+                                                     _lib._ptr(rho, C.c_double), max(M, 1), sm))
+        return frames, rho, sm
+
+    def selftest_lie(self, w):
+        """Device expmap / logmap / right_jacobian / Plus on rotation vectors w [n, 3] -> [n, 32] (see the header)."""
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        out = np.zeros((len(w), 32))
+        self._ck(self.lib.pvio_b200_selftest_lie(self.h, len(w), _lib._ptr(w, C.c_double), _lib._ptr(out, C.c_double)))
+        return out
+
     def sync(self):
         self._ck(self.lib.pvio_b200_sync(self.h))
 

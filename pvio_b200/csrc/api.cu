@@ -1,5 +1,7 @@
 // libpvio_b200: C-ABI entry points (include/pvio_b200.h), host-side packing and launch
-// orchestration of the bundle-adjustment kernels.  No torch types, no CPU fallback.
+// orchestration of the bundle-adjustment kernels.  No torch types, no CPU fallback, no environment switches:
+// one pipeline (frame-major table -> linearise -> Schur -> solve -> back-substitution / candidate), in fp32
+// Jacobians for visual-only windows and fp64 for windows with motion states.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -8,12 +10,11 @@
 #include <cstring>
 #include <numeric>
 #include "api_internal.h"
-#include "ba_lin.cuh"
-#include "ba_lin2.cuh"
-#include "ba_lin3.cuh"
+#include "ba_fobs.cuh"
+#include "ba_linearize.cuh"
 #include "ba_schur.cuh"
-#include "ba_schur_tc.cuh"
 #include "ba_solve.cuh"
+#include "ba_tr.cuh"
 #include "ba_update.cuh"
 
 namespace pvio {
@@ -46,62 +47,65 @@ static void release(DevBuf<T> &b) {
     b.d = nullptr; b.h = nullptr; b.n = 0;
 }
 
-#define TRY(x) do { int rc__ = (x); if (rc__ != 0) return rc__; } while (0)
+void drop_graphs(Handle *h) {
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+    h->graphs.clear();
+}
 
 static int ensure_inertial(Handle *h) {
     if (h->have_inertial) return 0;
     const size_t W = h->W, N = h->Ncap, dcap = 15 * N;
+    cudaStreamSynchronize(h->stream);
+    drop_graphs(h);                                 // the record array is reallocated below: pointers in cached graphs go stale
     TRY(alloc(h, h->imu_idx, W * N * 2, true));
     TRY(alloc(h, h->imu_data, W * N * kImuStride, true));
     TRY(alloc(h, h->prior_frames, W * N, true));
     TRY(alloc(h, h->prior_S, W * dcap * dcap, true));
-    TRY(alloc(h, h->prior_L, W * dcap * dcap, true));
+    TRY(alloc(h, h->prior_L, W * dcap * dcap, false));
     TRY(alloc(h, h->prior_e, W * dcap, true));
     TRY(alloc(h, h->prior_x0, W * N * kFrameStride, true));
+    // windows with motion states run the fp64 pipeline: h records of 8-byte elements
+    release(h->hs); release(h->jr); release(h->lm_w);
+    TRY(alloc(h, h->hs, W * N * (size_t)h->Mcap * 6 * sizeof(double), false));
+    TRY(alloc(h, h->jr, W * N * (size_t)h->Mcap * 2 * sizeof(double), false));
+    TRY(alloc(h, h->lm_w, W * (size_t)h->Mcap * 2 * sizeof(double), false));
+    h->hs_double = true;
     h->have_inertial = true;
     return 0;
 }
 
+// Plane buffers grow on demand WITHOUT losing the slots already packed into the pinned staging area
+// (the device copies are refreshed by the next upload anyway).
 static int ensure_planes(Handle *h, int T, int O) {
     if (h->have_planes && T <= h->Tcap && O <= h->Ocap) return 0;
-    release(h->plane_param); release(h->pt_plane); release(h->pt_begin); release(h->pt_frame); release(h->pt_z);
-    h->Tcap = std::max(T, 256);
-    h->Ocap = std::max(O, 256 * 8);
+    const int Tn = std::max({T, h->Tcap, 256}), On = std::max({O, h->Ocap, 256 * 8});
     const size_t W = h->W;
-    TRY(alloc(h, h->plane_param, W * h->Pcap * 4, true));
-    TRY(alloc(h, h->pt_plane, W * h->Tcap, true));
-    TRY(alloc(h, h->pt_begin, W * (h->Tcap + 1), true));
-    TRY(alloc(h, h->pt_frame, W * h->Ocap, true));
-    TRY(alloc(h, h->pt_z, W * h->Ocap * 2, true));
+    cudaStreamSynchronize(h->stream);
+    drop_graphs(h);
+    DevBuf<double> pp; DevBuf<int32_t> tp, tb, tf; DevBuf<float> tz;
+    TRY(alloc(h, pp, W * h->Pcap * 4, true));
+    TRY(alloc(h, tp, W * Tn, true));
+    TRY(alloc(h, tb, W * (Tn + 1), true));
+    TRY(alloc(h, tf, W * On, true));
+    TRY(alloc(h, tz, W * On * 2, true));
+    if (h->have_planes) {
+        memcpy(pp.h, h->plane_param.h, sizeof(double) * W * h->Pcap * 4);
+        for (size_t i = 0; i < W; ++i) {
+            memcpy(tp.h + i * Tn, h->pt_plane.h + i * h->Tcap, sizeof(int32_t) * h->Tcap);
+            memcpy(tb.h + i * (Tn + 1), h->pt_begin.h + i * (h->Tcap + 1), sizeof(int32_t) * (h->Tcap + 1));
+            memcpy(tf.h + i * On, h->pt_frame.h + i * h->Ocap, sizeof(int32_t) * h->Ocap);
+            memcpy(tz.h + i * On * 2, h->pt_z.h + i * h->Ocap * 2, sizeof(float) * h->Ocap * 2);
+        }
+    }
+    release(h->plane_param); release(h->pt_plane); release(h->pt_begin); release(h->pt_frame); release(h->pt_z);
+    h->plane_param = pp; h->pt_plane = tp; h->pt_begin = tb; h->pt_frame = tf; h->pt_z = tz;
+    h->Tcap = Tn; h->Ocap = On;
     h->have_planes = true;
     return 0;
 }
 
 // ------------------------------------------------------------------------ small kernels
-__global__ void finalize_kernel(WinCtrl *ctrl, const double *acc, const double *aux_cost, int apply,
-                                double *frames, const double *frames_cand, double *rho, const double *rho_cand,
-                                const WinHdr *hdr, int Ncap, int Mcap, double beta, int w0) {
-    const int w = blockIdx.x + w0;
-    WinCtrl &c = ctrl[w];
-    const double *a = acc + (size_t)w * kAcc;
-    if (threadIdx.x == 0) {
-        c.cand_cost_vis = a[0];
-        c.cand_cost = a[0] + aux_cost[w];
-        const double gdx = c.g_dot_dx + a[1];           // g . dx over poses + landmarks (full GN step)
-        const double rdx = c.dx_reg_dx + a[2];          // dx^T (mu D) dx
-        // model cost change of the step beta * dx_gn:  -(beta g.dx + beta^2/2 dx^T H dx),
-        // with dx^T H dx = -g.dx - dx^T (mu D) dx for the regularised Gauss-Newton step
-        c.model_change = -beta * gdx + 0.5 * beta * beta * (gdx + rdx);
-    }
-    if (apply) {
-        const int N = hdr[w].N, M = hdr[w].M;
-        for (int i = threadIdx.x; i < N * kFrameStride; i += blockDim.x)
-            frames[(size_t)w * Ncap * kFrameStride + i] = frames_cand[(size_t)w * Ncap * kFrameStride + i];
-        for (int i = threadIdx.x; i < M; i += blockDim.x) rho[(size_t)w * Mcap + i] = rho_cand[(size_t)w * Mcap + i];
-    }
-}
-
-// Lambda = S^T S of the marginalisation prior (once per solve; constant across iterations)
+// Lambda = S^T S of the marginalisation prior (once per upload; constant across iterations)
 __global__ void prior_lambda_kernel(const WinHdr *hdr, const double *S, double *L, int Ncap, int w0) {
     const int w = blockIdx.x + w0;
     const int d = 15 * hdr[w].n_prior, dcap = 15 * Ncap;
@@ -116,20 +120,12 @@ __global__ void prior_lambda_kernel(const WinHdr *hdr, const double *S, double *
     }
 }
 
-__global__ void init_ctrl_kernel(WinCtrl *ctrl, double mu, double radius) {
-    WinCtrl &c = ctrl[blockIdx.x];
-    if (threadIdx.x == 0) {
-        c.mu = mu; c.radius = radius; c.iteration = 0; c.accepted = 0; c.done = 0;
-        c.termination = PVIO_B200_TERM_NO_CONVERGENCE; c.solve_failed = 0; c.have_scale = 0; c.usable = 1;
-    }
-}
-
 // Landmark post-pass (bundle_adjustor.cpp:277-296): depth test in every observing camera
 // (anchor included) and mean pixel reprojection error.  One group of 16 lanes per landmark.
 __global__ void postpass_kernel(const WinHdr *hdr, const WinConst *cst, const ObsRec *obs, const LmRec *lms,
                                 const double *rho, const double *frames, uint8_t *valid, double *quality,
-                                double *err_acc, int Ncap, int Mcap, int Kcap) {
-    const int w = blockIdx.y;
+                                double *err_acc, int Ncap, int Mcap, int Kcap, int w0) {
+    const int w = blockIdx.y + w0;
     const WinHdr &H = hdr[w];
     const WinConst &wc = cst[w];
     __shared__ FrameSm F[kMaxFrames];
@@ -188,10 +184,46 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
     if (slot < 0 || slot >= h->W) return fail(h, PVIO_B200_EINVAL, "slot out of range");
     if (N < 1 || N > h->Ncap || N > kMaxFrames || M > h->Mcap || K > h->Kcap || M < 0 || K < 0)
         return fail(h, PVIO_B200_EINVAL, "window exceeds the handle's capacity");
+    if (!s->frames || (M > 0 && (!s->inv_depth || !w->lm_anchor || !w->lm_z_ref || !w->lm_obs_begin)) ||
+        (K > 0 && (!w->obs_frame || !w->obs_z)))
+        return fail(h, PVIO_B200_EINVAL, "null array in window / state");
+    // every index array of the caller is range-checked here: bad indices would become device-side out-of-bounds accesses
+    if (M > 0 && (w->lm_obs_begin[0] != 0 || w->lm_obs_begin[M] != K))
+        return fail(h, PVIO_B200_EINVAL, "lm_obs_begin must start at 0 and end at n_obs");
+    const bool inertial = w->use_inertial != 0;
+    const int n_imu = inertial ? w->n_imu : 0, n_prior = inertial ? w->n_prior : 0;
+    if (n_imu < 0 || n_prior < 0 || n_imu > h->Ncap || n_prior > h->Ncap || n_prior > N)
+        return fail(h, PVIO_B200_EINVAL, "too many IMU / prior frames");
+    for (int n = 0; n < n_imu; ++n) {
+        const int i = w->imu_frame_i[n], j = w->imu_frame_j[n];
+        if (i < 0 || i >= N || j < 0 || j >= N || i == j) return fail(h, PVIO_B200_EINVAL, "IMU factor with bad frame indices");
+    }
+    {
+        unsigned seen = 0;
+        for (int n = 0; n < n_prior; ++n) {
+            const int f = w->prior_frames[n];
+            if (f < 0 || f >= N || ((seen >> f) & 1u)) return fail(h, PVIO_B200_EINVAL, "prior_frames must be distinct window indices");
+            seen |= 1u << f;
+        }
+    }
+    if (w->n_plane_tracks < 0 || w->n_planes < 0 || w->n_planes > h->Pcap) return fail(h, PVIO_B200_EINVAL, "too many planes");
+    if (w->n_plane_tracks > 0) {
+        if (!w->pt_obs_begin || !w->pt_plane || !w->pt_obs_frame || !w->pt_obs_z || !w->plane_param || w->pt_obs_begin[0] != 0)
+            return fail(h, PVIO_B200_EINVAL, "null / malformed plane-track arrays");
+        for (int t = 0; t < w->n_plane_tracks; ++t) {
+            const int len = w->pt_obs_begin[t + 1] - w->pt_obs_begin[t];
+            if (len < 0 || len > kMaxFrames) return fail(h, PVIO_B200_EINVAL, "plane track too long / CSR offsets not monotone");
+            if (w->pt_plane[t] < 0 || w->pt_plane[t] >= w->n_planes) return fail(h, PVIO_B200_EINVAL, "pt_plane out of range");
+        }
+        const int O = w->pt_obs_begin[w->n_plane_tracks];
+        for (int i = 0; i < O; ++i)
+            if (w->pt_obs_frame[i] < 0 || w->pt_obs_frame[i] >= N) return fail(h, PVIO_B200_EINVAL, "pt_obs_frame out of range");
+    }
+    if (n_imu > 0 || n_prior > 0 || inertial) TRY(ensure_inertial(h));
     WinHdr &H = h->hdr.h[slot];
     WinConst &C = h->cst.h[slot];
     memset(&H, 0, sizeof(H));
-    H.N = N; H.M = M; H.K = K; H.use_inertial = w->use_inertial ? 1 : 0;
+    H.N = N; H.M = M; H.K = K; H.use_inertial = inertial ? 1 : 0;
     for (int f = 0; f < N; ++f) if (w->frame_fixed && w->frame_fixed[f]) H.fixed_mask |= 1 << f;
     memcpy(C.cam_q, w->cam_q_cs, 32); memcpy(C.cam_p, w->cam_p_cs, 24);
     memcpy(C.imu_q, w->imu_q_cs, 32); memcpy(C.imu_p, w->imu_p_cs, 24);
@@ -208,7 +240,11 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
     perm.resize(M);
     std::iota(perm.begin(), perm.end(), 0);
     bool sorted = true;
-    for (int l = 1; l < M; ++l) if (w->lm_anchor[l] < w->lm_anchor[l - 1]) { sorted = false; break; }
+    for (int l = 0; l < M; ++l) {
+        const int a = w->lm_anchor[l];
+        if (a < 0 || a >= N) return fail(h, PVIO_B200_EINVAL, "landmark with bad anchor");
+        if (l > 0 && a < w->lm_anchor[l - 1]) sorted = false;
+    }
     if (!sorted) std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return w->lm_anchor[a] < w->lm_anchor[b]; });
     ObsRec *ob = h->obs.h + (size_t)slot * h->Kcap;
     LmRec *lm = h->lms.h + (size_t)slot * h->Mcap;
@@ -219,7 +255,7 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
         const int a = w->lm_anchor[l];
         const int b0 = w->lm_obs_begin[l], b1 = w->lm_obs_begin[l + 1];
         const int n = b1 - b0;
-        if (a < 0 || a >= N || n < 0 || n >= kGroup) return fail(h, PVIO_B200_EINVAL, "landmark with bad anchor / too many observations");
+        if (b0 < 0 || b1 > K || n < 0 || n >= kGroup) return fail(h, PVIO_B200_EINVAL, "landmark with bad observation range / too many observations");
         lm[lp].zrx = (float)w->lm_z_ref[2 * l];
         lm[lp].zry = (float)w->lm_z_ref[2 * l + 1];
         lm[lp].obs_begin = k_out;
@@ -232,6 +268,7 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
                 return fail(h, PVIO_B200_EINVAL, "observation frames must be distinct and later than the anchor (Track::first_frame is the lowest id)");
             seen |= 1u << f;
         }
+        if (k_out + n > h->Kcap) return fail(h, PVIO_B200_EINVAL, "observation table overflow");
         for (int k = b0; k < b1; ++k) {
             const int f = w->obs_frame[k];
             const int pos = k_out + __builtin_popcount(seen & ((1u << f) - 1u));
@@ -242,7 +279,7 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
         lm[lp].meta = lm_meta(a, (w->lm_in_victim && w->lm_in_victim[l]) ? 1 : 0, n, seen);
         // chunks: <= kChunk landmarks of one anchor
         if (nch == 0 || (H.chunk_meta[nch - 1] >> 8) != a || (H.chunk_meta[nch - 1] & 0xff) == kChunk) {
-            if (nch == kMaxChunks || nch == h->Mcap / 32 + h->Ncap + 1) return fail(h, PVIO_B200_EINVAL, "too many landmark chunks");
+            if (nch == kMaxChunks) return fail(h, PVIO_B200_EINVAL, "too many landmark chunks");
             H.chunk_begin[nch] = lp;
             H.chunk_meta[nch] = (a << 8);
             ++nch;
@@ -250,25 +287,22 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
         H.chunk_meta[nch - 1] += 1;
     }
     H.n_chunks = nch;
-    h->slot_M[slot] = M; h->slot_N[slot] = N; h->slot_K[slot] = K;
-    h->max_slot_N = std::max(h->max_slot_N, N);
-    h->max_slot_free = std::max(h->max_slot_free, N - __builtin_popcount((unsigned)H.fixed_mask & ((1u << N) - 1u)));
+    H.K = k_out;
+    h->slot_M[slot] = M; h->slot_N[slot] = N; h->slot_K[slot] = k_out;
     h->perm_identity[slot] = sorted ? 1 : 0;
     // inertial part
-    H.n_imu = w->use_inertial ? w->n_imu : 0;
-    H.n_prior = w->use_inertial ? w->n_prior : 0;
-    if (H.n_imu > 0 || H.n_prior > 0) {
-        TRY(ensure_inertial(h));
-        if (H.n_imu > h->Ncap || H.n_prior > h->Ncap) return fail(h, PVIO_B200_EINVAL, "too many IMU / prior frames");
+    H.n_imu = n_imu;
+    H.n_prior = n_prior;
+    if (n_imu > 0 || n_prior > 0) {
         int32_t *ii = h->imu_idx.h + (size_t)slot * h->Ncap * 2;
-        for (int n = 0; n < H.n_imu; ++n) { ii[2 * n] = w->imu_frame_i[n]; ii[2 * n + 1] = w->imu_frame_j[n]; }
-        memcpy(h->imu_data.h + (size_t)slot * h->Ncap * kImuStride, w->imu_data, sizeof(double) * H.n_imu * kImuStride);
-        const size_t dcap = 15 * (size_t)h->Ncap, d = 15 * (size_t)H.n_prior;
-        for (int n = 0; n < H.n_prior; ++n) h->prior_frames.h[(size_t)slot * h->Ncap + n] = w->prior_frames[n];
+        for (int n = 0; n < n_imu; ++n) { ii[2 * n] = w->imu_frame_i[n]; ii[2 * n + 1] = w->imu_frame_j[n]; }
+        if (n_imu > 0) memcpy(h->imu_data.h + (size_t)slot * h->Ncap * kImuStride, w->imu_data, sizeof(double) * n_imu * kImuStride);
+        const size_t dcap = 15 * (size_t)h->Ncap, d = 15 * (size_t)n_prior;
+        for (int n = 0; n < n_prior; ++n) h->prior_frames.h[(size_t)slot * h->Ncap + n] = w->prior_frames[n];
         if (d > 0) {
             memcpy(h->prior_S.h + (size_t)slot * dcap * dcap, w->prior_S, sizeof(double) * d * d);   // dense d x d, row-major
             memcpy(h->prior_e.h + (size_t)slot * dcap, w->prior_e, sizeof(double) * d);
-            memcpy(h->prior_x0.h + (size_t)slot * h->Ncap * kFrameStride, w->prior_state0, sizeof(double) * H.n_prior * kFrameStride);
+            memcpy(h->prior_x0.h + (size_t)slot * h->Ncap * kFrameStride, w->prior_state0, sizeof(double) * n_prior * kFrameStride);
         }
     }
     // planes
@@ -276,15 +310,12 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
     if (H.n_ptracks > 0) {
         const int O = w->pt_obs_begin[H.n_ptracks];
         TRY(ensure_planes(h, H.n_ptracks, O));
-        if (H.n_planes > h->Pcap) return fail(h, PVIO_B200_EINVAL, "too many planes");
         memcpy(h->plane_param.h + (size_t)slot * h->Pcap * 4, w->plane_param, sizeof(double) * 4 * H.n_planes);
         memcpy(h->pt_plane.h + (size_t)slot * h->Tcap, w->pt_plane, sizeof(int32_t) * H.n_ptracks);
         memcpy(h->pt_begin.h + (size_t)slot * (h->Tcap + 1), w->pt_obs_begin, sizeof(int32_t) * (H.n_ptracks + 1));
         memcpy(h->pt_frame.h + (size_t)slot * h->Ocap, w->pt_obs_frame, sizeof(int32_t) * O);
         float *z = h->pt_z.h + (size_t)slot * h->Ocap * 2;
         for (int i = 0; i < 2 * O; ++i) z[i] = (float)w->pt_obs_z[i];
-        for (int t = 0; t < H.n_ptracks; ++t)
-            if (w->pt_obs_begin[t + 1] - w->pt_obs_begin[t] > kMaxFrames) return fail(h, PVIO_B200_EINVAL, "plane track too long");
     }
     return 0;
 }
@@ -296,7 +327,8 @@ static int h2d(Handle *h, DevBuf<T> &b, size_t per, int w0, int n, cudaStream_t 
     return 0;
 }
 
-// Host -> device copy of windows [w0, w0 + n) on stream st
+// Host -> device copy of windows [w0, w0 + n) on stream st, then the device-side preparation that is constant
+// across the iterations of a solve: the frame-major table and Lambda = S^T S of the priors.
 static int upload_range(Handle *h, int w0, int n, cudaStream_t st) {
     if (n < 1 || w0 < 0 || w0 + n > h->W) return fail(h, PVIO_B200_EINVAL, "bad window range");
     const size_t N = h->Ncap;
@@ -328,6 +360,12 @@ static int upload_range(Handle *h, int w0, int n, cudaStream_t st) {
         TRY(h2d(h, h->pt_frame, h->Ocap, w0, n, st));
         TRY(h2d(h, h->pt_z, (size_t)h->Ocap * 2, w0, n, st));
     }
+    FobsArgs fa;
+    fa.hdr = h->hdr.d; fa.obs = h->obs.d; fa.lms = h->lms.d; fa.fobs = h->fobs.d; fa.fobs_lm = h->fobs_lm.d; fa.seg = h->seg.d;
+    fa.Mcap = h->Mcap; fa.Kcap = h->Kcap; fa.w0 = w0;
+    fobs_build_kernel<<<n, 256, 0, st>>>(fa);
+    ++h->launches;
+    CK(h, cudaGetLastError());
     return 0;
 }
 
@@ -344,102 +382,146 @@ int pack_and_upload(Handle *h, const pvio_b200_window *w, const pvio_b200_state 
 
 // ------------------------------------------------------------------------ launches
 struct StepCfg {
-    double mu = -1.0;          // < 0: per-window ctrl.mu
+    double mu = -1.0;              // < 0: per-window WinCtrl::mu
     double beta = 1.0;             // truncated Gauss-Newton step: step = beta * dx_gn
-    double step_a = 0.0;           // dogleg: step = step_b * dx_gn - step_a * v  (step_b defaults to beta)
-    double step_b = -1.0;
-    int update_grid = 0;           // > 0: CTAs per window of the update sweep
-    int apply = 0;
+    int apply = 0;                 // plain GN step: the candidate becomes the state
     int compute_scale = 1;
     int alias_bias = 0;
     int dump = 0;
-    bool skip_linearize = false;   // reuse the previous linearisation (trust-region retry)
+    int loop = 0;                  // kernels obey the per-window trust-region flags
     int w0 = 0;                    // first window (sub-batch pipelining)
     cudaStream_t stream = nullptr; // nullptr: the handle's stream
 };
 
-static int lin_grid_x(Handle *h, int n) {
-    // one CTA per window once the batch fills the machine; otherwise split a window's chunks
-    const int target = 2 * h->sm_count;
-    int gx = std::max(1, target / std::max(n, 1));
-    return std::min(gx, n * 2 < h->sm_count ? 32 : 16);
+// what the windows [w0, w0 + n) need from the launch: worst case over the batch
+struct BatchShape {
+    int N = 1, M = 1, nfree = 1, D = 0;
+    bool inertial = false, planes = false;
+    size_t solve_smem_full = 0, solve_smem_lean = 0;
+};
+
+static size_t solve_smem_one(const WinHdr &H, bool lean) {
+    size_t D = (H.use_inertial ? 15 : 6) * (size_t)H.N;
+    if (lean) {                       // the lean kernel drops constant frames from the system
+        const int nfree = H.N - __builtin_popcount((unsigned)H.fixed_mask & ((1u << H.N) - 1u));
+        if (nfree > 0) D = 6 * (size_t)nfree;
+    }
+    const size_t nb = (D + 3) / 4, Dp = nb * 4;
+    const size_t np_ = (size_t)H.N * (H.N + 1) / 2;
+    size_t scr = lean ? Dp + 10 * 36 + 36 : std::max<size_t>(Dp, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);
+    if (H.use_inertial) scr = std::max<size_t>(scr, 2 * (4 * 450 + 64));
+    if (H.n_prior > 0) scr = std::max<size_t>(scr, 3 * 15 * (size_t)H.n_prior + 9 * (size_t)H.n_prior);
+    return sizeof(double) * ((nb + 1) * (nb + 2) / 2 * 16 + 4 * Dp + nb * 16 + (size_t)H.N * 36 + scr);
 }
 
-static size_t solve_smem(Handle *h, int w0, int n, bool lean) {
-    // worst case over the windows of the launch
-    size_t best = 0;
+static BatchShape batch_shape(Handle *h, int w0, int n, bool by_capacity) {
+    BatchShape b;
     for (int i = w0; i < w0 + n; ++i) {
         const WinHdr &H = h->hdr.h[i];
-        size_t D = (H.use_inertial ? 15 : 6) * (size_t)H.N;
-        if (lean) {                       // the lean kernel drops constant frames from the system
-            const int nfree = H.N - __builtin_popcount((unsigned)H.fixed_mask & ((1u << H.N) - 1u));
-            if (nfree > 0) D = 6 * (size_t)nfree;
-        }
-        const size_t nb = (D + 3) / 4, Dp = nb * 4;
-        const size_t np_ = (size_t)H.N * (H.N + 1) / 2;
-        size_t scr = lean ? Dp + 10 * 36 + 36 : std::max<size_t>(Dp, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);
-        if (H.use_inertial) scr = std::max<size_t>(scr, 2 * (4 * 450 + 64));
-        if (H.n_prior > 0) scr = std::max<size_t>(scr, 3 * 15 * (size_t)H.n_prior + 9 * (size_t)H.n_prior);
-        const size_t bytes = sizeof(double) * ((nb + 1) * (nb + 2) / 2 * 16 + 4 * Dp + nb * 16 + (size_t)H.N * 36 + scr);
-        best = std::max(best, bytes);
+        b.N = std::max(b.N, H.N); b.M = std::max(b.M, H.M);
+        const unsigned allm = (1u << H.N) - 1u, freem = ~(unsigned)H.fixed_mask & allm;
+        b.nfree = std::max(b.nfree, __builtin_popcount(freem));
+        b.inertial |= H.use_inertial != 0;
+        b.planes |= H.n_ptracks > 0;
+        b.solve_smem_full = std::max(b.solve_smem_full, solve_smem_one(H, false));
+        b.solve_smem_lean = std::max(b.solve_smem_lean, solve_smem_one(H, true));
     }
-    return best;
+    if (by_capacity) {                 // graph-cached launches: shapes depend on the frame count (part of the graph key) only
+        b.M = h->Mcap; b.nfree = b.N;
+        WinHdr H;
+        memset(&H, 0, sizeof(H));
+        H.N = b.N; H.use_inertial = b.inertial ? 1 : 0; H.n_prior = b.inertial ? b.N : 0;
+        b.solve_smem_full = solve_smem_one(H, false);
+    }
+    return b;
 }
 
-static int run_linearize(Handle *h, int n, const StepCfg &c) {
-    const int gx = lin_grid_x(h, n);
-    cudaStream_t st = c.stream ? c.stream : h->stream;
-    const size_t npc = (size_t)h->Ncap * (h->Ncap + 1) / 2;
-    if (gx > 1) CK(h, cudaMemsetAsync(h->Hred.d, 0, sizeof(double) * h->Hred.n, st));
-    (void)npc;
-    LinArgs a;
-    a.hdr = h->hdr.d; a.cst = h->cst.d; a.obs = h->obs.d; a.lms = h->lms.d; a.rho = h->rho.d; a.frames = h->frames.d;
-    a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d; a.hs_out = h->hs.d; a.hs_stride = h->hs_stride;
+static PipeArgs make_pipe_args(Handle *h, const StepCfg &c) {
+    PipeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.hdr = h->hdr.d; a.cst = h->cst.d; a.fobs = h->fobs.d; a.fobs_lm = h->fobs_lm.d; a.seg = h->seg.d; a.lms = h->lms.d;
+    a.rho = h->rho.d; a.frames = h->frames.d; a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d;
+    a.jr = h->jr.d; a.hs = h->hs.d; a.lm_w = h->lm_w.d; a.lm_msk = h->lm_msk.d;
     a.Hred = h->Hred.d; a.Hdd = h->Hdd.d; a.gdir = h->gdir.d; a.gred = h->gred.d; a.cost_vis = h->cost_vis.d;
     a.Ncap = h->Ncap; a.Mcap = h->Mcap; a.Kcap = h->Kcap;
-    a.compute_scale = c.compute_scale; a.victim_only = 0; a.mu_override = c.mu; a.w0 = c.w0;
-    const int slot = (h->kev_count % 512) * 2;
+    a.compute_scale = c.compute_scale; a.victim_only = 0; a.mu_override = c.mu; a.w0 = c.w0; a.loop = c.loop;
+    return a;
+}
+
+// CTAs per window of the sweeps: one once the batch fills the machine, otherwise a window is cut into row ranges
+static int sweep_grid_x(Handle *h, int n) { return n * 2 < h->sm_count ? 16 : 1; }
+
+// CTA shapes of the sweeps (fp32 pipeline): warps per CTA and resident CTAs per SM the register allocation targets.
+// Compile-time constants, chosen by measurement (profiles/r02*.md); -D overrides exist for tuning builds only.
+#ifndef PVIO_LIN_BLOCKS
+#define PVIO_LIN_BLOCKS 4
+#endif
+#ifndef PVIO_SCHUR_BLOCKS
+#define PVIO_SCHUR_BLOCKS 4
+#endif
+#ifndef PVIO_UPD_BLOCKS
+#define PVIO_UPD_BLOCKS 4
+#endif
+constexpr int kLinWarps = 4, kLinBlocks = PVIO_LIN_BLOCKS;
+constexpr int kSchurThreads = 128, kSchurBlocks = PVIO_SCHUR_BLOCKS;
+constexpr int kUpdWarps = 4, kUpdBlocks = PVIO_UPD_BLOCKS;
+
+template <typename real>
+static size_t schur_launch_smem(int N, int nfree) { return schur_smem_bytes<real>(N, kSchurThreads, nfree); }
+
+#define LAUNCH_CK(h, what)                                                                        \
+    do {                                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                     \
+        if (e__ != cudaSuccess) return fail((h), PVIO_B200_ECUDA, "launch of " what, e__);        \
+    } while (0)
+
+// linearise + Schur stage of windows [w0, w0 + n)
+static int run_linearize(Handle *h, int n, const StepCfg &c, const BatchShape &b, bool loss = true, bool victim_only = false) {
+    cudaStream_t st = c.stream ? c.stream : h->stream;
+    const int gx = sweep_grid_x(h, n);
+    PipeArgs a = make_pipe_args(h, c);
+    a.victim_only = victim_only ? 1 : 0;
+    if (gx > 1) CK(h, cudaMemsetAsync(h->Hred.d, 0, sizeof(double) * h->Hred.n, st));    // several CTAs accumulate one window's system with atomics
     if (h->kev.empty()) {
-        h->kev.resize(1024);
+        h->kev.resize(3 * 256);
         for (auto &e : h->kev) CK(h, cudaEventCreate(&e));
     }
-    if (!h->capturing) CK(h, cudaEventRecord(h->kev[slot], st));
-    // few windows: the group-per-landmark kernel exposes more parallelism per window (latency);
-    // many windows: the thread-per-landmark kernel issues ~2x fewer instructions (throughput)
-    // (the group kernel owns at most 256 Phase-B tiles: N <= 15)
-    // PVIO_B200_TC=1 and windows of <= 10 frames: the Schur SYRK runs on the tensor cores (tcgen05, ba_lin3.cuh).
-    // Opt-in: parity-green but 10 % slower than the CUDA-core SYRK on B200 (profiles/r01c_lin_tc.md)
-    const bool tc_ok = h->max_slot_N <= kTcMaxFrames && h->use_tc;
-    if (n * 2 < h->sm_count && h->Ncap * (h->Ncap + 1) <= kLinThreads) lin_schur_kernel<true><<<dim3(gx, n), kLinThreads, lin_smem_bytes(), st>>>(a);
-    else if (tc_ok && h->tc_gs == 4) lin_tc_kernel<true, 4><<<dim3(gx, n), kLinThreads, lin3_smem_bytes(std::min(h->Ncap, kTcMaxFrames)), st>>>(a);
-    else if (tc_ok && h->tc_gs == 2) lin_tc_kernel<true, 2><<<dim3(gx, n), kLinThreads, lin3_smem_bytes(std::min(h->Ncap, kTcMaxFrames)), st>>>(a);
-    else if (tc_ok) lin_tc_kernel<true, 1><<<dim3(gx, n), kLinThreads, lin3_smem_bytes(std::min(h->Ncap, kTcMaxFrames)), st>>>(a);
-    else if (h->split_schur && gx == 1) {
-        // split stage (default for whole-window CTAs): Phase A (records + direct blocks, ba_lin4.cuh), then the Schur
-        // sum as its own kernel at ~3x the occupancy (ba_schur.cuh): 0.83 ms instead of 0.90 ms per 4096 cfg2 windows
-        switch (h->split_shape) {
-            case 1: lin_a_kernel<true, 6, 3><<<dim3(1, n), 192, lin4_smem_bytes<6>(h->Ncap), st>>>(a); break;
-            case 2: lin_a_kernel<true, 4, 4><<<dim3(1, n), 128, lin4_smem_bytes<4>(h->Ncap), st>>>(a); break;
-            case 3: lin_a_kernel<true, 4, 5><<<dim3(1, n), 128, lin4_smem_bytes<4>(h->Ncap), st>>>(a); break;
-            default: lin_a_kernel<true, 8, 2><<<dim3(1, n), 256, lin4_smem_bytes<8>(h->Ncap), st>>>(a); break;
-        }
-        // CTA = the tiles of the free-frame pairs x 4 k-split lanes (x 2 / x 1 when that exceeds 256 threads)
-        const int nfree = std::max(1, h->max_slot_free), ntask = nfree * (nfree + 1) / 2;
-        const int ks = ntask * 4 <= kSchurThreads ? 4 : (ntask * 2 <= kSchurThreads ? 2 : 1);
-        const int nthr = std::min(kSchurThreads, ((ntask * ks + 31) / 32) * 32);
-        if (h->tc_mode == 2 && h->max_slot_N <= kTcMaxFrames) schur_tc_kernel<<<n, 128, schur_tc_smem_bytes(std::min(h->Ncap, kTcMaxFrames)), st>>>(a);
-        else if (nthr <= 160) schur_kernel<160, 4><<<n, nthr, schur_smem_bytes(h->Ncap), st>>>(a);
-        else schur_kernel<256, 2><<<n, nthr, schur_smem_bytes(h->Ncap), st>>>(a);
-        ++h->launches;
+    const int slot = (h->kev_count % 256) * 3;
+    const bool timed = !h->capturing;
+    if (timed) CK(h, cudaEventRecord(h->kev[slot], st));
+    const int Mp = (b.M + 31) & ~31;
+    const int sgx = std::min(gx, std::max(1, (b.M + kSlab - 1) / kSlab));
+    const bool dbl = h->hs_double;
+    if (!dbl) {
+        if (!loss) return fail(h, PVIO_B200_EINVAL, "the loss-free sweep runs in fp64");
+        lin_obs_kernel<true, float, kLinWarps, kLinBlocks><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<float>(b.N, Mp), st>>>(a);
+        LAUNCH_CK(h, "lin_obs_kernel<float>");
+        if (gx > 1) { lm_finish_kernel<float><<<dim3((b.M + 127) / 128, n), 128, 0, st>>>(a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<float>"); }
+        if (timed) CK(h, cudaEventRecord(h->kev[slot + 1], st));
+        schur_kernel<float, kSchurThreads, kSchurBlocks><<<dim3(sgx, n), kSchurThreads, schur_launch_smem<float>(b.N, b.nfree), st>>>(a);
+        LAUNCH_CK(h, "schur_kernel<float>");
+    } else {
+        if (loss) lin_obs_kernel<true, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp), st>>>(a);
+        else lin_obs_kernel<false, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp), st>>>(a);
+        LAUNCH_CK(h, "lin_obs_kernel<double>");
+        if (gx > 1) { lm_finish_kernel<double><<<dim3((b.M + 127) / 128, n), 128, 0, st>>>(a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<double>"); }
+        if (timed) CK(h, cudaEventRecord(h->kev[slot + 1], st));
+        schur_kernel<double, kSchurThreads, 1><<<dim3(sgx, n), kSchurThreads, schur_launch_smem<double>(b.N, b.nfree), st>>>(a);
+        LAUNCH_CK(h, "schur_kernel<double>");
     }
-    else lin_tpl_kernel<true><<<dim3(gx, n), kLinThreads, lin2_smem_bytes(h->Ncap), st>>>(a);
-    if (!h->capturing) { CK(h, cudaEventRecord(h->kev[slot + 1], st)); ++h->kev_count; }
-    ++h->launches;
-    CK(h, cudaGetLastError());
+    if (timed) { CK(h, cudaEventRecord(h->kev[slot + 2], st)); ++h->kev_count; }
+    h->launches += 2;
     return 0;
 }
 
-static int run_solve(Handle *h, int n, const StepCfg &c) {
+int run_marg_vision(Handle *h) {
+    StepCfg c;
+    c.mu = 0.0; c.compute_scale = 1;
+    const BatchShape b = batch_shape(h, 0, 1, false);
+    return run_linearize(h, 1, c, b, false, true);
+}
+
+static int run_solve(Handle *h, int n, const StepCfg &c, const BatchShape &b) {
     SolveArgs a;
     memset(&a, 0, sizeof(a));
     a.hdr = h->hdr.d; a.cst = h->cst.d; a.frames = h->frames.d; a.ctrl = h->ctrl.d;
@@ -451,36 +533,17 @@ static int run_solve(Handle *h, int n, const StepCfg &c) {
     a.pt_z = h->pt_z.d; a.Pcap = h->Pcap; a.Tcap = h->Tcap; a.Ocap = h->Ocap;
     a.pose_scale = h->pose_scale.d; a.dx_pose = h->dx_pose.d; a.v_pose = h->v_pose.d;
     a.Hfull = c.dump ? h->Hfull.d : nullptr; a.gfull = c.dump ? h->gfull.d : nullptr;
-    a.Ncap = h->Ncap; a.compute_scale = c.compute_scale; a.mu_override = c.mu; a.w0 = c.w0;
-    a.dbg = nullptr;
-    if (!h->capturing && getenv("PVIO_B200_SOLVE_STAMPS")) {       // profiling aid: clock64 stamps of the solve kernel's phases
-        static long long *dbg = nullptr;
-        long long hst[16];
-        if (!dbg) { cudaMalloc(&dbg, 16 * sizeof(long long)); cudaMemset(dbg, 0, 16 * sizeof(long long)); }
-        else {
-            cudaStreamSynchronize(h->stream);
-            cudaMemcpy(hst, dbg, sizeof(hst), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "solve stamps (clk):");
-            for (int i = 1; i < 6; ++i) fprintf(stderr, " %lld", hst[i] - hst[i - 1]);
-            fprintf(stderr, "\n");
-        }
-        a.dbg = dbg;
-    }
+    a.Ncap = h->Ncap; a.compute_scale = c.compute_scale; a.mu_override = c.mu; a.w0 = c.w0; a.loop = c.loop;
     cudaStream_t st = c.stream ? c.stream : h->stream;
     // visual-only batches: the lean kernel (no IMU / prior / plane code, no full staging), a narrow CTA
     // per window so that many windows are resident per SM; otherwise the full kernel with a wide CTA
-    bool visual = n >= 64;
-    for (int i = c.w0; i < c.w0 + n && visual; ++i) {
-        const WinHdr &H = h->hdr.h[i];
-        if (H.use_inertial || H.n_ptracks > 0) visual = false;
-    }
-    size_t smem = solve_smem(h, c.w0, n, visual);
-    if (visual && smem > 48 * 1024) { visual = false; smem = solve_smem(h, c.w0, n, false); }
+    const bool visual = n >= 64 && !b.inertial && !b.planes && b.solve_smem_lean <= 48 * 1024;
+    const size_t smem = visual ? b.solve_smem_lean : b.solve_smem_full;
     if (smem > 220 * 1024) return fail(h, PVIO_B200_EINVAL, "reduced system too large for shared memory");
     if (visual) solve_kernel_visual<<<n, 64, smem, st>>>(a);
     else solve_kernel<<<n, 256, smem, st>>>(a);
     ++h->launches;
-    CK(h, cudaGetLastError());
+    LAUNCH_CK(h, "solve_kernel");
     return 0;
 }
 
@@ -493,82 +556,107 @@ static CostArgs make_cost_args(Handle *h, const StepCfg &c) {
     k.plane_param = h->plane_param.d; k.pt_plane = h->pt_plane.d; k.pt_begin = h->pt_begin.d; k.pt_frame = h->pt_frame.d;
     k.pt_z = h->pt_z.d; k.Pcap = h->Pcap; k.Tcap = h->Tcap; k.Ocap = h->Ocap; k.Ncap = h->Ncap; k.out = h->aux_cost.d;
     k.w0 = c.w0;
+    k.ctrl = h->ctrl.d; k.acc = h->acc.d; k.frames_state = h->frames.d; k.rho_state = h->rho.d; k.rho_cand = h->rho_cand.d;
+    k.Mcap = h->Mcap; k.loop = c.loop; k.apply = c.apply; k.beta = c.beta;
     return k;
 }
 
-// |J v|^2 for the Cauchy point of the dogleg step (acc slots 9 and 10); single window path
-static int run_jv(Handle *h, const StepCfg &c) {
-    cudaStream_t st = c.stream ? c.stream : h->stream;
-    CK(h, cudaMemsetAsync(h->acc.d + 9, 0, sizeof(double) * 2, st));
+static UpdArgs make_upd_args(Handle *h, const StepCfg &c) {
     UpdArgs u;
     memset(&u, 0, sizeof(u));
     u.hdr = h->hdr.d; u.cst = h->cst.d; u.obs = h->obs.d; u.lms = h->lms.d; u.rho = h->rho.d; u.frames = h->frames.d;
-    u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.hs = h->hs.d; u.hs_stride = h->hs_stride; u.dx_pose = h->dx_pose.d; u.acc = h->acc.d;
-    u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.w0 = 0; u.v_pose = h->v_pose.d;
-    jv_vision_kernel<true><<<dim3(16, 1), kLinThreads, 0, st>>>(u);
-    JvAuxArgs ja;
-    ja.c = make_cost_args(h, c);
-    ja.v_pose = h->v_pose.d; ja.acc = h->acc.d;
-    jv_aux_kernel<<<1, 64, sizeof(double) * 15 * kMaxFrames, st>>>(ja);
-    h->launches += 2;
-    CK(h, cudaGetLastError());
+    u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.hs = h->hs.d;
+    u.fobs = h->fobs.d; u.fobs_lm = h->fobs_lm.d; u.seg = h->seg.d; u.dx_pose = h->dx_pose.d;
+    u.rho_cand = h->rho_cand.d; u.frames_cand = h->frames_cand.d; u.dx_lm = h->dx_lm.d; u.lm_v = h->lm_v.d; u.acc = h->acc.d;
+    u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.w0 = c.w0;
+    u.step_a = 0.0; u.step_b = c.beta; u.v_pose = h->v_pose.d; u.loop = c.loop;
+    return u;
+}
+
+template <int kMode>
+static int launch_update(Handle *h, int n, const StepCfg &c, const BatchShape &b, int gx) {
+    cudaStream_t st = c.stream ? c.stream : h->stream;
+    const UpdArgs u = make_upd_args(h, c);
+    const int Mp = (b.M + 31) & ~31;
+    constexpr int kW = kMode == 1 ? 8 : kUpdWarps;
+    constexpr int kB = kMode == 1 ? 2 : 4, kBf = kMode == 1 ? 2 : kUpdBlocks;
+    if (!h->hs_double) update_obs_kernel<true, float, kW, kBf, kMode><<<dim3(gx, n), kW * 32, upd_smem_bytes<float>(b.N, Mp), st>>>(u);
+    else update_obs_kernel<true, double, kW, kB, kMode><<<dim3(gx, n), kW * 32, upd_smem_bytes<double>(b.N, Mp), st>>>(u);
+    ++h->launches;
+    LAUNCH_CK(h, "update_obs_kernel");
     return 0;
 }
 
-static int run_update(Handle *h, int n, const StepCfg &c) {
+static int launch_aux_cost(Handle *h, int n, const StepCfg &c) {
     cudaStream_t st = c.stream ? c.stream : h->stream;
-    CK(h, cudaMemsetAsync(h->acc.d + (size_t)kAcc * c.w0, 0, sizeof(double) * kAcc * n, st));
-    UpdArgs u;
-    u.hdr = h->hdr.d; u.cst = h->cst.d; u.obs = h->obs.d; u.lms = h->lms.d; u.rho = h->rho.d; u.frames = h->frames.d;
-    u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.hs = h->hs.d; u.hs_stride = h->hs_stride; u.dx_pose = h->dx_pose.d;
-    u.rho_cand = h->rho_cand.d; u.frames_cand = h->frames_cand.d; u.dx_lm = h->dx_lm.d; u.acc = h->acc.d;
-    u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.w0 = c.w0;
-    u.step_a = c.step_a; u.step_b = c.step_b >= 0.0 ? c.step_b : c.beta; u.v_pose = h->v_pose.d;
-    const int gx = lin_grid_x(h, n);
-    // few windows: one chunk per CTA-warp so that a single window spreads over 16 CTAs
-    const int ugx = n * 2 < h->sm_count ? 16 : 1;
-    (void)gx;
-    update_tpl_kernel<true><<<dim3(ugx, n), kLinThreads, 0, st>>>(u);
-    ++h->launches;
-    CostArgs k = make_cost_args(h, c);
+    const CostArgs k = make_cost_args(h, c);
     aux_cost_kernel<<<n, 64, sizeof(double) * 15 * kMaxFrames, st>>>(k);
     ++h->launches;
-    finalize_kernel<<<n, 128, 0, st>>>(h->ctrl.d, h->acc.d, h->aux_cost.d, c.apply, h->frames.d, h->frames_cand.d,
-                                      h->rho.d, h->rho_cand.d, h->hdr.d, h->Ncap, h->Mcap, c.beta, c.w0);
-    ++h->launches;
-    CK(h, cudaGetLastError());
+    LAUNCH_CK(h, "aux_cost_kernel");
     return 0;
 }
 
-static int run_step_raw(Handle *h, int n, const StepCfg &c, int kind) {
-    if (!c.skip_linearize) {
-        TRY(run_linearize(h, n, c));
-        TRY(run_solve(h, n, c));
+// One plain Gauss-Newton iteration (fixed mu, step beta * dx_gn): linearise, Schur, solve, back-substitution +
+// candidate in one sweep, non-vision cost + optional acceptance.  5 launches.
+static int run_gn_step(Handle *h, int n, const StepCfg &c, const BatchShape &b) {
+    cudaStream_t st = c.stream ? c.stream : h->stream;
+    TRY(run_linearize(h, n, c, b));
+    TRY(run_solve(h, n, c, b));
+    CK(h, cudaMemsetAsync(h->acc.d + (size_t)kAcc * c.w0, 0, sizeof(double) * kAcc * n, st));
+    TRY(launch_update<0>(h, n, c, b, sweep_grid_x(h, n)));
+    TRY(launch_aux_cost(h, n, c));
+    return 0;
+}
+
+// One iteration of the device-side trust-region loop (ba_tr.cuh): 8 launches, no host decision.
+static int iteration_body(Handle *h, int n, const StepCfg &c, const BatchShape &b) {
+    cudaStream_t st = c.stream ? c.stream : h->stream;
+    TRY(run_linearize(h, n, c, b));
+    TRY(run_solve(h, n, c, b));
+    TRY(launch_update<1>(h, n, c, b, 1));
+    {
+        const UpdArgs u = make_upd_args(h, c);
+        jv_vision_kernel<true><<<dim3(sweep_grid_x(h, n), n), kLinThreads, 0, st>>>(u);
+        LAUNCH_CK(h, "jv_vision_kernel");
+        JvAuxArgs ja;
+        ja.c = make_cost_args(h, c);
+        ja.v_pose = h->v_pose.d; ja.acc = h->acc.d;
+        jv_aux_kernel<<<n, 64, sizeof(double) * 15 * kMaxFrames, st>>>(ja);
+        LAUNCH_CK(h, "jv_aux_kernel");
+        h->launches += 2;
     }
-    if (kind == 0) TRY(run_update(h, n, c));
+    TRY(launch_update<2>(h, n, c, b, sweep_grid_x(h, n)));
+    TRY(launch_aux_cost(h, n, c));
     return 0;
 }
 
-// kind 0: linearise + solve (unless skipped) + update sweep; kind 1: linearise + solve only.
-// Small launches (latency path) are captured once into a CUDA graph and replayed: 6-8 nodes cost one
-// launch instead of 6-8.
-static int run_step(Handle *h, int n, const StepCfg &c, int kind = 0) {
-    const bool graphable = h->use_graphs && n * 2 < h->sm_count && c.w0 == 0 && c.stream == nullptr && !c.dump &&
-                           !getenv("PVIO_B200_SOLVE_STAMPS");
-    if (!graphable) return run_step_raw(h, n, c, kind);
-    const WinHdr &H = h->hdr.h[0];
-    int shape = 0;
-    for (int i = 0; i < n; ++i) shape = shape * 31 + h->hdr.h[i].N * 4 + h->hdr.h[i].use_inertial * 2 + (h->hdr.h[i].n_ptracks > 0);
-    Handle::GraphKey key(n, shape, H.N, kind, c.compute_scale, c.skip_linearize ? 1 : 0, c.apply, c.alias_bias,
-                         (int)(solve_smem(h, 0, n, false) >> 4), c.mu, c.step_a, c.step_b >= 0.0 ? c.step_b : c.beta);
+// The whole trust-region solve of the first n uploaded windows: init + max_iter (+ spare) identical bodies.  For the
+// latency path (few windows) the sequence is captured once into a CUDA graph keyed by (n, max_iter, flags) with
+// capacity-sized launch shapes, and replayed: ONE launch per solve, no device -> host traffic inside.
+static int run_solve_loop(Handle *h, int n, int max_iter, double max_time, double radius0, int alias_bias) {
+    StepCfg c;
+    c.mu = -1.0; c.loop = 1; c.alias_bias = alias_bias; c.compute_scale = 0;
+    const bool graphable = n * 2 < h->sm_count;
+    const BatchShape b = batch_shape(h, 0, n, graphable);
+    const int bodies = max_iter + 2;                 // spare bodies absorb retries of a failed linear solve (mu *= 10)
+    init_ctrl_kernel<<<n, 32, 0, h->stream>>>(h->ctrl.d, 1e-8, radius0, max_iter, max_time, 0);
+    ++h->launches;
+    LAUNCH_CK(h, "init_ctrl_kernel");
+    if (!graphable) {
+        for (int it = 0; it < bodies; ++it) TRY(iteration_body(h, n, c, b));
+        return 0;
+    }
+    const Handle::GraphKey key(1, n, max_iter, (alias_bias ? 1 : 0) | (b.inertial ? 2 : 0) | (b.planes ? 4 : 0) | (h->hs_double ? 8 : 0) | (b.N << 4));
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
+        if (h->graphs.size() >= 16) drop_graphs(h);
         const int64_t l0 = h->launches;
         cudaGraph_t g = nullptr;
         cudaGraphExec_t ge = nullptr;
         CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         h->capturing = true;
-        const int rc = run_step_raw(h, n, c, kind);
+        int rc = 0;
+        for (int i = 0; i < bodies && rc == 0; ++i) rc = iteration_body(h, n, c, b);
         h->capturing = false;
         const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
         if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
@@ -581,6 +669,15 @@ static int run_step(Handle *h, int n, const StepCfg &c, int kind = 0) {
     }
     CK(h, cudaGraphLaunch(it->second.first, h->stream));
     h->launches += it->second.second;
+    return 0;
+}
+
+static int run_postpass(Handle *h, int n, bool want_flags, double *err_acc) {
+    postpass_kernel<<<dim3(n * 2 < h->sm_count ? 8 : 1, n), 256, 0, h->stream>>>(
+        h->hdr.d, h->cst.d, h->obs.d, h->lms.d, h->rho.d, h->frames.d, want_flags ? h->valid.d : nullptr,
+        want_flags ? h->quality.d : nullptr, err_acc, h->Ncap, h->Mcap, h->Kcap, 0);
+    ++h->launches;
+    CK(h, cudaGetLastError());
     return 0;
 }
 
@@ -602,11 +699,39 @@ static int scatter_dx(Handle *h, int w0, int n, double *dx, int64_t dx_stride, d
 }
 
 static int download_dx(Handle *h, int n, double *dx, int64_t dx_stride, double *costs) {
+    if (n < 1 || n > h->W) return fail(h, PVIO_B200_EINVAL, "bad window count");
     CK(h, cudaMemcpyAsync(h->dx_pose.h, h->dx_pose.d, sizeof(double) * h->Ncap * 15 * n, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaMemcpyAsync(h->dx_lm.h, h->dx_lm.d, sizeof(double) * h->Mcap * n, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaMemcpyAsync(h->ctrl.h, h->ctrl.d, sizeof(WinCtrl) * n, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return scatter_dx(h, 0, n, dx, dx_stride, costs);
+}
+
+// device -> host of the solved state + summaries of windows [w0, w0 + n) on stream st (async)
+static int download_state_async(Handle *h, int w0, int n, cudaStream_t st) {
+    const size_t N = h->Ncap;
+    CK(h, cudaMemcpyAsync(h->frames_out.h + (size_t)w0 * N * kFrameStride, h->frames.d + (size_t)w0 * N * kFrameStride,
+                          sizeof(double) * N * kFrameStride * n, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->rho_out.h + (size_t)w0 * h->Mcap, h->rho.d + (size_t)w0 * h->Mcap, sizeof(double) * h->Mcap * n,
+                          cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->ctrl.h + w0, h->ctrl.d + w0, sizeof(WinCtrl) * n, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+static void fill_summary(const WinCtrl &c, pvio_b200_summary *sm) {
+    memset(sm, 0, sizeof(*sm));
+    sm->iterations = c.iteration; sm->accepted_steps = c.accepted; sm->termination = c.termination; sm->usable = c.usable;
+    sm->initial_cost = c.initial_cost; sm->final_cost = c.cost; sm->final_radius = c.radius; sm->final_mu = c.mu;
+}
+
+static void scatter_state(Handle *h, int i, double *frames, double *inv_depth) {
+    const int N = h->slot_N[i], M = h->slot_M[i];
+    if (frames) memcpy(frames, h->frames_out.h + (size_t)i * h->Ncap * kFrameStride, sizeof(double) * N * kFrameStride);
+    if (inv_depth) {
+        const double *r = h->rho_out.h + (size_t)i * h->Mcap;
+        const std::vector<int32_t> &perm = h->perm[i];
+        for (int lp = 0; lp < M; ++lp) inv_depth[perm[lp]] = r[lp];
+    }
 }
 
 }  // namespace pvio
@@ -616,17 +741,20 @@ using namespace pvio;
 // ======================================================================== C ABI
 extern "C" {
 
-const char *pvio_b200_version(void) { return "pvio_b200 0.1 (sm_100a)"; }
+const char *pvio_b200_version(void) { return "pvio_b200 0.2 (sm_100a)"; }
 
 int pvio_b200_create(int device, int max_windows, int max_frames, int max_landmarks, int max_obs,
                      pvio_b200_handle *out) {
     if (!out) return PVIO_B200_EINVAL;
     *out = nullptr;
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return PVIO_B200_ENODEV;
-    if (max_windows < 1 || max_frames < 1 || max_frames > kMaxFrames || max_landmarks < 1 || max_obs < 1) return PVIO_B200_EINVAL;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev || device < 0) return PVIO_B200_ENODEV;
+    if (max_windows < 1 || max_frames < 1 || max_frames > kMaxFrames || max_landmarks < 1 || max_landmarks > 65534 || max_obs < 1)
+        return PVIO_B200_EINVAL;
     Handle *h = new Handle();
-    h->device = device; h->W = max_windows; h->Ncap = max_frames; h->Mcap = max_landmarks; h->Kcap = max_obs;
+    h->device = device; h->W = max_windows; h->Ncap = max_frames;
+    h->Mcap = (max_landmarks + 3) & ~3;                      // the Schur kernel's bulk copies move 16-byte granules (4 masks)
+    h->Kcap = max_obs;
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return PVIO_B200_ENODEV; }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
@@ -634,18 +762,23 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     *out = reinterpret_cast<pvio_b200_handle>(h);
     CK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(h, cudaEventCreate(&h->ev0)); CK(h, cudaEventCreate(&h->ev1));
-    CK(h, cudaEventCreate(&h->evk0)); CK(h, cudaEventCreate(&h->evk1));
     const size_t W = h->W, N = h->Ncap, M = h->Mcap, K = h->Kcap, npc = N * (N + 1) / 2;
     TRY(alloc(h, h->hdr, W, true)); TRY(alloc(h, h->cst, W, true));
     TRY(alloc(h, h->obs, W * K, true)); TRY(alloc(h, h->lms, W * M, true));
+    TRY(alloc(h, h->fobs, W * K, false)); TRY(alloc(h, h->fobs_lm, W * K, false)); TRY(alloc(h, h->seg, W * kSegTab, false));
     TRY(alloc(h, h->rho, W * M, true)); TRY(alloc(h, h->frames, W * N * kFrameStride, true));
     TRY(alloc(h, h->ctrl, W, true));
     TRY(alloc(h, h->rho_cand, W * M, false)); TRY(alloc(h, h->frames_cand, W * N * kFrameStride, false));
     TRY(alloc(h, h->lm_scale, W * M, false)); TRY(alloc(h, h->lm_aux, W * M, false));
-    h->hs_stride = (size_t)(M / 32 + N + 1) * 32 * hs_rec(N);
-    TRY(alloc(h, h->hs, W * h->hs_stride, false));
-    TRY(alloc(h, h->dx_lm, W * M, true)); TRY(alloc(h, h->dx_pose, W * N * 15, true));
+    TRY(alloc(h, h->hs, W * N * M * 6 * sizeof(float), false)); TRY(alloc(h, h->jr, W * N * M * 2 * sizeof(float), false));
+    TRY(alloc(h, h->lm_w, W * M * 2 * sizeof(float), false)); TRY(alloc(h, h->lm_msk, W * M, false));
+    {   // landing area of downloaded states: host only
+        CK(h, cudaMallocHost(&h->frames_out.h, sizeof(double) * W * N * kFrameStride));
+        CK(h, cudaMallocHost(&h->rho_out.h, sizeof(double) * W * M));
+    }
+    TRY(alloc(h, h->dx_lm, W * M, true)); TRY(alloc(h, h->lm_v, W * M, false)); TRY(alloc(h, h->dx_pose, W * N * 15, true));
     TRY(alloc(h, h->pose_scale, W * N * 15, false)); TRY(alloc(h, h->v_pose, W * N * 15, false));
+    TRY(alloc(h, h->valid, W * M, true)); TRY(alloc(h, h->quality, W * M, true));
     {   // the reduced-system outputs of the linearise kernel live in ONE allocation so that the
         // multi-CTA-per-window mode (atomic accumulation) needs a single memset per launch
         const size_t n_sys = W * (npc * 36 + N * 36 + N * 6 + N * 6 + 1);
@@ -654,31 +787,28 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
         h->gdir.d = h->Hdd.d + W * N * 36; h->gdir.n = 0;
         h->gred.d = h->gdir.d + W * N * 6; h->gred.n = 0;
         h->cost_vis.d = h->gred.d + W * N * 6; h->cost_vis.n = 0;
-    } TRY(alloc(h, h->acc, W * kAcc, true)); TRY(alloc(h, h->aux_cost, W, false));
+    }
+    TRY(alloc(h, h->acc, W * kAcc, true)); TRY(alloc(h, h->aux_cost, W, false));
     TRY(alloc(h, h->Hfull, (15 * N) * (15 * N), true)); TRY(alloc(h, h->gfull, 15 * N, true));
-    // unallocated optional buffers still need valid (dummy) device pointers? kernels never touch them
     h->perm.resize(W); h->perm_identity.assign(W, 1); h->slot_M.assign(W, 0); h->slot_N.assign(W, 0); h->slot_K.assign(W, 0);
-    CK(h, cudaFuncSetAttribute(lin_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem_bytes()));
-    CK(h, cudaFuncSetAttribute(lin_tpl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin2_smem_bytes(kMaxFrames)));
-    CK(h, cudaFuncSetAttribute(lin_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin3_smem_bytes(kTcMaxFrames)));
-    CK(h, cudaFuncSetAttribute(lin_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin3_smem_bytes(kTcMaxFrames)));
-    CK(h, cudaFuncSetAttribute(lin_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin3_smem_bytes(kTcMaxFrames)));
-    { const char *e = getenv("PVIO_B200_TC_GS"); h->tc_gs = e ? atoi(e) : 2; }
-    { const char *e = getenv("PVIO_B200_TC"); h->use_tc = e && e[0] == '1'; h->tc_mode = e ? atoi(e) : 0; }
-    CK(h, cudaFuncSetAttribute(schur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_tc_smem_bytes(kTcMaxFrames)));
-    CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<8>(kMaxFrames)));
-    CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<6>(kMaxFrames)));
-    CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<4>(kMaxFrames)));
-    CK(h, cudaFuncSetAttribute(lin_a_kernel<true, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin4_smem_bytes<4>(kMaxFrames)));
-    { const char *e = getenv("PVIO_B200_SPLIT_SHAPE"); h->split_shape = e ? atoi(e) : 3; }    // 4 warps x 5 CTAs per SM (96 registers) measured best
-    CK(h, cudaFuncSetAttribute(schur_kernel<160, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem_bytes(kMaxFrames)));
-    CK(h, cudaFuncSetAttribute(schur_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem_bytes(kMaxFrames)));
-    { const char *e = getenv("PVIO_B200_SPLIT"); h->split_schur = !(e && e[0] == '0'); }     // default on; 0: the fused kernel
-    CK(h, cudaFuncSetAttribute(lin_tpl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin2_smem_bytes(kMaxFrames)));
-    CK(h, cudaFuncSetAttribute(lin_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem_bytes()));
-    CK(h, cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CK(h, cudaFuncSetAttribute(solve_kernel_visual, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
-    init_ctrl_kernel<<<(int)W, 32, 0, h->stream>>>(h->ctrl.d, 1e-8, 1e4);
+    {   // opt in to large dynamic shared memory ONCE per kernel with the device limit: the attribute is process-wide, so a
+        // per-handle value would be overwritten by the next handle with other capacities
+        const int lim = (int)prop.sharedMemPerBlockOptin - 2048;
+        CK(h, cudaFuncSetAttribute(lin_obs_kernel<true, float, kLinWarps, kLinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(lin_obs_kernel<true, double, kLinWarps, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(lin_obs_kernel<false, double, kLinWarps, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(schur_kernel<float, kSchurThreads, kSchurBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(schur_kernel<double, kSchurThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(update_obs_kernel<true, float, kUpdWarps, kUpdBlocks, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(update_obs_kernel<true, float, 8, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(update_obs_kernel<true, float, kUpdWarps, kUpdBlocks, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(update_obs_kernel<true, double, kUpdWarps, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(update_obs_kernel<true, double, 8, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(update_obs_kernel<true, double, kUpdWarps, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CK(h, cudaFuncSetAttribute(solve_kernel_visual, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+    }
+    init_ctrl_kernel<<<(int)W, 32, 0, h->stream>>>(h->ctrl.d, 1e-8, 1e4, 10, 0.0, 0);
     ++h->launches;
     CK(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -692,7 +822,9 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     if (h->pnp_dev) cudaFree(h->pnp_dev);
     if (h->pnp_host) cudaFreeHost(h->pnp_host);
     klt_free(h);
+    marg_free(h);
     release(h->hdr); release(h->cst); release(h->obs); release(h->lms); release(h->rho); release(h->frames);
+    release(h->fobs); release(h->fobs_lm); release(h->seg); release(h->jr); release(h->lm_w); release(h->lm_msk); release(h->frames_out); release(h->rho_out); release(h->lm_v); release(h->valid); release(h->quality);
     release(h->ctrl); release(h->rho_cand); release(h->frames_cand); release(h->lm_scale); release(h->lm_aux); release(h->hs);
     release(h->dx_lm); release(h->dx_pose); release(h->pose_scale); release(h->v_pose); release(h->Hred);
     release(h->acc); release(h->aux_cost);
@@ -700,9 +832,9 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     release(h->imu_idx); release(h->imu_data); release(h->prior_frames); release(h->prior_S); release(h->prior_L);
     release(h->prior_e); release(h->prior_x0);
     release(h->plane_param); release(h->pt_plane); release(h->pt_begin); release(h->pt_frame); release(h->pt_z);
-    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+    drop_graphs(h);
     for (auto &e : h->kev) cudaEventDestroy(e);
-    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evk0); cudaEventDestroy(h->evk1);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     for (auto &e : h->ev_up) cudaEventDestroy(e);
     for (auto &e : h->ev_done) cudaEventDestroy(e);
     for (auto &e : h->ev_down) cudaEventDestroy(e);
@@ -724,37 +856,44 @@ int64_t pvio_b200_kernel_launches(pvio_b200_handle hh) {
 
 int pvio_b200_sync(pvio_b200_handle hh) {
     Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return PVIO_B200_EINVAL;
     CK(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 
 int pvio_b200_timer_start(pvio_b200_handle hh) {
     Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return PVIO_B200_EINVAL;
     CK(h, cudaEventRecord(h->ev0, h->stream));
     return 0;
 }
 
 int pvio_b200_timer_stop(pvio_b200_handle hh, float *ms) {
     Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !ms) return PVIO_B200_EINVAL;
     CK(h, cudaEventRecord(h->ev1, h->stream));
     CK(h, cudaEventSynchronize(h->ev1));
     CK(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
     return 0;
 }
 
-// which = 0: duration of the most recent linearise+Schur launch; which = 1: MEAN duration over the
-// launches since the last reset (at most the latest 512); which = -1: reset the accumulation.
+// Device time of the linearise + Schur stage from the CUDA events recorded around its launches:
+// which = 0 the most recent stage; 1 the MEAN stage over the launches since the last reset (at most the latest 256);
+// 2 / 3 the mean of the linearise / the Schur kernel alone; -1 resets the accumulation.
 int pvio_b200_last_kernel_ms(pvio_b200_handle hh, int which, float *ms) {
     Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return PVIO_B200_EINVAL;
     if (which < 0) { h->kev_count = 0; if (ms) *ms = 0.f; return 0; }
+    if (!ms) return PVIO_B200_EINVAL;
     if (h->kev_count == 0) { *ms = 0.f; return 0; }     // graph-replayed launches are not individually timed
     CK(h, cudaStreamSynchronize(h->stream));
-    const int n = which == 0 ? 1 : std::min(h->kev_count, 512);
+    const int n = which == 0 ? 1 : std::min(h->kev_count, 256);
     double tot = 0.0;
     for (int i = 0; i < n; ++i) {
-        const int slot = ((h->kev_count - 1 - i) % 512) * 2;
+        const int slot = ((h->kev_count - 1 - i) % 256) * 3;
         float t = 0.f;
-        CK(h, cudaEventElapsedTime(&t, h->kev[slot], h->kev[slot + 1]));
+        const int e0 = which == 3 ? 1 : 0, e1 = which == 2 ? 1 : 2;
+        CK(h, cudaEventElapsedTime(&t, h->kev[slot + e0], h->kev[slot + e1]));
         tot += t;
     }
     *ms = (float)(tot / n);
@@ -769,6 +908,7 @@ int pvio_b200_batch_set_window(pvio_b200_handle hh, int slot, const pvio_b200_wi
 
 int pvio_b200_batch_replicate(pvio_b200_handle hh, int n) {
     Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return PVIO_B200_EINVAL;
     if (n < 1 || n > h->W) return fail(h, PVIO_B200_EINVAL, "bad window count");
     const size_t N = h->Ncap;
     for (int i = 1; i < n; ++i) {
@@ -800,20 +940,50 @@ int pvio_b200_batch_replicate(pvio_b200_handle hh, int n) {
 
 int pvio_b200_batch_upload(pvio_b200_handle hh, int n) {
     Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return PVIO_B200_EINVAL;
     return upload(h, n);
 }
 
 int pvio_b200_batch_gn_step(pvio_b200_handle hh, int n, double mu, int apply) {
     Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return PVIO_B200_EINVAL;
     if (n < 1 || n > h->n_uploaded) return fail(h, PVIO_B200_EINVAL, "windows not uploaded");
     StepCfg c;
     c.mu = mu; c.apply = apply; c.compute_scale = 1;
-    return run_step(h, n, c);
+    return run_gn_step(h, n, c, batch_shape(h, 0, n, false));
 }
 
 int pvio_b200_batch_download(pvio_b200_handle hh, int n, double *dx, int64_t dx_stride, double *costs) {
     Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return PVIO_B200_EINVAL;
     return download_dx(h, n, dx, dx_stride, costs);
+}
+
+// sub-batch schedule of the pipelined host paths: small batches first and last (the first upload and the last
+// kernels + download are the only parts of the pipeline that nothing overlaps), 512-window batches in between
+static std::vector<int> sub_batches(int n) {
+    std::vector<int> sizes;
+    if (n < 1024) { sizes.push_back(n); return sizes; }
+    int mid = n - 2 * (128 + 256);
+    sizes.push_back(128); sizes.push_back(256);
+    while (mid > 0) { const int m = std::min(512, mid); sizes.push_back(m); mid -= m; }
+    sizes.push_back(256); sizes.push_back(128);
+    return sizes;
+}
+
+static int ensure_pipeline_streams(Handle *h, int nsub) {
+    if (!h->stream_up) {
+        CK(h, cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
+        CK(h, cudaStreamCreateWithFlags(&h->stream_down, cudaStreamNonBlocking));
+    }
+    while ((int)h->ev_up.size() < nsub) {
+        cudaEvent_t a, b, c_;
+        CK(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&c_, cudaEventDisableTiming));
+        h->ev_up.push_back(a); h->ev_done.push_back(b); h->ev_down.push_back(c_);
+    }
+    return 0;
 }
 
 // End-to-end step with HOST buffers.  Large batches are cut into sub-batches and pipelined over
@@ -822,42 +992,20 @@ int pvio_b200_batch_download(pvio_b200_handle hh, int n, double *dx, int64_t dx_
 // max(copy, compute) instead of their sum.
 int pvio_b200_batch_gn_step_host(pvio_b200_handle hh, int n, double mu, double *dx, int64_t dx_stride, double *costs) {
     Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return PVIO_B200_EINVAL;
     if (n < 1 || n > h->W) return fail(h, PVIO_B200_EINVAL, "bad window count");
-    // sub-batch schedule: small batches first and last (the first upload and the last kernels + download are the
-    // only parts of the pipeline that nothing overlaps), 512-window batches in between
-    static const int sub_env = getenv("PVIO_B200_SUB") ? atoi(getenv("PVIO_B200_SUB")) : 0;     // uniform size (experiments)
-    std::vector<int> sizes;
-    if (n < 1024) sizes.push_back(n);
-    else if (sub_env > 0) { for (int r = n; r > 0; r -= sub_env) sizes.push_back(std::min(sub_env, r)); }
-    else {
-        int mid = n - 2 * (128 + 256);
-        sizes.push_back(128); sizes.push_back(256);
-        while (mid > 0) { const int m = std::min(512, mid); sizes.push_back(m); mid -= m; }
-        sizes.push_back(256); sizes.push_back(128);
-    }
+    const std::vector<int> sizes = sub_batches(n);
     const int nsub = (int)sizes.size();
     if (nsub == 1) {
         TRY(upload(h, n));
         StepCfg c;
         c.mu = mu; c.apply = 0; c.compute_scale = 1;
-        TRY(run_step(h, n, c));
+        TRY(run_gn_step(h, n, c, batch_shape(h, 0, n, false)));
         return download_dx(h, n, dx, dx_stride, costs);
     }
     std::vector<int> starts(nsub, 0);
     for (int i = 1; i < nsub; ++i) starts[i] = starts[i - 1] + sizes[i - 1];
-    if (!h->stream_up) {
-        CK(h, cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
-        CK(h, cudaStreamCreateWithFlags(&h->stream_down, cudaStreamNonBlocking));
-    }
-    while ((int)h->ev_up.size() < nsub) {
-        cudaEvent_t a, b;
-        CK(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        CK(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-        h->ev_up.push_back(a); h->ev_done.push_back(b);
-        cudaEvent_t c_;
-        CK(h, cudaEventCreateWithFlags(&c_, cudaEventDisableTiming));
-        h->ev_down.push_back(c_);
-    }
+    TRY(ensure_pipeline_streams(h, nsub));
     for (int i = 0; i < nsub; ++i) {
         const int w0 = starts[i], m = sizes[i];
         TRY(upload_range(h, w0, m, h->stream_up));
@@ -865,7 +1013,7 @@ int pvio_b200_batch_gn_step_host(pvio_b200_handle hh, int n, double mu, double *
         CK(h, cudaStreamWaitEvent(h->stream, h->ev_up[i], 0));
         StepCfg c;
         c.mu = mu; c.apply = 0; c.compute_scale = 1; c.w0 = w0;
-        TRY(run_step(h, m, c));
+        TRY(run_gn_step(h, m, c, batch_shape(h, w0, m, false)));
         CK(h, cudaEventRecord(h->ev_done[i], h->stream));
         CK(h, cudaStreamWaitEvent(h->stream_down, h->ev_done[i], 0));
         CK(h, cudaMemcpyAsync(h->dx_pose.h + (size_t)w0 * h->Ncap * 15, h->dx_pose.d + (size_t)w0 * h->Ncap * 15,
@@ -886,6 +1034,79 @@ int pvio_b200_batch_gn_step_host(pvio_b200_handle hh, int n, double mu, double *
     return 0;
 }
 
+// Full trust-region solve (device-side loop, per-window termination) of the first n uploaded windows; the states on
+// the device are overwritten with the solutions.
+int pvio_b200_batch_solve(pvio_b200_handle hh, int n, const pvio_b200_options *opt) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return PVIO_B200_EINVAL;
+    if (n < 1 || n > h->n_uploaded) return fail(h, PVIO_B200_EINVAL, "windows not uploaded");
+    const int max_iter = opt ? opt->max_iterations : 10;
+    const double radius0 = (opt && opt->initial_trust_region_radius > 0) ? opt->initial_trust_region_radius : 1e4;
+    return run_solve_loop(h, n, max_iter, opt ? opt->max_time : 0.0, radius0, opt ? opt->alias_bias : 1);
+}
+
+int pvio_b200_batch_download_state(pvio_b200_handle hh, int n, double *frames, int64_t frames_stride, double *inv_depth,
+                                   int64_t inv_depth_stride, pvio_b200_summary *summaries) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return PVIO_B200_EINVAL;
+    if (n < 1 || n > h->W) return fail(h, PVIO_B200_EINVAL, "bad window count");
+    TRY(download_state_async(h, 0, n, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; ++i) {
+        scatter_state(h, i, frames ? frames + (size_t)i * frames_stride : nullptr, inv_depth ? inv_depth + (size_t)i * inv_depth_stride : nullptr);
+        if (summaries) fill_summary(h->ctrl.h[i], &summaries[i]);
+    }
+    return 0;
+}
+
+// upload + solve + download with HOST buffers, pipelined over sub-batches like pvio_b200_batch_gn_step_host: one
+// host -> device copy buys up to max_iterations Gauss-Newton iterations per window.
+int pvio_b200_batch_solve_host(pvio_b200_handle hh, int n, const pvio_b200_options *opt, double *frames, int64_t frames_stride,
+                               double *inv_depth, int64_t inv_depth_stride, pvio_b200_summary *summaries) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return PVIO_B200_EINVAL;
+    if (n < 1 || n > h->W) return fail(h, PVIO_B200_EINVAL, "bad window count");
+    const int max_iter = opt ? opt->max_iterations : 10;
+    const double radius0 = (opt && opt->initial_trust_region_radius > 0) ? opt->initial_trust_region_radius : 1e4;
+    const int alias = opt ? opt->alias_bias : 1;
+    const std::vector<int> sizes = sub_batches(n);
+    const int nsub = (int)sizes.size();
+    if (nsub == 1) {
+        TRY(upload(h, n));
+        TRY(run_solve_loop(h, n, max_iter, opt ? opt->max_time : 0.0, radius0, alias));
+        return pvio_b200_batch_download_state(hh, n, frames, frames_stride, inv_depth, inv_depth_stride, summaries);
+    }
+    std::vector<int> starts(nsub, 0);
+    for (int i = 1; i < nsub; ++i) starts[i] = starts[i - 1] + sizes[i - 1];
+    TRY(ensure_pipeline_streams(h, nsub));
+    for (int i = 0; i < nsub; ++i) {
+        const int w0 = starts[i], m = sizes[i];
+        TRY(upload_range(h, w0, m, h->stream_up));
+        CK(h, cudaEventRecord(h->ev_up[i], h->stream_up));
+        CK(h, cudaStreamWaitEvent(h->stream, h->ev_up[i], 0));
+        StepCfg c;
+        c.mu = -1.0; c.loop = 1; c.alias_bias = alias; c.compute_scale = 0; c.w0 = w0;
+        const BatchShape b = batch_shape(h, w0, m, false);
+        init_ctrl_kernel<<<m, 32, 0, h->stream>>>(h->ctrl.d, 1e-8, radius0, max_iter, opt ? opt->max_time : 0.0, w0);
+        ++h->launches;
+        for (int it = 0; it < max_iter + 2; ++it) TRY(iteration_body(h, m, c, b));
+        CK(h, cudaEventRecord(h->ev_done[i], h->stream));
+        CK(h, cudaStreamWaitEvent(h->stream_down, h->ev_done[i], 0));
+        TRY(download_state_async(h, w0, m, h->stream_down));
+        CK(h, cudaEventRecord(h->ev_down[i], h->stream_down));
+    }
+    h->n_uploaded = n;
+    for (int i = 0; i < nsub; ++i) {
+        CK(h, cudaEventSynchronize(h->ev_down[i]));
+        for (int k = starts[i]; k < starts[i] + sizes[i]; ++k) {
+            scatter_state(h, k, frames ? frames + (size_t)k * frames_stride : nullptr, inv_depth ? inv_depth + (size_t)k * inv_depth_stride : nullptr);
+            if (summaries) fill_summary(h->ctrl.h[k], &summaries[k]);
+        }
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int pvio_b200_ba_gn_step(pvio_b200_handle hh, const pvio_b200_window *w, const pvio_b200_state *s, double mu,
                          double *dx, double *cost, double *new_cost, double *Hred, double *gred) {
     Handle *h = reinterpret_cast<Handle *>(hh);
@@ -898,7 +1119,7 @@ int pvio_b200_ba_gn_step(pvio_b200_handle hh, const pvio_b200_window *w, const p
         CK(h, cudaMemsetAsync(h->Hfull.d, 0, sizeof(double) * h->Hfull.n, h->stream));
         CK(h, cudaMemsetAsync(h->gfull.d, 0, sizeof(double) * h->gfull.n, h->stream));
     }
-    TRY(run_step(h, 1, c));
+    TRY(run_gn_step(h, 1, c, batch_shape(h, 0, 1, false)));
     double costs[2];
     const int N = w->n_frames, M = w->n_landmarks;
     TRY(download_dx(h, 1, dx, (int64_t)N * 15 + M, costs));
@@ -915,172 +1136,43 @@ int pvio_b200_ba_gn_step(pvio_b200_handle hh, const pvio_b200_window *w, const p
     return 0;
 }
 
-// Trust-region loop: the minimiser logic of ceres::Solve as PVIO configures it
-// (solver_options.h:26-33; TrustRegionMinimizer + dogleg defaults of Ceres 1.14), driven from
-// the host with one small device->host read per iteration.  When the Gauss-Newton step leaves the
-// trust region the Cauchy point is computed with one extra J.v sweep and the traditional dogleg
-// interpolation is applied, as dogleg_strategy.cc does.
+// BundleAdjustorSolver::solve (bundle_adjustor.cpp:63-299) behind the shim's gather: pack, one host -> device copy,
+// the device-side trust-region loop (ONE graph launch, ba_tr.cuh), the landmark post-pass, one device -> host copy.
 int pvio_b200_ba_solve(pvio_b200_handle hh, const pvio_b200_window *w, pvio_b200_state *s,
                        const pvio_b200_options *opt, pvio_b200_summary *summary, uint8_t *valid, double *quality) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (!h || !w || !s) return PVIO_B200_EINVAL;
     const int max_iter = opt ? opt->max_iterations : 10;
     const int alias = opt ? opt->alias_bias : 1;
-    const double max_time = (opt && opt->max_time > 0) ? opt->max_time : 1e6;
-    const auto t_begin = std::chrono::steady_clock::now();
+    const double radius0 = (opt && opt->initial_trust_region_radius > 0) ? opt->initial_trust_region_radius : 1e4;
     TRY(pack_window(h, 0, w, s));
     TRY(upload(h, 1));
     CK(h, cudaEventRecord(h->ev0, h->stream));
-    double radius = (opt && opt->initial_trust_region_radius > 0) ? opt->initial_trust_region_radius : 1e4, mu = 1e-8;
-    bool reuse = false;
-    StepCfg c;
-    c.apply = 0; c.alias_bias = alias; c.compute_scale = 1;
-    pvio_b200_summary sm;
-    memset(&sm, 0, sizeof(sm));
-    sm.termination = PVIO_B200_TERM_NO_CONVERGENCE; sm.usable = 1;
-    auto read_ctrl = [&](WinCtrl &o, double *acc) -> int {
-        CK(h, cudaMemcpyAsync(h->ctrl.h, h->ctrl.d, sizeof(WinCtrl), cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(h->acc.h, h->acc.d, sizeof(double) * kAcc, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));
-        o = h->ctrl.h[0];
-        memcpy(acc, h->acc.h, sizeof(double) * kAcc);
-        return 0;
-    };
-    WinCtrl ct;
-    double acc[kAcc];
-    int it = 0;
-    bool first = true;
-    double cost = 0.0;
-    while (it < max_iter) {
-        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() > max_time) break;
-        ++it;
-        c.mu = mu; c.beta = 1.0; c.skip_linearize = reuse;
-        TRY(run_step(h, 1, c));
-        TRY(read_ctrl(ct, acc));
-        if (first) {
-            sm.initial_cost = ct.cost;
-            first = false;
-            if (ct.gmax <= 1e-10) { sm.termination = PVIO_B200_TERM_CONVERGENCE; --it; cost = ct.cost; break; }
-        }
-        c.compute_scale = 0;
-        cost = ct.cost;
-        if (ct.solve_failed) {                 // dogleg_strategy.cc: retry the GN solve with a larger mu
-            mu *= 10.0;
-            reuse = false;
-            if (mu > 1.0) { sm.termination = PVIO_B200_TERM_FAILURE; sm.usable = 0; break; }
-            --it;
-            continue;
-        }
-        // ---- DoglegStrategy::ComputeStep (TRADITIONAL_DOGLEG), all norms in the diag-scaled space
-        const double gn_norm = std::sqrt(ct.gn_norm2 + acc[3]);
-        const double gdx = ct.g_dot_dx + acc[1];                 // g . dx_gn  (= grad . gn in scaled space)
-        const double rdx = ct.dx_reg_dx + acc[2];                // dx_gn^T (mu D) dx_gn
-        double sa = 0.0, sb = 1.0, step_norm = gn_norm;
-        double grad2 = 0.0, v_rd = 0.0, jv2 = 0.0;
-        if (gn_norm > radius) {
-            // Cauchy point: alpha = |grad|^2 / |J S D^-1 grad|^2 needs one J.v sweep
-            TRY(run_jv(h, c));
-            double acc2[kAcc];
-            WinCtrl ct2;
-            TRY(read_ctrl(ct2, acc2));
-            grad2 = ct.grad2 + acc[7];
-            v_rd = ct.v_reg_dx + acc[8];
-            jv2 = acc2[9] + acc2[10];
-            const double g_norm = std::sqrt(grad2);
-            const double alpha = grad2 / jv2;
-            if (g_norm * alpha >= radius) {                       // scaled steepest descent to the boundary
-                sa = radius / g_norm; sb = 0.0;
-            } else {                                              // dogleg interpolation (dogleg_strategy.cc)
-                const double b_dot_a = -alpha * gdx;
-                const double a2 = (alpha * g_norm) * (alpha * g_norm);
-                const double bma2 = a2 - 2.0 * b_dot_a + gn_norm * gn_norm;
-                const double cc = b_dot_a - a2;
-                const double dd = std::sqrt(cc * cc + bma2 * (radius * radius - a2));
-                const double beta = cc <= 0 ? (dd - cc) / bma2 : (radius * radius - a2) / (dd + cc);
-                sa = alpha * (1.0 - beta); sb = beta;
-            }
-            step_norm = radius;
-            c.step_a = sa; c.step_b = sb; c.skip_linearize = true;
-            TRY(run_step(h, 1, c));
-            TRY(read_ctrl(ct, acc));
-            c.step_a = 0.0; c.step_b = -1.0;
-        }
-        // model cost change -(g.s + s^T H s / 2) of s = sb dx_gn - sa v, using H dx_gn = -g - (mu D) dx_gn
-        const double dHd = -gdx - rdx, vHd = -grad2 - v_rd;
-        const double sHs = sb * sb * dHd - 2.0 * sa * sb * vHd + sa * sa * jv2;
-        const double model_change = -(sb * gdx - sa * grad2) - 0.5 * sHs;
-        const double beta = sb;
-        if (!(model_change > 0.0)) { radius *= 0.5; reuse = true; continue; }       // invalid step
-        const double x_norm = std::sqrt(ct.xnorm2 + acc[5]);
-        const double step_amb = std::sqrt(acc[6] + acc[4]);
-        if (step_amb <= 1e-8 * (x_norm + 1e-8)) { sm.termination = PVIO_B200_TERM_CONVERGENCE; break; }
-        if (std::fabs(cost - ct.cand_cost) <= 1e-6 * cost) { sm.termination = PVIO_B200_TERM_CONVERGENCE; break; }
-        const double rel = (cost - ct.cand_cost) / model_change;
-        if (rel > 1e-3) {
-            // accept: candidate becomes the state
-            finalize_kernel<<<1, 128, 0, h->stream>>>(h->ctrl.d, h->acc.d, h->aux_cost.d, 1, h->frames.d, h->frames_cand.d,
-                                                     h->rho.d, h->rho_cand.d, h->hdr.d, h->Ncap, h->Mcap, beta, 0);
-            ++h->launches;
-            ++sm.accepted_steps;
-            cost = ct.cand_cost;
-            if (rel < 0.25) radius *= 0.5;
-            if (rel > 0.75) radius = std::max(radius, 3.0 * step_norm);
-            mu = std::max(1e-8, 2.0 * mu / 10.0);
-            reuse = false;
-            // gradient tolerance at the new point is checked after the next linearisation
-            if (it < max_iter) {
-                StepCfg g = c;
-                g.mu = mu; g.beta = 1.0; g.skip_linearize = false;
-                // peek: linearise + solve only, to read |g|_inf and the re-evaluated cost (ceres re-evaluates
-                // the cost at the accepted point together with the Jacobian)
-                TRY(run_step(h, 1, g, 1));
-                TRY(read_ctrl(ct, acc));
-                cost = ct.cost;
-                reuse = true;                // the next iteration reuses this linearisation
-                if (ct.gmax <= 1e-10) { sm.termination = PVIO_B200_TERM_CONVERGENCE; break; }
-            }
-        } else {
-            radius *= 0.5;
-            reuse = true;
-        }
-        if (radius <= 1e-32) { sm.termination = PVIO_B200_TERM_CONVERGENCE; break; }
-    }
+    TRY(run_solve_loop(h, 1, max_iter, opt ? opt->max_time : 0.0, radius0, alias));
     CK(h, cudaEventRecord(h->ev1, h->stream));
-    sm.iterations = it;
-    sm.final_cost = cost;
-    sm.final_radius = radius; sm.final_mu = mu;
-    // read back the state
-    const int N = w->n_frames, M = w->n_landmarks;
-    CK(h, cudaMemcpyAsync(h->frames.h, h->frames.d, sizeof(double) * N * kFrameStride, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaMemcpyAsync(h->rho.h, h->rho.d, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
-    uint8_t *d_valid = nullptr;
-    double *d_quality = nullptr;
-    if ((!opt || opt->run_postpass) && (valid || quality)) {
-        CK(h, cudaMalloc(&d_valid, M > 0 ? M : 1));
-        CK(h, cudaMalloc(&d_quality, sizeof(double) * (M > 0 ? M : 1)));
-        postpass_kernel<<<dim3(8, 1), 256, 0, h->stream>>>(h->hdr.d, h->cst.d, h->obs.d, h->lms.d, h->rho.d, h->frames.d,
-                                                          d_valid, d_quality, nullptr, h->Ncap, h->Mcap, h->Kcap);
-        ++h->launches;
+    const int M = w->n_landmarks;
+    const bool post = (!opt || opt->run_postpass) && (valid || quality);
+    if (post) {
+        TRY(run_postpass(h, 1, true, nullptr));
+        CK(h, cudaMemcpyAsync(h->valid.h, h->valid.d, (size_t)std::max(M, 1), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(h->quality.h, h->quality.d, sizeof(double) * std::max(M, 1), cudaMemcpyDeviceToHost, h->stream));
     }
+    TRY(download_state_async(h, 0, 1, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-    sm.solve_seconds = ms * 1e-3;
-    memcpy(s->frames, h->frames.h, sizeof(double) * N * kFrameStride);
-    const std::vector<int32_t> &perm = h->perm[0];
-    for (int lp = 0; lp < M; ++lp) s->inv_depth[perm[lp]] = h->rho.h[lp];
-    if (d_valid) {
-        std::vector<uint8_t> hv(M);
-        std::vector<double> hq(M);
-        CK(h, cudaMemcpy(hv.data(), d_valid, M, cudaMemcpyDeviceToHost));
-        CK(h, cudaMemcpy(hq.data(), d_quality, sizeof(double) * M, cudaMemcpyDeviceToHost));
+    scatter_state(h, 0, s->frames, s->inv_depth);
+    if (post) {
+        const std::vector<int32_t> &perm = h->perm[0];
         for (int lp = 0; lp < M; ++lp) {
-            if (valid) valid[perm[lp]] = hv[lp];
-            if (quality) quality[perm[lp]] = hq[lp];
+            if (valid) valid[perm[lp]] = h->valid.h[lp];
+            if (quality) quality[perm[lp]] = h->quality.h[lp];
         }
-        cudaFree(d_valid); cudaFree(d_quality);
     }
-    if (summary) *summary = sm;
+    if (summary) {
+        fill_summary(h->ctrl.h[0], summary);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        summary->solve_seconds = ms * 1e-3;
+    }
     return 0;
 }
 
@@ -1090,9 +1182,7 @@ int pvio_b200_reprojection_error(pvio_b200_handle hh, const pvio_b200_window *w,
     TRY(pack_window(h, 0, w, s));
     TRY(upload(h, 1));
     CK(h, cudaMemsetAsync(h->acc.d, 0, sizeof(double) * 8, h->stream));
-    postpass_kernel<<<dim3(8, 1), 256, 0, h->stream>>>(h->hdr.d, h->cst.d, h->obs.d, h->lms.d, h->rho.d, h->frames.d,
-                                                      nullptr, nullptr, h->acc.d, h->Ncap, h->Mcap, h->Kcap);
-    ++h->launches;
+    TRY(run_postpass(h, 1, false, h->acc.d));
     CK(h, cudaMemcpyAsync(h->acc.h, h->acc.d, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     *error = h->acc.h[0] / std::max(h->acc.h[1], 1.0);
@@ -1138,6 +1228,12 @@ int pvio_b200_clahe(pvio_b200_handle hh, const uint8_t *src, int width, int heig
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (!h || !src || !dst) return PVIO_B200_EINVAL;
     return clahe_impl(h, src, width, height, stride, clip_limit, tiles_x, tiles_y, dst);
+}
+
+int pvio_b200_selftest_lie(pvio_b200_handle hh, int n, const double *w, double *out) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !w || !out || n < 1) return PVIO_B200_EINVAL;
+    return selftest_lie_impl(h, n, w, out);
 }
 
 }  // extern "C"

@@ -19,15 +19,16 @@ struct DevBuf {
 };
 
 struct KltState;         // klt.cu
+struct MargScratch;      // ba_marg.cu
 
 struct Handle {
     int device = 0;
     int W = 1, Ncap = 0, Mcap = 0, Kcap = 0;
-    int Pcap = 4, Tcap = 0, Ocap = 0;            // planes / plane tracks / plane observations
+    int Pcap = 4, Tcap = 0, Ocap = 0;            // planes / plane tracks / plane observations per window
     cudaStream_t stream = nullptr;
     cudaStream_t stream_up = nullptr, stream_down = nullptr;   // copy streams of the pipelined host path
     std::vector<cudaEvent_t> ev_up, ev_done, ev_down;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     int64_t launches = 0;
     int sm_count = 148;
@@ -35,16 +36,25 @@ struct Handle {
     // vision (always allocated)
     DevBuf<WinHdr> hdr;
     DevBuf<WinConst> cst;
-    DevBuf<ObsRec> obs;
+    DevBuf<ObsRec> obs;                          // landmark-major table as the shim gathers it (uploaded)
+    DevBuf<FObs> fobs;                           // frame-major table, built on the device after every upload
+    DevBuf<uint16_t> fobs_lm;
+    DevBuf<int32_t> seg;                         // [W][kSegTab]
     DevBuf<LmRec> lms;
     DevBuf<double> rho, frames;
     DevBuf<WinCtrl> ctrl;
-    DevBuf<double> rho_cand, frames_cand, lm_scale, dx_lm, dx_pose, pose_scale, v_pose;
+    DevBuf<double> rho_cand, frames_cand, lm_scale, dx_lm, lm_v, dx_pose, pose_scale, v_pose;
     DevBuf<LmAux> lm_aux;
-    DevBuf<float> hs;                            // [W][hs_stride] sqrt(w_l) h_l records, linearise -> update
-    size_t hs_stride = 0;                        // (Mcap / 32 + Ncap + 1) chunks x 32 slots x 6 Ncap floats
+    DevBuf<unsigned char> hs;                    // [W][Ncap][Mcap][6] float (visual-only windows) or double (inertial):
+    DevBuf<unsigned char> jr;                    //   unscaled h records / [W][Ncap][Mcap][2] (j.j, j.r), linearise -> Schur / update
+    DevBuf<unsigned char> lm_w;                  // [W][Mcap][2] real: pivot w_l, w_l g_l
+    DevBuf<int32_t> lm_msk;                      // [W][Mcap] frame mask of each landmark
+    bool hs_double = false;
+    DevBuf<double> frames_out, rho_out;          // pinned landing area of downloaded states (the upload staging stays intact)
     DevBuf<double> Hred, Hdd, gdir, gred, cost_vis, acc, aux_cost;
     DevBuf<double> Hfull, gfull;                 // debug dump (single window only)
+    DevBuf<uint8_t> valid;                       // post-pass results
+    DevBuf<double> quality;
     // inertial / prior / planes (allocated on first use)
     bool have_inertial = false;
     DevBuf<int32_t> imu_idx, prior_frames;
@@ -58,24 +68,18 @@ struct Handle {
     std::vector<int> slot_M, slot_N, slot_K;
     std::vector<uint8_t> perm_identity;
     int n_uploaded = 0;
-    int max_slot_free = 0;        // most free (non FF_FIX_POSE) frames of any window packed so far
-    int max_slot_N = 0;           // largest window packed so far (selects the tensor-core linearise kernel)
-    int tc_gs = 1;                // k-steps per TMEM partial sum (PVIO_B200_TC_GS, experiments)
-    int split_shape = 3;          // CTA shape of lin_a_kernel (experiments)
-    bool split_schur = true;      // PVIO_B200_SPLIT=1: linearise stage as two kernels (Phase A, then schur_kernel)
-    int tc_mode = 0;              // PVIO_B200_TC: 1 = fused tcgen05 linearise kernel, 2 = split stage with the tcgen05 Schur kernel
-    bool use_tc = false;          // PVIO_B200_TC=1: tcgen05 Schur SYRK (lin_tc_kernel) instead of the CUDA-core one
-    float last_lin_ms = 0.f;
-    // ring of event pairs around every linearise+Schur launch (roofline timing without host syncs)
+    // ring of event triples around the linearise + Schur launches (roofline timing without host syncs)
     std::vector<cudaEvent_t> kev;
     int kev_count = 0;
-    // CUDA graphs of the single-window launch sequences (latency path), keyed by everything that
-    // shapes the launches; replayed on later calls (device buffers are persistent)
-    typedef std::tuple<int, int, int, int, int, int, int, int, int, double, double, double> GraphKey;
+    // CUDA graphs of the latency path (few windows): the whole trust-region solve / one GN iteration as ONE launch.
+    // Key: (kind, n, max_iter, flags) -- no floating-point values; all scalars the kernels need live in WinCtrl.
+    // Launch shapes use the handle's capacities, so a graph survives window-shape changes between keyframes.
+    // Cleared whenever a device buffer is reallocated (pointers are baked into the nodes).
+    typedef std::tuple<int, int, int, int> GraphKey;
     std::map<GraphKey, std::pair<cudaGraphExec_t, int>> graphs;
     bool capturing = false;
-    bool use_graphs = true;
     KltState *klt = nullptr;
+    MargScratch *marg = nullptr;
     double *pnp_dev = nullptr, *pnp_host = nullptr;   // pnp.cu: device buffer + pinned staging, grown on demand
     size_t pnp_words = 0;
 };
@@ -88,8 +92,13 @@ int fail(Handle *h, int code, const char *what, cudaError_t e = cudaSuccess);
         if (e__ != cudaSuccess) return fail((h), PVIO_B200_ECUDA, #call, e__); \
     } while (0)
 
-// api.cu: pack window into slot 0 and copy it to the device
+#define TRY(x) do { int rc__ = (x); if (rc__ != 0) return rc__; } while (0)
+
+// api.cu: pack window into slot 0, copy it to the device, build the frame-major table
 int pack_and_upload(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s);
+// api.cu: linearise + Schur of window 0 with the fp64 pipeline, no loss (the marginaliser's reprojection part)
+int run_marg_vision(Handle *h);
+void drop_graphs(Handle *h);
 // klt.cu
 int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int width, int height, int stride,
                    const float *prev_pts, float *next_pts, uint8_t *status, float *err, int n_points,
@@ -103,5 +112,8 @@ int pnp_solve_impl(Handle *h, const pvio_b200_pnp_problem *pb, double *frame, co
 // ba_marg.cu
 int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s, int index,
                      double *S_out, double *e_out, double *H_out, double *b_out);
+void marg_free(Handle *h);
+// selftest.cu
+int selftest_lie_impl(Handle *h, int n, const double *w_in, double *out);
 
 }  // namespace pvio

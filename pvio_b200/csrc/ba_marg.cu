@@ -2,8 +2,8 @@
 //
 //   prior J^T J                                   :369-413   marg_assemble_kernel
 //   IMU factors adjacent to the victim            :416-450   marg_assemble_kernel
-//   reprojection factors of victim-seen tracks    :453-533   lin_tpl_kernel<false> (no loss, quirk Q3)
-//   landmark Schur (1/mat, isfinite skip)         :536-545   lin_tpl_kernel<false>
+//   reprojection factors of victim-seen tracks    :453-533   lin_obs_kernel<false, double> (no loss, quirk Q3; ba_linearize.cuh)
+//   landmark Schur (1/mat, isfinite skip)         :536-545   schur_kernel<double> (ba_schur.cuh)
 //   frame Schur with the explicit 15x15 inverse   :547-581   marg_reduce_kernel
 //   eigen factorisation, clamp lambda <= 1e-8     :583-590   marg_eig_kernel (parallel cyclic Jacobi)
 // All dense algebra is fp64.  Runs once per keyframe (not per iteration): latency, not bandwidth.
@@ -11,7 +11,6 @@
 #include <vector>
 #include "api_internal.h"
 #include "ba_lin.cuh"
-#include "ba_lin2.cuh"
 #include "ba_solve.cuh"
 
 namespace pvio {
@@ -20,7 +19,7 @@ struct MargArgs {
     const WinHdr *hdr;
     const WinConst *cst;
     const double *frames;
-    const double *Hred, *gred;         // vision part (xi coordinates) from lin_schur_kernel<false>
+    const double *Hred, *gred;         // vision part (xi coordinates) from the linearise + Schur stage
     const int32_t *imu_idx;
     const double *imu_data;
     const int32_t *prior_frames;
@@ -322,32 +321,44 @@ __global__ void __launch_bounds__(512) marg_eig_kernel(double *A, double *V, con
     }
 }
 
+// Persistent device scratch of the marginaliser (it runs at every keyframe: nothing is allocated in the steady state).
+struct MargScratch {
+    double *buf = nullptr;
+    size_t words = 0;
+};
+
+void marg_free(Handle *h) {
+    if (h->marg) {
+        if (h->marg->buf) cudaFree(h->marg->buf);
+        delete h->marg;
+        h->marg = nullptr;
+    }
+}
+
 int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s, int index,
                      double *S_out, double *e_out, double *H_out, double *b_out) {
     const int N = w->n_frames;
     if (index < 0 || index >= N || N < 2) return fail(h, PVIO_B200_EINVAL, "marginalize: bad frame index");
     if (!w->use_inertial) return fail(h, PVIO_B200_EINVAL, "marginalize: the window must carry motion states");
+    const int n = 15 * N, dk = n - 15;
+    if ((S_out || e_out) && dk > 256) return fail(h, PVIO_B200_EINVAL, "marginalize: window too large for the eigen-solver");
     int rc = pack_and_upload(h, w, s);
     if (rc != 0) return rc;
-    const int n = 15 * N, dk = n - 15;
-    // vision part: no loss, victim-seen landmarks only, mu = 0
-    const size_t npc = (size_t)h->Ncap * (h->Ncap + 1) / 2;
-    CK(h, cudaMemsetAsync(h->Hred.d, 0, sizeof(double) * h->Hred.n, h->stream));
-    (void)npc;
-    LinArgs a;
-    a.hdr = h->hdr.d; a.cst = h->cst.d; a.obs = h->obs.d; a.lms = h->lms.d; a.rho = h->rho.d; a.frames = h->frames.d;
-    a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d; a.hs_out = nullptr; a.hs_stride = 0;
-    a.Hred = h->Hred.d; a.Hdd = h->Hdd.d; a.gdir = h->gdir.d; a.gred = h->gred.d; a.cost_vis = h->cost_vis.d;
-    a.Ncap = h->Ncap; a.Mcap = h->Mcap; a.Kcap = h->Kcap;
-    a.compute_scale = 1; a.victim_only = 1; a.mu_override = 0.0; a.w0 = 0;
-    lin_tpl_kernel<false><<<dim3(4, 1), kLinThreads, lin2_smem_bytes(h->Ncap), h->stream>>>(a);
-    ++h->launches;
-    // dense buffers
-    double *dH = nullptr, *db = nullptr, *dHk = nullptr, *dbk = nullptr, *dV = nullptr, *dS = nullptr, *de = nullptr, *dscr = nullptr;
-    CK(h, cudaMalloc(&dH, sizeof(double) * n * n)); CK(h, cudaMalloc(&db, sizeof(double) * n));
-    CK(h, cudaMalloc(&dHk, sizeof(double) * dk * dk)); CK(h, cudaMalloc(&dbk, sizeof(double) * dk));
-    CK(h, cudaMalloc(&dV, sizeof(double) * dk * dk)); CK(h, cudaMalloc(&dS, sizeof(double) * dk * dk));
-    CK(h, cudaMalloc(&de, sizeof(double) * dk)); CK(h, cudaMalloc(&dscr, sizeof(double) * (2048 + 64 * h->Ncap)));
+    // dense buffers: sized once from the handle's frame capacity
+    const size_t ncap = 15 * (size_t)h->Ncap, dcap = ncap - 15;
+    const size_t words = ncap * ncap + ncap + 3 * dcap * dcap + 2 * dcap + 2048 + 64 * (size_t)h->Ncap;
+    if (!h->marg) h->marg = new MargScratch();
+    if (h->marg->words < words) {
+        if (h->marg->buf) cudaFree(h->marg->buf);
+        h->marg->buf = nullptr; h->marg->words = 0;
+        CK(h, cudaMalloc(&h->marg->buf, sizeof(double) * words));
+        h->marg->words = words;
+    }
+    double *dH = h->marg->buf, *db = dH + ncap * ncap, *dHk = db + ncap, *dV = dHk + dcap * dcap, *dS = dV + dcap * dcap,
+           *dbk = dS + dcap * dcap, *de = dbk + dcap, *dscr = de + dcap;
+    // vision part: no loss, victim-seen landmarks only, mu = 0, fp64 (lin_obs_kernel<false, double> + schur_kernel<double>)
+    rc = run_marg_vision(h);
+    if (rc != 0) return rc;
     MargArgs m;
     m.hdr = h->hdr.d; m.cst = h->cst.d; m.frames = h->frames.d; m.Hred = h->Hred.d; m.gred = h->gred.d;
     m.imu_idx = h->imu_idx.d; m.imu_data = h->imu_data.d; m.prior_frames = h->prior_frames.d;
@@ -359,7 +370,6 @@ int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state
     if (H_out) CK(h, cudaMemcpyAsync(H_out, dHk, sizeof(double) * dk * dk, cudaMemcpyDeviceToHost, h->stream));
     if (b_out) CK(h, cudaMemcpyAsync(b_out, dbk, sizeof(double) * dk, cudaMemcpyDeviceToHost, h->stream));
     if (S_out || e_out) {
-        if (dk > 256) return fail(h, PVIO_B200_EINVAL, "marginalize: window too large for the eigen-solver");
         marg_eig_kernel<<<1, 512, 0, h->stream>>>(dHk, dV, dbk, dk, dS, de, 30);
         ++h->launches;
         if (S_out) CK(h, cudaMemcpyAsync(S_out, dS, sizeof(double) * dk * dk, cudaMemcpyDeviceToHost, h->stream));
@@ -367,7 +377,6 @@ int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state
     }
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaGetLastError());
-    cudaFree(dH); cudaFree(db); cudaFree(dHk); cudaFree(dbk); cudaFree(dV); cudaFree(dS); cudaFree(de); cudaFree(dscr);
     return 0;
 }
 

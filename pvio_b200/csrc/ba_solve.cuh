@@ -16,6 +16,7 @@
 #include "ba_math.cuh"
 #include "ba_types.h"
 #include "ba_lin.cuh"
+#include "ba_tr.cuh"
 
 namespace pvio {
 
@@ -53,10 +54,10 @@ struct SolveArgs {
     double *Hfull;             // optional [W][(15 Ncap)^2] dump of the reduced system (delta coords, before regularisation)
     double *gfull;             // optional [W][15 Ncap]
     int Ncap;
-    int compute_scale;
+    int compute_scale;         // ignored when loop != 0 (then: WinCtrl::have_scale == 0)
     int w0;
     double mu_override;
-    long long *dbg;            // optional [16] clock64 stamps of window w0 (profiling aid)
+    int loop;                  // 1: iteration of the device-side trust-region loop (ba_tr.cuh): obey the window's flags
 };
 
 // The dense system is stored as packed lower-triangular 4x4 TILES (tile (I,J), J <= I, at
@@ -449,10 +450,9 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const double *frames = a.frames + (size_t)w * a.Ncap * kFrameStride;
     WinCtrl &ctrl = a.ctrl[w];
+    if (a.loop && (ctrl.done || ctrl.reuse)) return;         // finished, or the rejected step's linearisation is still valid
+    const int compute_scale = a.loop ? (ctrl.have_scale == 0) : a.compute_scale;
     const double mu = a.mu_override >= 0.0 ? a.mu_override : ctrl.mu;
-    int stamp_i = 0;
-#define STAMP() do { if (a.dbg && tid == 0 && blockIdx.x == 0) a.dbg[stamp_i] = clock64(); ++stamp_i; } while (0)
-    STAMP();
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nb = (D + 3) >> 2, Dp = nb * 4;               // block rows of 4; rows >= D are identity padding
@@ -489,8 +489,6 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             }
     }
     __syncthreads();
-
-    STAMP();   // 1: init done
     const int npairs = N * (N + 1) / 2;
     const int npairs_cap = a.Ncap * (a.Ncap + 1) / 2;
     if (!kFull) {
@@ -629,8 +627,6 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         }
     }
     __syncthreads();
-
-    STAMP();   // 2: vision transform done
     // ---- IMU factors (bundle_adjustor.cpp:220-242): no loss
     if (kFull && inertial && H.n_imu > 0) {
         const int32_t *idx = a.imu_idx + (size_t)w * a.Ncap * 2;
@@ -782,8 +778,6 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             go[(compact ? __fns(freem, 0, fi + 1) : fi) * 15 + (i % stride)] = g[i];
         }
     }
-
-    STAMP();   // 3: factors done
     // ---- Jacobi scale, LM diagonal, constant blocks
     double *scale = a.pose_scale + (size_t)w * 15 * a.Ncap;
     double my_gdx = 0.0;
@@ -791,7 +785,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         const int f = i / stride, c = i - f * stride;
         const double hii = A[tri(i, i)] + hcorr[i];          // diagonal of the UNREDUCED J^T J
         double sc;
-        if (a.compute_scale) { sc = 1.0 / (1.0 + sqrt(fmax(hii, 0.0))); scale[i] = sc; }
+        if (compute_scale) { sc = 1.0 / (1.0 + sqrt(fmax(hii, 0.0))); scale[i] = sc; }
         else sc = scale[i];
         const double reg = mu > 0.0 ? lm_reg(hii, sc, mu) : 0.0;
         xs[i] = reg;                                          // keep reg for the scalars below
@@ -817,10 +811,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         xs[i] = -g[i];
     }
     __syncthreads();
-
-    STAMP();   // 4: scaling/masking done
     const bool ok = chol_solve_tiled(A, xs, nb, Linv, &flag_sm);
-    STAMP();   // 5: solve done
 
     // ---- outputs
     double *dxo = a.dx_pose + (size_t)w * a.Ncap * 15;
@@ -883,7 +874,8 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             ctrl.cost_vis = a.cost_vis[w];
             ctrl.cost = a.cost_vis[w] + cost_sm[1] + cost_sm[2] + cost_sm[3];
             ctrl.solve_failed = ok ? 0 : 1;
-            if (a.compute_scale) ctrl.have_scale = 1;
+            if (compute_scale) ctrl.have_scale = 1;
+            ctrl.fresh = 1;
         }
     }
 }
@@ -910,6 +902,16 @@ struct CostArgs {
     int Pcap, Tcap, Ocap, Ncap;
     int w0;
     double *out;                   // [W] non-vision candidate cost
+    // step acceptance (tail of the kernel)
+    WinCtrl *ctrl;
+    const double *acc;             // [W][kAcc] scalars of the sweeps
+    double *frames_state;          // [W][Ncap][16] accepted state (overwritten by the candidate on acceptance)
+    double *rho_state;             // [W][Mcap]
+    const double *rho_cand;
+    int Mcap;
+    int loop;                      // 1: tr_decide (device-side trust-region loop); 0: plain Gauss-Newton step, `apply` decides
+    int apply;
+    double beta;                   // loop == 0: the step was beta * dx_gn (model change of the truncated step)
 };
 
 static __global__ void aux_cost_kernel(CostArgs a) {
@@ -920,8 +922,11 @@ static __global__ void aux_cost_kernel(CostArgs a) {
     const double *fc = a.frames_cand + (size_t)w * a.Ncap * kFrameStride;
     const double *fcur = a.frames_cur + (size_t)w * a.Ncap * kFrameStride;
     __shared__ double acc;
+    __shared__ int accept_sm;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *r0 = reinterpret_cast<double *>(smem_raw);
+    WinCtrl &ctrl = a.ctrl[w];
+    if (a.loop && (ctrl.done || ctrl.skip)) { if (tid == 0) ctrl.fresh = 0; return; }
     if (tid == 0) acc = 0.0;
     __syncthreads();
     if (H.use_inertial) {
@@ -981,7 +986,30 @@ static __global__ void aux_cost_kernel(CostArgs a) {
         }
     }
     __syncthreads();
-    if (tid == 0) a.out[w] = acc;
+    // ---- step acceptance: what ceres does after evaluating the candidate (trust_region_minimizer.cc)
+    if (tid == 0) {
+        a.out[w] = acc;
+        const double *av = a.acc + (size_t)w * kAcc;
+        bool accept;
+        if (a.loop) accept = tr_decide(ctrl, av, acc);
+        else {
+            ctrl.cand_cost_vis = av[0];
+            ctrl.cand_cost = av[0] + acc;
+            const double gdx = ctrl.g_dot_dx + av[1];           // g . dx over poses + landmarks (full GN step)
+            const double rdx = ctrl.dx_reg_dx + av[2];          // dx^T (mu D) dx
+            // model cost change of the step beta * dx_gn:  -(beta g.dx + beta^2/2 dx^T H dx),
+            // with dx^T H dx = -g.dx - dx^T (mu D) dx for the regularised Gauss-Newton step
+            ctrl.model_change = -a.beta * gdx + 0.5 * a.beta * a.beta * (gdx + rdx);
+            accept = a.apply != 0;
+        }
+        accept_sm = accept ? 1 : 0;
+    }
+    __syncthreads();
+    if (accept_sm) {             // the candidate becomes the state
+        const int N = H.N, M = H.M;
+        for (int i = tid; i < N * kFrameStride; i += nt) a.frames_state[(size_t)w * a.Ncap * kFrameStride + i] = fc[i];
+        for (int i = tid; i < M; i += nt) a.rho_state[(size_t)w * a.Mcap + i] = a.rho_cand[(size_t)w * a.Mcap + i];
+    }
 }
 
 // |J v|^2 over the IMU / prior / plane blocks (loss-corrected), one CTA per window: the non-vision
@@ -990,7 +1018,7 @@ struct JvAuxArgs {
     CostArgs c;               // same inputs as aux_cost_kernel (frames_cand unused; frames_cur = current state)
     const double *v_pose;     // [W][Ncap][15]
     double *acc;              // [W][kAcc], slot 10
-};
+};  // c.loop != 0: runs only for windows whose GN step left the trust region, then picks the dogleg step (tr_after_jv)
 
 static __global__ void jv_aux_kernel(JvAuxArgs ja) {
     const CostArgs &a = ja.c;
@@ -1003,6 +1031,9 @@ static __global__ void jv_aux_kernel(JvAuxArgs ja) {
     __shared__ double acc;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *ev = reinterpret_cast<double *>(smem_raw);      // [15 n_prior] E v
+    WinCtrl &ctrl = a.ctrl[w];
+    if (a.loop && (ctrl.done || ctrl.skip)) return;
+    if (a.loop && !ctrl.need_jv) { if (tid == 0) tr_after_jv(ctrl, ja.acc + (size_t)w * kAcc); return; }
     if (tid == 0) acc = 0.0;
     __syncthreads();
     if (H.use_inertial) {
@@ -1067,7 +1098,11 @@ static __global__ void jv_aux_kernel(JvAuxArgs ja) {
         }
     }
     __syncthreads();
-    if (tid == 0 && acc != 0.0) atomicAdd(ja.acc + (size_t)w * kAcc + 10, acc);
+    if (tid == 0) {
+        double *av = ja.acc + (size_t)w * kAcc;
+        if (acc != 0.0) av[10] += acc;           // one CTA per window owns slot 10
+        if (a.loop) tr_after_jv(ctrl, av);
+    }
 }
 
 }  // namespace pvio

@@ -12,6 +12,8 @@ constexpr int kFrameStride = 16;    // doubles per frame state
 constexpr int kImuStride = 288;     // doubles per IMU factor record
 constexpr int kMaxChunks = 96;      // anchor-homogeneous chunks of <= 32 landmarks per window
 constexpr int kAcc = 16;            // doubles per window accumulated by the update / J.v sweeps
+constexpr int kMaxSeg = kMaxFrames * (kMaxFrames - 1) / 2;   // (target, anchor) segments of the frame-major table
+constexpr int kSegTab = 2 * (kMaxSeg + 1);                   // ints per window: seg_begin[kMaxSeg + 1], seg_row[kMaxSeg + 1]
 
 struct __align__(8) ObsRec {        // one reprojection residual block (non-anchor observation), 8 B
     float zx, zy;                   // normalised keypoint in the target frame
@@ -37,6 +39,15 @@ PVIO_HD unsigned lm_mask(int32_t meta) { return (unsigned)meta >> 16; }
 PVIO_HD int32_t lm_meta(int anchor, int victim, int n_obs, unsigned mask) {
     return (int32_t)((unsigned)anchor | ((unsigned)victim << 4) | ((unsigned)n_obs << 8) | (mask << 16));
 }
+
+// Frame-major observation table (built on the device from the landmark-major one, ba_fobs.cuh): the residual
+// blocks sorted by (target frame t, anchor frame a, landmark), segment sp = t (t - 1) / 2 + a.  A warp of the
+// linearise / update sweeps works on 32 consecutive entries of ONE segment ("row"), so the target frame is
+// warp-uniform (held in registers) and the per-(t, a) direct blocks are plain register sums.
+struct __align__(8) FObs { float zx, zy; };
+
+// per-landmark sums of the linearise sweep (H_ll, g_l), formed by the Schur kernel
+struct LmSum { double hll, gl; };
 
 struct WinHdr {                     // per-window integers
     int32_t N, M, K, use_inertial;
@@ -64,8 +75,14 @@ struct WinCtrl {                    // per-window solver state (device resident)
     double g_dot_dx, dx_reg_dx, gn_norm2, gmax, xnorm2, dxnorm2;
     double model_change;
     double grad2, v_reg_dx;         // |D^-1 S g|^2 and v^T (mu D) dx over the pose block (dogleg)
+    // device-side trust-region loop (ba_tr.cuh)
+    double step_a, step_b;          // step = step_b * dx_gn - step_a * v of the current iteration
+    double step_norm;               // its norm in the scaled space
+    double initial_cost;
+    double max_time_ns, t_start_ns; // solver_options.h:30; %globaltimer at the start of the solve
     int32_t iteration, accepted, done, termination;
-    int32_t solve_failed, have_scale, usable, pad;
+    int32_t solve_failed, have_scale, usable, reuse;   // reuse: the next iteration keeps linearisation and GN solve
+    int32_t need_jv, skip, max_iter, fresh;            // skip: the rest of this iteration's kernels do nothing
 };
 
 // per-landmark Schur scalars written by the linearise kernel, read by the update kernel

@@ -6,7 +6,7 @@ images.  Everything is seeded; seed 648 is the reference's own RNG seed (config.
 Returns (Window, State initial_guess, State truth).
 """
 import numpy as np
-from .window import Window, State
+from pvio_b200.window import Window, State
 from . import so3
 
 EUROC = dict(

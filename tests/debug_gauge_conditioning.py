@@ -4,7 +4,7 @@ uses the oracle."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from pvio_b200 import synth
+from synthetic import synth
 from pvio_b200.bundle_adjustor import BundleAdjustor
 from oracle import ba_oracle as bo
 np.set_printoptions(precision=3, linewidth=220)

@@ -6,7 +6,7 @@ tests/test_oracle_functors.py.  Run: python tests/golden/make_ba_golden.py"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from pvio_b200 import synth
+from synthetic import synth
 from oracle import ba_oracle as bo
 
 CASES = {

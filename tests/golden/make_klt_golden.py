@@ -5,7 +5,7 @@ import os, sys
 import numpy as np
 import cv2
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from pvio_b200 import synth
+from synthetic import synth
 
 prev, nxt, pts, truth = synth.make_klt_pair(seed=648, size=(256, 192), n_points=48)
 prev = prev.copy(); nxt = nxt.copy()

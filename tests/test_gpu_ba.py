@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import ba_oracle as bo
-from pvio_b200 import synth
+from synthetic import synth
 from pvio_b200.bundle_adjustor import BundleAdjustor
 
 pytestmark = pytest.mark.gpu
@@ -131,16 +131,11 @@ def test_gn_step_cfg4_planes(ba):
     _check_step(ba, w, st)
 
 
-@pytest.mark.parametrize("mode", ["fused", "tc", "split", "split_tc"])
 @pytest.mark.parametrize("case", ["cfg2", "cfg2b", "ragged", "cfg3", "cfg4", "cfg2_free", "cfg2_n16"])
-def test_throughput_kernels_match_oracle(case, mode, monkeypatch):
-    """Batches of >= 74 windows run the thread-per-landmark linearise kernels: lin_tpl_kernel (CUDA-core
-    Schur SYRK, the default) and, with PVIO_B200_TC=1 and windows of <= 10 frames, lin_tc_kernel (tcgen05
-    3xTF32 Schur SYRK).  Both against the oracle step on the same windows."""
-    # "split": Phase A (lin_tpl_kernel<.., false>) + schur_kernel streaming the records through a bulk-copy ring
-    # "split_tc": the same split with the Schur sum on the tensor cores (schur_tc_kernel)
-    monkeypatch.setenv("PVIO_B200_TC", {"tc": "1", "split_tc": "2"}.get(mode, "0"))
-    monkeypatch.setenv("PVIO_B200_SPLIT", "1" if mode in ("split", "split_tc") else "0")
+def test_throughput_kernels_match_oracle(case):
+    """Batches of >= 74 windows run one CTA per window in every sweep (no atomics across CTAs) and, for visual-only
+    windows, the lean solve kernel: the same pipeline as a single window, other launch shapes.  Against the oracle
+    step on the same windows."""
     if case == "cfg2":
         w, st, _ = synth.make_cfg2()
     elif case == "cfg2b":
@@ -151,7 +146,7 @@ def test_throughput_kernels_match_oracle(case, mode, monkeypatch):
         w, st, _ = synth.make_cfg3()
     elif case == "cfg4":
         w, st, _ = synth.make_cfg4()
-    elif case == "cfg2_n16":           # the largest window of the ABI: the tensor-core variants must fall back by themselves
+    elif case == "cfg2_n16":           # the largest window of the ABI
         w, st, _ = synth.make_cfg2(N=16, M=240, staggered=True, seed=12)
     else:
         w, st, _ = synth.make_cfg2(N=8, M=200, seed=31)
@@ -171,19 +166,16 @@ def test_throughput_kernels_match_oracle(case, mode, monkeypatch):
     tol = TOL_DX
     for i in (0, W - 1):
         e = _rel(dx[i], ref['dx'])
-        print(case, "mode", mode, "window", i, "dx rel err", e)
+        print(case, "window", i, "dx rel err", e)
         assert e < tol
         assert abs(costs[i, 0] - ref['cost']) <= 2e-6 * ref['cost']
     assert np.array_equal(dx[0], dx[W - 1])
 
 
-@pytest.mark.parametrize("split", ["1", "0"])
 @pytest.mark.parametrize("mixed_inertial", [False, True])
-def test_throughput_heterogeneous_batch(split, mixed_inertial, monkeypatch):
+def test_throughput_heterogeneous_batch(mixed_inertial):
     """One launch over windows of different sizes, anchors, visibility patterns and fixed-frame sets (and, in the
     second variant, visual-only and inertial windows side by side): every window against its own oracle step."""
-    monkeypatch.setenv("PVIO_B200_SPLIT", split)
-    monkeypatch.setenv("PVIO_B200_TC", "0")
     kinds = [synth.make_cfg2(N=10, M=120, seed=41)[:2], synth.make_cfg2(N=6, M=80, staggered=True, seed=42)[:2], _ragged_window()]
     w3, s3, _ = synth.make_cfg2(N=8, M=100, seed=43)
     w3.frame_fixed[:] = 0; w3.frame_fixed[0] = 1; w3.frame_fixed[5] = 1
@@ -275,8 +267,9 @@ def test_solve_matches_oracle_loop(ba, maker, kw):
     assert summ['iterations'] == ref_sum['iterations']
     assert abs(summ['final_cost'] - ref_sum['final_cost']) <= 1e-5 * ref_sum['final_cost']
     move = np.linalg.norm(ref_state.p - st.p)
-    assert np.linalg.norm(out.p - ref_state.p) < 2e-5 * max(move, 1e-3) + 1e-9
-    assert np.linalg.norm(out.rho - ref_state.rho) < 2e-5 * np.linalg.norm(ref_state.rho - st.rho) + 1e-9
+    print("state err", np.linalg.norm(out.p - ref_state.p) / max(move, 1e-3), np.linalg.norm(out.rho - ref_state.rho) / np.linalg.norm(ref_state.rho - st.rho))
+    assert np.linalg.norm(out.p - ref_state.p) < 1e-5 * max(move, 1e-3) + 1e-9
+    assert np.linalg.norm(out.rho - ref_state.rho) < 1e-5 * np.linalg.norm(ref_state.rho - st.rho) + 1e-9
     # post-pass flags are bit-exact, quality to fp tolerance
     valid, quality = bo.landmark_postpass(w, ref_state)
     assert np.array_equal(summ['valid'], valid)
@@ -324,7 +317,7 @@ def test_marginalize_then_solve_chain(ba):
     w2.prior_bg0, w2.prior_ba0 = st.bg[keep].copy(), st.ba[keep].copy()
     st2 = st.copy()
     st2.p[1:] += 1e-3
-    _check_step(ba, w2, st2, tol=5e-5)
+    _check_step(ba, w2, st2)
 
 
 def test_pipelined_host_step_matches_resident_step():
@@ -367,12 +360,18 @@ def test_golden_vectors(ba, name):
     g = np.load(_GOLD)
     w, st, _ = _CASES[name]()
     out = ba.gn_step(w, st, mu=1e-8, want_system=True)
-    tol = 1e-5 if name != "cfg3" else 5e-5      # 6-frame inertial windows are weakly conditioned
+    tol = TOL_DX
+    print(name, "dx", _rel(out["dx"], g[name + "_dx"]), "cost", abs(out["cost"] - float(g[name + "_cost"])) / float(g[name + "_cost"]),
+          "newcost", abs(out["new_cost"] - float(g[name + "_newcost"])) / max(float(g[name + "_newcost"]), 1.0),
+          )
     assert _rel(out["dx"], g[name + "_dx"]) < tol
     assert abs(out["cost"] - float(g[name + "_cost"])) < 2e-6 * float(g[name + "_cost"])
     assert abs(out["new_cost"] - float(g[name + "_newcost"])) < 5e-5 * max(float(g[name + "_newcost"]), 1.0)
-    P = 15 * w.N
-    assert np.max(np.abs(out["gred"] - g[name + "_gred"])) < 1e-5 * np.max(np.abs(g[name + "_gred"]))
+    # gradient of the FREE coordinates (constant blocks, FF_FIX_POSE, have none in ceres; the kernels skip their terms)
+    free = np.ones(15 * w.N, dtype=bool)
+    for f in np.nonzero(w.frame_fixed)[0]:
+        free[15 * f:15 * f + 6] = False
+    assert np.max(np.abs(out["gred"] - g[name + "_gred"])[free]) < 1e-5 * np.max(np.abs(g[name + "_gred"][free]))
     if name + "_margH" in g:
         S, e, Hm, bm = ba.marginalize_frame(w, st, 0, want_info=True)
         hs = np.maximum(np.sqrt(np.abs(np.diag(g[name + "_margH"]))), 1e-3)
@@ -400,8 +399,14 @@ def test_edge_cases_ragged_and_extreme_sizes(ba):
     _check_step(big, w, st)
     # (c) the reference's default window (10 + 1 frames, config.cpp) with IMU + prior: D = 165
     w, st, _ = synth.make_cfg3(N=11, M=200, seed=13)
-    _check_step(big, w, st, tol=5e-5)
+    _check_step(big, w, st)
     big.close()
+    # (c') 1500 landmarks: the Schur kernel's partial sums are flushed to fp64 in the middle of the window (every 11 slabs of
+    # 64 landmarks with 8 free frames), its two-slab ring is drained and refilled around the flush
+    wide = BundleAdjustor(max_windows=1, max_frames=10, max_landmarks=1500, max_obs=13500)
+    w, st, _ = synth.make_cfg2(N=10, M=1500, seed=14)
+    _check_step(wide, w, st)
+    wide.close()
     # (d) capacity overflow and malformed input are rejected, not truncated
     from pvio_b200.bundle_adjustor import PvioB200Error
     small = BundleAdjustor(max_windows=1, max_frames=4, max_landmarks=8, max_obs=16)
@@ -430,5 +435,58 @@ def test_solve_dogleg_and_rejections_match_oracle(ba):
               ref_sum['final_cost'], summ['final_cost'])
         assert summ['iterations'] == ref_sum['iterations']
         assert summ['accepted_steps'] == sum(ref_sum['accepted'])
-        assert abs(summ['final_cost'] - ref_sum['final_cost']) <= 1e-4 * ref_sum['final_cost']
-        assert np.linalg.norm(out.p - ref_state.p) < 2e-4 * max(np.linalg.norm(ref_state.p - st.p), 1e-3)
+        print('final cost rel', abs(summ['final_cost'] - ref_sum['final_cost']) / ref_sum['final_cost'], 'state', np.linalg.norm(out.p - ref_state.p) / max(np.linalg.norm(ref_state.p - st.p), 1e-3))
+        assert abs(summ['final_cost'] - ref_sum['final_cost']) <= 1e-5 * ref_sum['final_cost']
+        assert np.linalg.norm(out.p - ref_state.p) < 2e-5 * max(np.linalg.norm(ref_state.p - st.p), 1e-3)
+
+
+def test_batch_solve_matches_single_window_solve(ba):
+    """pvio_b200_batch_solve: the device-side trust-region loop over a batch with per-window termination gives every
+    window the result of its own pvio_b200_ba_solve (same kernels, same decisions), including a window that
+    converges early while the others keep iterating."""
+    kinds = [synth.make_cfg2(N=6, M=80, seed=51)[:2], synth.make_cfg2(N=5, M=40, seed=52)[:2], synth.make_cfg2(N=6, M=80, seed=53)[:2]]
+    # the second kind starts at the solution of a previous solve: it terminates after a step or two
+    s_conv, _ = ba.solve(*kinds[1], max_iterations=40)
+    kinds[1] = (kinds[1][0], s_conv)
+    singles = [ba.solve(w, st, max_iterations=7) for w, st in kinds]
+    W = 8
+    for i in range(W):
+        ba.batch_set(i, *kinds[i % 3])
+    ba.batch_upload(W)
+    ba.batch_solve(W, max_iterations=7)
+    frames, rho, sm = ba.batch_download_state(W, 6, 80)
+    for i in range(W):
+        w, st = kinds[i % 3]
+        ref_state, ref_sum = singles[i % 3]
+        assert sm[i]['iterations'] == ref_sum['iterations'] and sm[i]['termination'] == ref_sum['termination']
+        assert sm[i]['accepted_steps'] == ref_sum['accepted_steps']
+        assert abs(sm[i]['final_cost'] - ref_sum['final_cost']) <= 1e-9 * ref_sum['final_cost']
+        assert np.allclose(frames[i, :w.N, 4:7], ref_state.p, rtol=0, atol=1e-9)
+        assert np.allclose(rho[i, :w.M], ref_state.rho, rtol=1e-9, atol=0)
+    assert len({sm[i]['iterations'] for i in range(3)}) > 1        # the windows really stopped at different iterations
+
+
+def test_device_lie_group_helpers_across_taylor_branches(ba):
+    """expmap / logmap / right_jacobian / Plus ON THE DEVICE (csrc/ba_math.cuh) against the NumPy oracle (oracle/lie.py),
+    swept across the Taylor thresholds of geometry/lie_algebra.cpp:35-55 (angle ~ 1.2e-4 * 720^(1/4) = 6.3e-4,
+    1.2e-4 * 5040^(1/4) = 1.0e-3, 1.5e-8 * sqrt(24) = 7.3e-8, 1.5e-8 * sqrt(120) = 1.6e-7), angle 0, and angles up to pi."""
+    from oracle import lie
+    rng = np.random.default_rng(7)
+    angles = np.concatenate([[0.0], np.geomspace(1e-12, 1e-2, 60), [6.3e-4 * (1 + d) for d in (-1e-6, 0, 1e-6)],
+                             [1.028e-3 * (1 + d) for d in (-1e-4, 1e-4)], [7.3e-8, 1.63e-7],
+                             np.linspace(0.01, np.pi - 1e-3, 40), [np.pi - 1e-6, np.pi - 1e-9]])
+    axes = rng.standard_normal((len(angles), 3))
+    axes /= np.linalg.norm(axes, axis=1)[:, None]
+    wv = axes * angles[:, None]
+    out = ba.selftest_lie(wv)
+    for i, v in enumerate(wv):
+        q = lie.expmap(v)
+        assert np.allclose(out[i, 0:4], q, rtol=0, atol=1e-15), (i, angles[i])
+        assert np.allclose(out[i, 4:7], lie.logmap(q), rtol=1e-9, atol=1e-15), (i, angles[i])
+        J = lie.right_jacobian(v)
+        assert np.allclose(out[i, 7:16].reshape(3, 3), J, rtol=0, atol=1e-15), (i, angles[i])
+        assert np.allclose(out[i, 16:25].reshape(3, 3), np.linalg.inv(J), rtol=0, atol=1e-13), (i, angles[i])
+        assert np.allclose(out[i, 25:29], lie.quat_plus(q, v), rtol=0, atol=1e-15), (i, angles[i])
+    # log(exp(w)) = w away from the branch point, in particular just below pi
+    big = angles > 1e-6
+    assert np.allclose(out[big, 4:7], wv[big], rtol=1e-9, atol=1e-12)

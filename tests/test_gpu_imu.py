@@ -60,7 +60,7 @@ def test_preintegrate_batch_is_independent_of_order():
 def test_preintegrated_records_feed_the_ba_kernels():
     """cfg3 with its IMU records replaced by device-integrated ones: same GN step as with the host records."""
     from oracle import ba_oracle as bo
-    from pvio_b200 import synth
+    from synthetic import synth
     w, st, truth = synth.make_cfg3(N=6, M=100)
     ba = BundleAdjustor(max_windows=1, max_frames=8, max_landmarks=128, max_obs=1024)
     rec = imu.preintegrate(ba, truth.imu_factors, truth.imu_noise)

@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from oracle import klt_oracle as ko
-from pvio_b200 import synth, klt
+from pvio_b200 import klt
+from synthetic import synth
 from pvio_b200.bundle_adjustor import BundleAdjustor
 
 pytestmark = pytest.mark.gpu

@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from oracle import pnp_oracle as po
-from pvio_b200 import synth, pnp
+from pvio_b200 import pnp
+from synthetic import synth
 from pvio_b200.bundle_adjustor import BundleAdjustor
 
 pytestmark = pytest.mark.gpu

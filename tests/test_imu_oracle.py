@@ -4,7 +4,7 @@ package's own host mirror (pvio_b200.so3.PreIntegrator, written independently fo
 import numpy as np
 
 from oracle import imu_oracle, lie
-from pvio_b200 import so3
+from synthetic import so3
 
 COV = (np.eye(3) * 2.8791e-8, np.eye(3) * 4.0e-6, np.eye(3) * 3.7608e-10, np.eye(3) * 9.0e-6)
 

@@ -5,7 +5,7 @@ import pytest
 
 cv2 = pytest.importorskip("cv2")
 from oracle import klt_oracle as ko
-from pvio_b200 import synth
+from synthetic import synth
 
 
 def _cv(prev, nxt, pts, init):

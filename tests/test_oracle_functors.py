@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 from oracle import ba_oracle as bo
 from oracle import lie
-from pvio_b200 import synth
+from synthetic import synth
 
 EPS = 1e-6
 

@@ -1,7 +1,7 @@
 """Latency probe of the inertial single-window path (cfg3: 9 frames, 8 IMU factors, 120-dim prior)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pvio_b200 import synth
+from synthetic import synth
 from pvio_b200.bundle_adjustor import BundleAdjustor
 ba = BundleAdjustor(max_windows=1, max_frames=12, max_landmarks=640, max_obs=6000)
 w, st, _ = synth.make_cfg3()

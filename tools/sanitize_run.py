@@ -2,7 +2,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from pvio_b200 import synth, klt
+from pvio_b200 import klt
+from synthetic import synth
 from pvio_b200.bundle_adjustor import BundleAdjustor
 ba = BundleAdjustor(max_windows=80, max_frames=8, max_landmarks=96, max_obs=800)
 w, st, _ = synth.make_cfg2(N=6, M=70, staggered=True)
@@ -10,7 +11,7 @@ print('gn_step cfg2', np.linalg.norm(ba.gn_step(w, st)['dx']))
 for i in range(80):
     ba.batch_set(i, w, st)
 ba.batch_upload(80); ba.batch_gn_step(80, 1e-8, apply=True); dx, c = ba.batch_download(80, 15 * 6 + 70)
-print('batch 80 (tpl kernels + lean solve)', np.linalg.norm(dx[79]), c[0])
+print('batch 80 (one CTA per window + lean solve)', np.linalg.norm(dx[79]), c[0])
 w3, st3, _ = synth.make_cfg3(N=6, M=60)
 print('gn_step cfg3', np.linalg.norm(ba.gn_step(w3, st3)['dx']))
 w4, st4, _ = synth.make_cfg4(N=6, M=40, tracks_per_plane=20)
@@ -23,7 +24,7 @@ print('reproj err', ba.compute_reprojection_error(w, st))
 prev, nxt, pts, _ = synth.make_klt_pair(size=(160, 120), n_points=20)
 p, s_, e_ = klt.track_keypoints(ba, prev, nxt, pts)
 print('klt', int(s_.sum()))
-# newer kernels: PnP, IMU pre-integration, triangulation, tensor-core SYRK (self-test and opt-in lin kernel)
+# PnP, IMU pre-integration, triangulation, Lie self-test, batched device-side solve
 from pvio_b200 import pnp, imu, triangulate as tri
 d = synth.make_pnp()
 _, ps = pnp.visual_inertial_pnp(ba, d['frame'], d['last'], d['imu'], d['pts'], d['zs'], d['cam_q'], d['cam_p'], d['imu_q'], d['imu_p'], d['W'], True)
@@ -34,15 +35,8 @@ P = np.array([np.c_[np.eye(3), -np.array([0.3 * i, 0, 0])] for i in range(4)])  
 X = np.array([0.2, 0.1, 5.0])
 zz = np.array([(P[f] @ np.r_[X, 1])[:2] / (P[f] @ np.r_[X, 1])[2] for f in range(4)])
 print('tri', tri.triangulate(ba, P, [0, 4], [0, 1, 2, 3], zz)[0])
-import ctypes as C
-A = np.random.default_rng(0).standard_normal((200, 64)).astype(np.float32); D = np.zeros((64, 64))
-ba.lib.pvio_b200_selftest_syrk.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_double)]
-print('syrk', ba.lib.pvio_b200_selftest_syrk(ba.h, A.ctypes.data_as(C.POINTER(C.c_float)), 200, D.ctypes.data_as(C.POINTER(C.c_double))), D[0, 0])
-ba.close()
-os.environ['PVIO_B200_TC'] = '1'
-ba = BundleAdjustor(max_windows=80, max_frames=8, max_landmarks=96, max_obs=800)
-for i in range(80):
-    ba.batch_set(i, w, st)
-ba.batch_upload(80); ba.batch_gn_step(80, 1e-8, apply=False); dx2, _ = ba.batch_download(80, 15 * 6 + 70)
-print('batch 80 (tcgen05 lin kernel)', np.linalg.norm(dx2[79]))
+print('lie', np.linalg.norm(ba.selftest_lie(np.array([[0.1, 0.2, 0.3], [1e-9, 0, 0], [3.14159, 0, 0]]))))
+ba.batch_set(0, w, st); ba.batch_replicate(80); ba.batch_upload(80); ba.batch_solve(80, max_iterations=3)
+fr, rh, sm = ba.batch_download_state(80, w.N, w.M)
+print('batch solve', sm[0]['iterations'], sm[79]['final_cost'])
 ba.close()
