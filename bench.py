@@ -5,9 +5,15 @@ Metric: Gauss-Newton iterations/sec on the 10-keyframe x 500-landmark window (BA
 reprojection-only, frames 0 and 1 fixed, K_res = 4500).  One "step" = one full GN iteration
 (linearise all factors + Cauchy weights -> Schur-eliminate inverse depths -> solve the reduced
 system -> back-substitute -> Plus -> candidate cost) over a batch of W independent cfg2 windows
-per GPU; value = windows * iterations / second over all GPUs.  W = 4096 by default so the inputs
-(377 MB) exceed the 126 MB L2.  Single-window latency (the reference's one-solve-at-a-time use),
-the solve() call and KLT tracks/s are reported as extra keys of the same line.
+per GPU; value = windows * iterations / second over all GPUs, inputs resident in HBM, timed with CUDA events.
+W = 4096 by default so that the inputs exceed the 126 MB L2.
+
+e2e = the same metric through the reference-facing C-ABI call with HOST buffers
+(pvio_b200_batch_solve_host: pinned host staging -> device, the device-side trust-region solve of up to 10
+iterations per window, solved states back), host <-> device copies inside the timed region.
+
+Extra keys of the same line: the other BASELINE configurations with the CPU port timed beside them (single cfg3 / cfg4
+windows, marginalisation, literal config 5), single-window latency, a heterogeneous batch, KLT, PnP, IMU pre-integration.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--windows W]
 Multi-GPU: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N (one rank per GPU;
@@ -29,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "GN iters/sec on 10-KF x 500-landmark window (window-iterations/s)"
 UNIT = "window-iterations/s"
+WORKLOAD = "cfg2: 10 KF x 500 landmarks, K_res = 4500, reprojection-only Gauss-Newton, frames 0-1 fixed; independent windows"
 
 
 def bytes_alg(N, M, K, D):
@@ -90,41 +97,68 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def cpu_reference(win, st, n_sample, threads=0):
-    """The reference's CPU implementation of the path: oracle/ba_oracle.c (Ceres/Eigen are absent, so
-    the fp64 C restatement stands in, kind = "port"), independent windows over all host threads."""
+def pin_to_gpu_numa(local_rank):
+    """Run this rank (and the pinned staging it allocates from now on) on the CPUs of its GPU's NUMA node: the
+    host -> device copies of the end-to-end path then do not cross the socket interconnect."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        for line in out.splitlines():
+            f = line.replace("\x1b[4m", "").replace("\x1b[0m", "").split("\t")
+            if f and f[0].strip() == f"GPU{local_rank}":
+                cand = [x.strip() for x in f if x.strip() and all(c in "0123456789,-" for c in x.strip()) and ("-" in x or "," in x)]
+                if not cand:
+                    return None
+                cpus = set()
+                for part in cand[0].split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+                cpus &= os.sched_getaffinity(0)
+                if cpus:
+                    os.sched_setaffinity(0, cpus)
+                    return f"{cand[0]} ({len(cpus)} usable)"
+    except Exception:
+        return None
+    return None
+
+
+def cpu_rate(kind, win, st, n_sample, threads=0, **kw):
+    """The reference's CPU implementation of the path: oracle/ba_oracle.c (Ceres / Eigen are absent, so the fp64 C
+    restatement stands in, kind = "port"), n_sample independent windows over `threads` host threads (0: all usable)."""
     from oracle import c_oracle
-    c_oracle.gn_step_batch(win, st, 8, threads)          # warm-up / page-in
+    c_oracle.batch(kind, win, st, max(2, min(8, n_sample)), threads, **kw)          # warm-up / page-in
     t = time.perf_counter()
-    _, _, used = c_oracle.gn_step_batch(win, st, n_sample, threads)
+    used, units = c_oracle.batch(kind, win, st, n_sample, threads, **kw)
     dt = time.perf_counter() - t
-    return n_sample / dt, used, dt
+    return units / dt, used, dt, units
 
 
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return 0
+    from oracle import c_oracle
     from synthetic import synth
     win, st, _ = synth.make_cfg2()
-    ncpu = os.cpu_count() or 1
-    n_sample = max(64, min(args.windows, 128 * ncpu))     # ~10-30 s of CPU work in total over the run
+    cores = c_oracle.usable_cores()
+    # bounded sample: ~1 s of work per step on this box's cores (one window-iteration is ~0.8 ms on one core)
+    n_sample = int(max(64, min(args.windows, 1024 * max(1, cores // 8))))
     times = []
     for i in range(args.warmup + args.steps):
-        v, used, dt = cpu_reference(win, st, n_sample)
+        v, used, dt, units = cpu_rate("gn_step", win, st, n_sample)
         if i >= args.warmup:
             times.append(dt)
     tot = sum(times)
     value = n_sample * args.steps / tot
-    one, _, _ = cpu_reference(win, st, 32, threads=1)
+    one, _, _, _ = cpu_rate("gn_step", win, st, 32, threads=1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cfg2 (10 KF x 500 landmarks, K_res=4500, reprojection-only GN) x {n_sample} windows per step",
-                   "windows_per_step": n_sample},
+        "config": {"workload": WORKLOAD, "windows_per_step": n_sample,
+                   "note": "bounded sample of the same workload: independent cfg2 windows over every usable host core"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
-                         "sample": f"{n_sample} independent cfg2 window-iterations per step over all host threads; "
+                         "sample": f"{n_sample} independent cfg2 window-iterations per step over {used} host threads "
+                                   f"(usable cores: sched_getaffinity capped by the cgroup quota = {cores}); "
                                    "oracle/ba_oracle.c (fp64 restatement; Ceres/Eigen are not installed)",
                          "single_thread_value": one},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -133,8 +167,18 @@ def run_reference(args):
     return 0
 
 
+def time_call(fn, reps, warm=1):
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = fn()
+    return (time.perf_counter() - t0) / reps, out
+
+
 def run_gpu(args):
     rank, local_rank, world = dist_env()
+    numa = pin_to_gpu_numa(local_rank)
     import torch
     use_dist = world > 1
     if use_dist:
@@ -144,14 +188,21 @@ def run_gpu(args):
     from pvio_b200 import klt, pnp, imu
     from synthetic import synth
     from pvio_b200.bundle_adjustor import BundleAdjustor
+    from pvio_b200 import _lib as L
+    import ctypes as C
 
     W = args.windows
     win, st, _ = synth.make_cfg2()
     N, M, K = win.N, win.M, win.K
     D = 6 * int(np.sum(win.frame_fixed == 0))
-    stride = 15 * N + M
     ba = BundleAdjustor(device=local_rank, max_windows=W, max_frames=N, max_landmarks=512, max_obs=4608)
-    ba.batch_set(0, win, st)
+    # pack: the shim's per-window gather -> device layout in the pinned staging (host work, outside every timed region)
+    pa = L.PackedArgs(win, st)
+    n_pack = min(W, 256)
+    t0 = time.perf_counter()
+    for i in range(n_pack):
+        ba.lib.pvio_b200_batch_set_window(ba.h, i, C.byref(pa.cw), C.byref(pa.cs))
+    pack_us = (time.perf_counter() - t0) / n_pack * 1e6
     ba.batch_replicate(W)
     ba.batch_upload(W)
     ba.sync()
@@ -161,8 +212,22 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches0 = ba.kernel_launches
-    for _ in range(max(args.warmup, 3)):
+    def allmax(x):
+        if not use_dist:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if not use_dist:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         ba.batch_gn_step(W, 1e-8, apply=False)
     ba.sync()
     ba.last_kernel_ms(-1)
@@ -175,62 +240,98 @@ def run_gpu(args):
     ms = ba.timer_stop()
     barrier()
     launches = ba.kernel_launches - l0
-    lin_ms = ba.last_kernel_ms(1)
+    stage_ms, lin_ms, schur_ms = ba.last_kernel_ms(1), ba.last_kernel_ms(2), ba.last_kernel_ms(3)
     clocks = sampler.stop() if sampler else None
-    if use_dist:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
-        lt = torch.tensor([launches], device="cuda", dtype=torch.float64)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
-    else:
-        ms_max = ms
+    ms_max = allmax(ms)
+    launches = int(allsum(launches))
     value = world * W * args.steps / (ms_max * 1e-3)
 
-    # ---- end to end through the C-ABI with HOST buffers: H2D of the packed batch + step + D2H of dx
+    # ---- end to end through the C-ABI with HOST buffers: H2D of the packed batch + device-side solve + D2H of the states
+    fr_out = np.zeros((W, N * 16)); rho_out = np.zeros((W, M))
+    ba.batch_solve_host(W, N, M, max_iterations=10, frames=fr_out, rho=rho_out)
+    barrier()
+    e2e_steps = max(2, min(args.steps, 4))
+    t0 = time.perf_counter()
+    its = 0
+    for _ in range(e2e_steps):
+        _, _, sm = ba.batch_solve_host(W, N, M, max_iterations=10, frames=fr_out, rho=rho_out)
+        its += sum(x.iterations for x in sm)
+    e2e_s = allmax(time.perf_counter() - t0)
+    barrier()
+    e2e_value = allsum(its) / e2e_s
+    its_per_window = its / (e2e_steps * W)
+    # one GN iteration per upload (round 1's end-to-end figure, transfer-bound), for continuity
+    stride = 15 * N + M
     dx = np.zeros((W, stride)); costs = np.zeros((W, 2))
     ba.batch_gn_step_host(W, stride, 1e-8, dx, costs)
     barrier()
-    e2e_steps = max(2, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         ba.batch_gn_step_host(W, stride, 1e-8, dx, costs)
-    e2e_s = time.perf_counter() - t0
+    e2e1_s = allmax(time.perf_counter() - t0)
     barrier()
-    if use_dist:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * W * e2e_steps / e2e_s
+    e2e1_value = world * W * e2e_steps / e2e1_s
     h2d = W * (8 * 4608 + 16 * 512 + 8 * 512 + 8 * 16 * N + 832 + 224)
-    d2h = W * (8 * 15 * N + 8 * 512 + 168)
+    d2h = W * (8 * 16 * N + 8 * 512 + 216)
+
+    # ---- heterogeneous batch (5 window kinds: sizes, anchors, visibility, fixed sets differ), same GN step
+    kinds = [synth.make_cfg2(N=10, M=500, seed=41)[:2], synth.make_cfg2(N=10, M=420, staggered=True, seed=42)[:2],
+             synth.make_cfg2(N=8, M=300, seed=43)[:2], synth.make_cfg2(N=9, M=350, staggered=True, seed=44)[:2],
+             synth.make_cfg2(N=10, M=500, seed=45)[:2]]
+    kinds[2][0].frame_fixed[:] = 0; kinds[2][0].frame_fixed[0] = 1; kinds[2][0].frame_fixed[5] = 1
+    pas = [L.PackedArgs(w_, s_) for w_, s_ in kinds]
+    for i in range(W):
+        p_ = pas[i % len(pas)]
+        ba.lib.pvio_b200_batch_set_window(ba.h, i, C.byref(p_.cw), C.byref(p_.cs))
+    ba.batch_upload(W)
+    for _ in range(3):
+        ba.batch_gn_step(W, 1e-8, apply=False)
+    ba.sync(); ba.timer_start()
+    for _ in range(max(3, args.steps // 2)):
+        ba.batch_gn_step(W, 1e-8, apply=False)
+    het_ms = ba.timer_stop() / max(3, args.steps // 2)
+    barrier()
 
     if rank != 0:
+        # literal config 5 needs every rank (below); the other extras are rank 0's
+        run_cfg5(local_rank, rank, world, use_dist, allmax if use_dist else (lambda x: x))
         if use_dist:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (linearise + Schur), CUDA events around every launch
+    # ---- roofline of the dominant stage (linearise + Schur), CUDA events around every launch
     balg = bytes_alg(N, M, K, D)
     peak, peak_src = measured_peak()
-    achieved = balg * W / (lin_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "lin_schur_traffic.json")
+    achieved = balg * W / (stage_ms * 1e-3) / 1e9
+    traffic = warp_instr = None
+    counters_src = None
+    tp = os.path.join(ROOT, "profiles", "r02_stage_counters.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp))["dram_bytes_per_window"] * W
+            cj = json.load(open(tp))
+            traffic = cj["dram_bytes_per_window"] * W
+            warp_instr = cj["warp_instructions_per_window"]
+            counters_src = cj.get("source")
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "lin_a_kernel + schur_kernel (linearise + Schur stage, timed together)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_alg_per_window": balg, "windows_per_launch": W, "kernel_ms": lin_ms,
-                "kernel_share_of_step": lin_ms / (ms / args.steps),
-                "note": "algorithmic bytes / CUDA-event time of the stage (two launches: linearisation 0.49 ms, Schur sum 0.34 ms; SURVEY's byte figure covers both); DRAM traffic of the stage = 264 KB per window: 55 KB of inputs (8-byte observation records: below the 92 KB algorithmic figure), 65 KB of sqrt(w) h records written, 139 KB read back by the Schur kernel, 5 KB of outputs (a deliberate compute-for-bandwidth trade: the records also save the update kernel one linearisation per observation, and HBM is at 7 % while the SMs are latency-bound); "
-                        "arithmetic intensity ~33 flop/B is above the fp32 ridge (11.5 flop/B), so on CUDA cores the kernel is "
-                        "FP32-issue bound, see DESIGN.md 4.1"}
+            pass
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_frac = None
+    if warp_instr:
+        # issue-slot roofline: warp instructions issued / (SMs x 4 schedulers x clock x time)
+        issue_frac = warp_instr * W / (148 * 4 * sm_mhz * 1e6 * stage_ms * 1e-3)
+    roofline = {"bound": "hbm", "kernel": "lin_obs_kernel + schur_kernel (linearise + Schur stage, timed together)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "bytes_alg_per_window": balg, "windows_per_launch": W,
+                "kernel_ms": stage_ms, "linearise_ms": lin_ms, "schur_ms": schur_ms,
+                "kernel_share_of_step": stage_ms / (ms / args.steps),
+                "issue_slot_frac": issue_frac, "warp_instructions_per_window": warp_instr, "counters_source": counters_src,
+                "note": "achieved = algorithmic bytes (SURVEY 8d) / CUDA-event time of the stage measured in this run; "
+                        "issue_slot_frac = ncu-counted warp instructions of both kernels per window x windows / "
+                        "(148 SMs x 4 schedulers x SM clock x the same time): the stage is latency / issue bound, not HBM bound "
+                        "(arithmetic intensity ~33 flop/B, above the fp32 ridge) -- see DESIGN.md 4"}
 
-    # ---- single window: latency of one GN iteration and of a whole solve() through the C-ABI
+    # ---- single window, one at a time (the reference's real use): latency through the C-ABI
+    from oracle import c_oracle
     ba1 = BundleAdjustor(device=local_rank, max_windows=1, max_frames=N, max_landmarks=512, max_obs=4608)
     ba1.batch_set(0, win, st); ba1.batch_upload(1)
     for _ in range(5):
@@ -239,64 +340,56 @@ def run_gpu(args):
     for _ in range(50):
         ba1.batch_gn_step(1, 1e-8, apply=False)
     us_iter = ba1.timer_stop() * 1e3 / 50
-    ba1.solve(win, st, max_iterations=10)
-    t0 = time.perf_counter()
-    for _ in range(5):
-        _, summ = ba1.solve(win, st, max_iterations=10)
-    solve_ms = (time.perf_counter() - t0) * 1e3 / 5
-    single = {"gn_iters_per_s": 1e6 / us_iter, "us_per_iteration": us_iter, "solve_call_ms": solve_ms,
-              "solve_iterations": int(summ["iterations"]), "solve_iters_per_s_e2e": summ["iterations"] / (solve_ms * 1e-3)}
-    # the window a running VIO solves at every keyframe (cfg3: 9 frames, 8 IMU factors, 120-dim prior), one at a time
-    try:
-        w3, s3, _ = synth.make_cfg3()
-        ba3 = BundleAdjustor(device=local_rank, max_windows=1, max_frames=w3.N, max_landmarks=320, max_obs=2048)
-        ba3.solve(w3, s3, max_iterations=10)
-        t0 = time.perf_counter()
-        for _ in range(5):
-            _, summ3 = ba3.solve(w3, s3, max_iterations=10)
-        single["inertial_window_solve_call_ms"] = (time.perf_counter() - t0) * 1e3 / 5
-        single["inertial_window_iterations"] = int(summ3["iterations"])
-        single["inertial_window_device_ms"] = summ3["solve_seconds"] * 1e3
-        ba3.close()
-    except Exception as e:          # an extra, never allowed to take the headline line down
-        single["inertial_window_error"] = str(e)
+    solve_s, (_, summ) = time_call(lambda: ba1.solve(win, st, max_iterations=10), 20, warm=2)
+    cpu1 = time_call(lambda: c_oracle.solve(win, st, max_iter=10), 5)
+    single = {"gn_iters_per_s": 1e6 / us_iter, "us_per_iteration": us_iter, "solve_call_ms": solve_s * 1e3,
+              "solve_device_ms": summ["solve_seconds"] * 1e3, "solve_iterations": int(summ["iterations"]),
+              "solve_iters_per_s_e2e": summ["iterations"] / solve_s,
+              "cpu_port_solve_ms_1_thread": cpu1[0] * 1e3, "cpu_port_iterations": int(cpu1[1][2]["iterations"])}
+    ba1.close()
+
+    # ---- BASELINE configs 3 and 4 (inertial windows with prior / planes) and the marginaliser, CPU port beside the GPU
+    extras = {}
+    for name, maker in (("cfg3_inertial_prior", synth.make_cfg3), ("cfg4_planes", synth.make_cfg4)):
+        try:
+            w3, s3, _ = maker()
+            b3 = BundleAdjustor(device=local_rank, max_windows=1, max_frames=w3.N, max_landmarks=320, max_obs=2560)
+            ts, (_, sm3) = time_call(lambda: b3.solve(w3, s3, max_iterations=10), 50, warm=3)
+            worst = max(time_call(lambda: b3.solve(w3, s3, max_iterations=10), 1, warm=0)[0] for _ in range(50))
+            tc, cs = time_call(lambda: c_oracle.solve(w3, s3, max_iter=10), 5)
+            entry = {"N": int(w3.N), "M": int(w3.M), "K_res": int(w3.K), "gpu_solve_call_ms": ts * 1e3,
+                     "gpu_solve_call_ms_worst_of_50": worst * 1e3, "gpu_solve_device_ms": sm3["solve_seconds"] * 1e3,
+                     "iterations": int(sm3["iterations"]), "cpu_port_solve_ms_1_thread": tc * 1e3,
+                     "cpu_port_iterations": int(cs[2]["iterations"]), "speedup_vs_1_thread": tc / ts}
+            if name == "cfg3_inertial_prior":
+                tm, _ = time_call(lambda: b3.marginalize_frame(w3, s3, 0), 20, warm=2)
+                tcm, _ = time_call(lambda: c_oracle.marginalize(w3, s3, 0), 10)
+                extras["marginalize_frame"] = {"gpu_call_ms": tm * 1e3, "cpu_port_ms_1_thread": tcm * 1e3, "D": 15 * int(w3.N)}
+            b3.close()
+            extras[name] = entry
+        except Exception as e:          # an extra never takes the headline line down
+            extras[name] = {"error": str(e)}
+
+    # ---- literal BASELINE config 5: 8 independent cfg3 windows (seeds 648..655), window i -> GPU i mod G, full solves
+    cfg5 = run_cfg5(local_rank, rank, world, use_dist, allmax)
 
     # ---- KLT tracks/s (752x480, 500 points, 21x21, 4 levels) through the C-ABI with host images
     prev, nxt, pts, _ = synth.make_klt_pair()
-    klt.track_keypoints(ba1, prev, nxt, pts)
-    t0 = time.perf_counter()
-    for _ in range(20):
-        klt.track_keypoints(ba1, prev, nxt, pts)
-    klt_s = (time.perf_counter() - t0) / 20
+    kb = BundleAdjustor(device=local_rank, max_windows=1, max_frames=4, max_landmarks=8, max_obs=16)
+    klt_s, _ = time_call(lambda: klt.track_keypoints(kb, prev, nxt, pts), 20)
     klt_info = {"tracks_per_s_e2e": len(pts) / klt_s, "ms_per_frame_pair": klt_s * 1e3, "points": int(len(pts))}
-    # from the RAW frames: CLAHE(6, 8x8) on the device + pyramids + LK (OpenCvImage::preprocess + track_keypoints)
-    klt.track_keypoints(ba1, prev, nxt, pts, clahe_clip=6.0)
-    t0 = time.perf_counter()
-    for _ in range(20):
-        klt.track_keypoints(ba1, prev, nxt, pts, clahe_clip=6.0)
-    raw_s = (time.perf_counter() - t0) / 20
+    raw_s, _ = time_call(lambda: klt.track_keypoints(kb, prev, nxt, pts, clahe_clip=6.0), 20)
     klt_info["raw_frames_tracks_per_s_e2e"] = len(pts) / raw_s
     klt_info["raw_frames_ms_per_frame_pair"] = raw_s * 1e3
     try:
         import cv2
         crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
         p0 = pts.reshape(-1, 1, 2)
-        cv2.calcOpticalFlowPyrLK(prev, nxt, p0.copy(), p0.copy(), winSize=(21, 21), maxLevel=3, criteria=crit,
-                                 flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
-        t0 = time.perf_counter()
-        for _ in range(10):
-            cv2.calcOpticalFlowPyrLK(prev, nxt, p0.copy(), p0.copy(), winSize=(21, 21), maxLevel=3, criteria=crit,
-                                     flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
-        cv_s = (time.perf_counter() - t0) / 10
+        cv_call = lambda: cv2.calcOpticalFlowPyrLK(prev, nxt, p0.copy(), p0.copy(), winSize=(21, 21), maxLevel=3, criteria=crit,
+                                                   flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        cv_s, _ = time_call(cv_call, 10)
         klt_info["cv2_tracks_per_s"] = len(pts) / cv_s
         klt_info["cv2_threads"] = cv2.getNumThreads()
-        cl = cv2.createCLAHE(6.0, (8, 8))
-        t0 = time.perf_counter()
-        for _ in range(10):
-            a_, b_ = cl.apply(prev), cl.apply(nxt)
-            cv2.calcOpticalFlowPyrLK(a_, b_, p0.copy(), p0.copy(), winSize=(21, 21), maxLevel=3, criteria=crit,
-                                     flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
-        klt_info["cv2_raw_frames_tracks_per_s"] = len(pts) / ((time.perf_counter() - t0) / 10)
     except Exception as e:      # cv2 is the reference's KLT; report if it is unavailable
         klt_info["cv2_tracks_per_s"] = None
         klt_info["cv2_error"] = str(e)
@@ -304,72 +397,91 @@ def run_gpu(args):
     # ---- visual_inertial_pnp (150 points + IMU prior): one kernel launch per solve, host buffers in/out
     d = synth.make_pnp()
     pargs = (d['frame'], d['last'], d['imu'], d['pts'], d['zs'], d['cam_q'], d['cam_p'], d['imu_q'], d['imu_p'], d['W'], True)
-    _, psum = pnp.visual_inertial_pnp(ba1, *pargs)
-    t0 = time.perf_counter()
-    for _ in range(20):
-        _, psum = pnp.visual_inertial_pnp(ba1, *pargs)
-    pnp_info = {"ms_per_solve_e2e": (time.perf_counter() - t0) * 1e3 / 20, "kernel_ms": psum["solve_seconds"] * 1e3,
+    pnp_s, (_, psum) = time_call(lambda: pnp.visual_inertial_pnp(kb, *pargs), 20)
+    pnp_info = {"ms_per_solve_e2e": pnp_s * 1e3, "kernel_ms": psum["solve_seconds"] * 1e3,
                 "iterations": int(psum["iterations"]), "points": int(len(d['pts']))}
+    kb.close()
 
-    # ---- IMU pre-integration (PreIntegrator::integrate): 8 factors x 4096 windows, 40 samples each, host buffers in/out
-    rng = np.random.default_rng(648)
-    nf, ks = 32768, 40
-    tt = np.arange(ks) / 200.0
-    base = np.c_[tt, rng.normal(0, 0.3, (ks, 3)), rng.normal(0, 1.0, (ks, 3)) + np.array([0.0, 0.0, 9.81])]
-    factors = [(base, tt[-1] + 0.004, np.zeros(3), np.zeros(3))] * nf
-    noise = (np.eye(3) * 2.8791e-8, np.eye(3) * 4.0e-6, np.eye(3) * 3.7608e-10, np.eye(3) * 9.0e-6)
-    begin = np.arange(nf + 1, dtype=np.int32) * ks
-    samples = np.ascontiguousarray(np.tile(base, (nf, 1)))
-    t_end = np.full(nf, tt[-1] + 0.004); bias = np.zeros((nf, 6)); rec = np.zeros((nf, 288))
-    noise_a = np.ascontiguousarray(np.array([c.reshape(9) for c in noise]))
-    import ctypes as C
-    from pvio_b200 import _lib as L
-    fn = ba1.lib.pvio_b200_preintegrate
-    fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
-                   C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    call = lambda: fn(ba1.h, nf, L._ptr(begin, C.c_int32), L._ptr(samples, C.c_double), L._ptr(t_end, C.c_double),
-                      L._ptr(bias, C.c_double), L._ptr(noise_a, C.c_double), L._ptr(rec, C.c_double))
-    call()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        call()
-    imu_s = (time.perf_counter() - t0) / 3
-    from oracle import imu_oracle
-    t0 = time.perf_counter()
-    for _ in range(20):
-        imu_oracle.integrate(base, tt[-1] + 0.004, np.zeros(3), np.zeros(3), *noise)
-    imu_cpu = 20 / (time.perf_counter() - t0)
-    imu_info = {"factors_per_s_e2e": nf / imu_s, "factors": nf, "samples_per_factor": ks,
-                "numpy_oracle_factors_per_s_1core": imu_cpu}
-
-    # ---- CPU baseline beside it (bounded sample, all host threads; plus one thread like num_threads=1)
-    ncpu = os.cpu_count() or 1
-    n_sample = max(256, 128 * ncpu)
-    cpu_v, cpu_used, cpu_dt = cpu_reference(win, st, n_sample)
-    cpu_one, _, _ = cpu_reference(win, st, 64, threads=1)
+    # ---- CPU baseline beside it (bounded sample, all usable host cores; plus one thread like num_threads = 1)
+    cores = c_oracle.usable_cores()
+    n_sample = int(max(256, 1024 * max(1, cores // 8)))
+    cpu_v, cpu_used, cpu_dt, _ = cpu_rate("gn_step", win, st, n_sample)
+    cpu_one, _, _, _ = cpu_rate("gn_step", win, st, 64, threads=1)
+    cpu_solve_v, _, _, _ = cpu_rate("solve", win, st, max(64, n_sample // 8), max_iter=10)
     cpu_baseline = {"value": cpu_v, "unit": UNIT, "cores": cpu_used, "kind": "port",
-                    "sample": f"{n_sample} independent cfg2 window-iterations over all host threads "
-                              f"({cpu_dt:.2f} s wall); oracle/ba_oracle.c, fp64, Ceres/Eigen unavailable",
-                    "single_thread_value": cpu_one}
+                    "sample": f"{n_sample} independent cfg2 window-iterations over {cpu_used} host threads "
+                              f"({cpu_dt:.2f} s wall; usable cores = sched_getaffinity capped by the cgroup quota = {cores}); "
+                              "oracle/ba_oracle.c, fp64, Ceres/Eigen unavailable",
+                    "single_thread_value": cpu_one, "full_solve_value": cpu_solve_v}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 Jacobians + f64 residuals/accumulation/solve", "data": "synthetic",
-        "config": {"workload": f"cfg2 (10 KF x 500 landmarks, K_res=4500, reprojection-only GN, frames 0-1 fixed) x {W} "
-                               "independent windows per GPU per step",
-                   "windows_per_gpu": W, "l2_policy": f"device-resident inputs {(8 * K + 24 * M + 128 * N + 1056) * W / 1e6:.0f} MB + {(M // 32 + 1) * 32 * (6 * N + 2) * 4 * W / 1e6:.0f} MB of intermediate records per step exceed the 126 MB L2",
-                   "parallelism": f"independent windows, {world} GPU(s), no data-path collective"},
+        "dtype": "f32 Jacobians + f64 residuals/accumulation/solve (visual-only windows); f64 throughout for inertial windows",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "windows_per_gpu": W,
+                   "l2_policy": f"device-resident inputs {(8 * K + 24 * M + 128 * N + 1056) * W / 1e6:.0f} MB + "
+                                f"{(16 * K + 32 * 6 * K // 6) * W / 1e6:.0f} MB of intermediate records per step exceed the 126 MB L2",
+                   "parallelism": f"independent windows, {world} GPU(s), no data-path collective",
+                   "cpu_affinity": numa},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "note": "pvio_b200_batch_gn_step_host: pinned host buffers -> device, one GN iteration, dx back"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "single_window": single, "klt": klt_info, "pnp": pnp_info, "imu_preintegration": imu_info,
+                "iterations_per_upload": its_per_window, "pack_us_per_window": pack_us,
+                "one_iteration_per_upload_value": e2e1_value,
+                "note": "pvio_b200_batch_solve_host: pinned host staging -> device, device-side trust-region solve "
+                        "(<= 10 iterations per window, per-window termination), solved states back; "
+                        "pack_us_per_window (the shim-side gather into the staging, host) is outside the timed region"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "heterogeneous_batch": {"ms_per_step": het_ms, "window_iterations_per_s": W / (het_ms * 1e-3),
+                                "kinds": "5 window shapes (N 8-10, M 300-500, staggered anchors, non-contiguous fixed frames)"},
+        "single_window": single, "configs": extras, "config5_8_windows": cfg5, "klt": klt_info, "pnp": pnp_info,
     }
     print(json.dumps(line))
-    ba.close(); ba1.close()
+    ba.close()
     if use_dist:
         dist.destroy_process_group()
     return 0
+
+
+def run_cfg5(local_rank, rank, world, use_dist, allmax):
+    """BASELINE config 5 as written: 8 independent cfg3-shaped windows (seeds 648..655), window i -> GPU i mod G, a full
+    solve each; time = max over ranks of the host-buffer call (upload + device-side solves + download)."""
+    try:
+        from synthetic import synth
+        from pvio_b200.bundle_adjustor import BundleAdjustor
+        wins = [synth.make_cfg3(seed=648 + i)[:2] for i in range(8)]
+        mine = [wins[i] for i in range(8) if i % world == rank]
+        b5 = BundleAdjustor(device=local_rank, max_windows=len(mine), max_frames=9, max_landmarks=320, max_obs=2560)
+        for i, (w_, s_) in enumerate(mine):
+            b5.batch_set(i, w_, s_)
+        N5, M5 = 9, 320
+        b5.batch_solve_host(len(mine), N5, M5, max_iterations=10)
+        if use_dist:
+            import torch.distributed as dist
+            import torch
+            dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 10
+        its = 0
+        for _ in range(reps):
+            _, _, sm = b5.batch_solve_host(len(mine), N5, M5, max_iterations=10)
+            its += sum(x.iterations for x in sm)
+        dt = allmax((time.perf_counter() - t0) / reps)
+        b5.close()
+        out = {"windows": 8, "gpus": world, "ms_per_batch_e2e": dt * 1e3, "windows_per_s": 8 / dt,
+               "iterations_rank0": its / reps}
+        if rank == 0:
+            from oracle import c_oracle
+            t0 = time.perf_counter()
+            tot = 0
+            for w_, s_ in wins:
+                tot += c_oracle.solve(w_, s_, max_iter=10)[2]["iterations"]
+            t1 = time.perf_counter() - t0
+            out["cpu_port_ms_1_thread_8_windows"] = t1 * 1e3
+            out["cpu_port_iterations"] = int(tot)
+        return out
+    except Exception as e:
+        return {"error": str(e)}
 
 
 def main():

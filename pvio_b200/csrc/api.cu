@@ -361,7 +361,7 @@ static int upload_range(Handle *h, int w0, int n, cudaStream_t st) {
         TRY(h2d(h, h->pt_z, (size_t)h->Ocap * 2, w0, n, st));
     }
     FobsArgs fa;
-    fa.hdr = h->hdr.d; fa.obs = h->obs.d; fa.lms = h->lms.d; fa.fobs = h->fobs.d; fa.fobs_lm = h->fobs_lm.d; fa.seg = h->seg.d;
+    fa.hdr = h->hdr.d; fa.obs = h->obs.d; fa.lms = h->lms.d; fa.fobs = h->fobs.d; fa.seg = h->seg.d;
     fa.Mcap = h->Mcap; fa.Kcap = h->Kcap; fa.w0 = w0;
     fobs_build_kernel<<<n, 256, 0, st>>>(fa);
     ++h->launches;
@@ -439,7 +439,7 @@ static BatchShape batch_shape(Handle *h, int w0, int n, bool by_capacity) {
 static PipeArgs make_pipe_args(Handle *h, const StepCfg &c) {
     PipeArgs a;
     memset(&a, 0, sizeof(a));
-    a.hdr = h->hdr.d; a.cst = h->cst.d; a.fobs = h->fobs.d; a.fobs_lm = h->fobs_lm.d; a.seg = h->seg.d; a.lms = h->lms.d;
+    a.hdr = h->hdr.d; a.cst = h->cst.d; a.fobs = h->fobs.d; a.seg = h->seg.d; a.lms = h->lms.d;
     a.rho = h->rho.d; a.frames = h->frames.d; a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d;
     a.jr = h->jr.d; a.hs = h->hs.d; a.lm_w = h->lm_w.d; a.lm_msk = h->lm_msk.d;
     a.Hred = h->Hred.d; a.Hdd = h->Hdd.d; a.gdir = h->gdir.d; a.gred = h->gred.d; a.cost_vis = h->cost_vis.d;
@@ -460,7 +460,7 @@ static int sweep_grid_x(Handle *h, int n) { return n * 2 < h->sm_count ? 16 : 1;
 #define PVIO_SCHUR_BLOCKS 4
 #endif
 #ifndef PVIO_UPD_BLOCKS
-#define PVIO_UPD_BLOCKS 4
+#define PVIO_UPD_BLOCKS 8
 #endif
 constexpr int kLinWarps = 4, kLinBlocks = PVIO_LIN_BLOCKS;
 constexpr int kSchurThreads = 128, kSchurBlocks = PVIO_SCHUR_BLOCKS;
@@ -494,15 +494,15 @@ static int run_linearize(Handle *h, int n, const StepCfg &c, const BatchShape &b
     const bool dbl = h->hs_double;
     if (!dbl) {
         if (!loss) return fail(h, PVIO_B200_EINVAL, "the loss-free sweep runs in fp64");
-        lin_obs_kernel<true, float, kLinWarps, kLinBlocks><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<float>(b.N, Mp), st>>>(a);
+        lin_obs_kernel<true, float, kLinWarps, kLinBlocks><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<float>(b.N, Mp, kLinWarps), st>>>(a);
         LAUNCH_CK(h, "lin_obs_kernel<float>");
         if (gx > 1) { lm_finish_kernel<float><<<dim3((b.M + 127) / 128, n), 128, 0, st>>>(a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<float>"); }
         if (timed) CK(h, cudaEventRecord(h->kev[slot + 1], st));
         schur_kernel<float, kSchurThreads, kSchurBlocks><<<dim3(sgx, n), kSchurThreads, schur_launch_smem<float>(b.N, b.nfree), st>>>(a);
         LAUNCH_CK(h, "schur_kernel<float>");
     } else {
-        if (loss) lin_obs_kernel<true, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp), st>>>(a);
-        else lin_obs_kernel<false, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp), st>>>(a);
+        if (loss) lin_obs_kernel<true, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp, kLinWarps), st>>>(a);
+        else lin_obs_kernel<false, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp, kLinWarps), st>>>(a);
         LAUNCH_CK(h, "lin_obs_kernel<double>");
         if (gx > 1) { lm_finish_kernel<double><<<dim3((b.M + 127) / 128, n), 128, 0, st>>>(a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<double>"); }
         if (timed) CK(h, cudaEventRecord(h->kev[slot + 1], st));
@@ -566,7 +566,7 @@ static UpdArgs make_upd_args(Handle *h, const StepCfg &c) {
     memset(&u, 0, sizeof(u));
     u.hdr = h->hdr.d; u.cst = h->cst.d; u.obs = h->obs.d; u.lms = h->lms.d; u.rho = h->rho.d; u.frames = h->frames.d;
     u.ctrl = h->ctrl.d; u.lm_scale = h->lm_scale.d; u.lm_aux = h->lm_aux.d; u.hs = h->hs.d;
-    u.fobs = h->fobs.d; u.fobs_lm = h->fobs_lm.d; u.seg = h->seg.d; u.dx_pose = h->dx_pose.d;
+    u.fobs = h->fobs.d; u.seg = h->seg.d; u.dx_pose = h->dx_pose.d;
     u.rho_cand = h->rho_cand.d; u.frames_cand = h->frames_cand.d; u.dx_lm = h->dx_lm.d; u.lm_v = h->lm_v.d; u.acc = h->acc.d;
     u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.w0 = c.w0;
     u.step_a = 0.0; u.step_b = c.beta; u.v_pose = h->v_pose.d; u.loop = c.loop;
@@ -580,8 +580,8 @@ static int launch_update(Handle *h, int n, const StepCfg &c, const BatchShape &b
     const int Mp = (b.M + 31) & ~31;
     constexpr int kW = kMode == 1 ? 8 : kUpdWarps;
     constexpr int kB = kMode == 1 ? 2 : 4, kBf = kMode == 1 ? 2 : kUpdBlocks;
-    if (!h->hs_double) update_obs_kernel<true, float, kW, kBf, kMode><<<dim3(gx, n), kW * 32, upd_smem_bytes<float>(b.N, Mp), st>>>(u);
-    else update_obs_kernel<true, double, kW, kB, kMode><<<dim3(gx, n), kW * 32, upd_smem_bytes<double>(b.N, Mp), st>>>(u);
+    if (!h->hs_double) update_obs_kernel<true, float, kW, kBf, kMode><<<dim3(gx, n), kW * 32, upd_smem_bytes<float>(b.N, Mp, kW), st>>>(u);
+    else update_obs_kernel<true, double, kW, kB, kMode><<<dim3(gx, n), kW * 32, upd_smem_bytes<double>(b.N, Mp, kW), st>>>(u);
     ++h->launches;
     LAUNCH_CK(h, "update_obs_kernel");
     return 0;
@@ -765,7 +765,7 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     const size_t W = h->W, N = h->Ncap, M = h->Mcap, K = h->Kcap, npc = N * (N + 1) / 2;
     TRY(alloc(h, h->hdr, W, true)); TRY(alloc(h, h->cst, W, true));
     TRY(alloc(h, h->obs, W * K, true)); TRY(alloc(h, h->lms, W * M, true));
-    TRY(alloc(h, h->fobs, W * K, false)); TRY(alloc(h, h->fobs_lm, W * K, false)); TRY(alloc(h, h->seg, W * kSegTab, false));
+    TRY(alloc(h, h->fobs, W * K, false)); TRY(alloc(h, h->seg, W * kSegTab, false));
     TRY(alloc(h, h->rho, W * M, true)); TRY(alloc(h, h->frames, W * N * kFrameStride, true));
     TRY(alloc(h, h->ctrl, W, true));
     TRY(alloc(h, h->rho_cand, W * M, false)); TRY(alloc(h, h->frames_cand, W * N * kFrameStride, false));
@@ -824,7 +824,7 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     klt_free(h);
     marg_free(h);
     release(h->hdr); release(h->cst); release(h->obs); release(h->lms); release(h->rho); release(h->frames);
-    release(h->fobs); release(h->fobs_lm); release(h->seg); release(h->jr); release(h->lm_w); release(h->lm_msk); release(h->frames_out); release(h->rho_out); release(h->lm_v); release(h->valid); release(h->quality);
+    release(h->fobs); release(h->seg); release(h->jr); release(h->lm_w); release(h->lm_msk); release(h->frames_out); release(h->rho_out); release(h->lm_v); release(h->valid); release(h->quality);
     release(h->ctrl); release(h->rho_cand); release(h->frames_cand); release(h->lm_scale); release(h->lm_aux); release(h->hs);
     release(h->dx_lm); release(h->dx_pose); release(h->pose_scale); release(h->v_pose); release(h->Hred);
     release(h->acc); release(h->aux_cost);

@@ -38,7 +38,6 @@ struct Handle {
     DevBuf<WinConst> cst;
     DevBuf<ObsRec> obs;                          // landmark-major table as the shim gathers it (uploaded)
     DevBuf<FObs> fobs;                           // frame-major table, built on the device after every upload
-    DevBuf<uint16_t> fobs_lm;
     DevBuf<int32_t> seg;                         // [W][kSegTab]
     DevBuf<LmRec> lms;
     DevBuf<double> rho, frames;

@@ -14,7 +14,6 @@ struct FobsArgs {
     const ObsRec *obs;        // [W][Kcap] landmark-major
     const LmRec *lms;         // [W][Mcap]
     FObs *fobs;               // [W][Kcap] frame-major
-    uint16_t *fobs_lm;        // [W][Kcap] packed landmark index of each entry
     int32_t *seg;             // [W][kSegTab]: seg_begin[sp], then seg_row[sp] (rows of 32 before segment sp)
     int Mcap, Kcap;
     int w0;
@@ -77,7 +76,6 @@ __global__ void __launch_bounds__(256) fobs_build_kernel(FobsArgs a) {
     }
     __syncthreads();
     FObs *fo = a.fobs + (size_t)w * a.Kcap;
-    uint16_t *fl = a.fobs_lm + (size_t)w * a.Kcap;
     for (int ch = wv; ch < nch; ch += 8) {
         const int c = H.chunk_meta[ch] & 0xff;
         const int l = H.chunk_begin[ch] + lane;
@@ -90,8 +88,9 @@ __global__ void __launch_bounds__(256) fobs_build_kernel(FobsArgs a) {
             if ((m >> t) & 1u) {
                 const int pos = cnt[ch][t] + __popc(b & ((1u << lane) - 1u));
                 const ObsRec o = obs[lr.obs_begin + __popc(m & ((1u << t) - 1u))];
-                fo[pos].zx = o.zx; fo[pos].zy = o.zy;
-                fl[pos] = (uint16_t)l;
+                FObs rec;
+                rec.zx = o.zx; rec.zy = o.zy; rec.lm = l; rec.pad = 0;
+                fo[pos] = rec;
             }
         }
     }

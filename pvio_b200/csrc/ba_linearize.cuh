@@ -34,7 +34,6 @@ struct PipeArgs {
     const WinHdr *hdr;
     const WinConst *cst;
     const FObs *fobs;            // [W][Kcap] frame-major residual blocks
-    const uint16_t *fobs_lm;     // [W][Kcap]
     const int32_t *seg;          // [W][kSegTab]
     const LmRec *lms;            // [W][Mcap]
     const double *rho;           // [W][Mcap]
@@ -195,6 +194,31 @@ __device__ __constant__ signed char kQSlot[32] = {0, 1, 2, 3, 4, 5, -1, 6, 7, 8,
 // strictly-lower pair index (t > a)
 __device__ __forceinline__ int spair(int t, int a) { return t * (t - 1) / 2 + a; }
 
+constexpr int kRing = 4;                        // rows of the frame-major table in flight per warp (cp.async ring)
+
+// Walks the rows of a warp: row r lies in segment sp = (t, an), its first table entry is k0()
+struct RowCursor {
+    const int32_t *sbeg, *srow;
+    int r, sp, t, an, rows;
+    __device__ __forceinline__ RowCursor(const int32_t *sb, const int32_t *sr, int r0, int n_rows)
+        : sbeg(sb), srow(sr), r(r0), sp(0), t(1), an(0), rows(n_rows) { seek(); }
+    __device__ __forceinline__ void seek() { if (r < rows) while (srow[sp + 1] <= r) { ++sp; if (++an == t) { ++t; an = 0; } } }
+    __device__ __forceinline__ void advance() { ++r; seek(); }
+    __device__ __forceinline__ int k0() const { return sbeg[sp] + (r - srow[sp]) * 32; }
+};
+
+// request row pf.r (if the warp owns it) into `dst` (32 entries) and move the prefetch cursor on; one commit group per
+// call, empty or not, so that the consumer's wait_group count stays uniform
+__device__ __forceinline__ void row_prefetch(RowCursor &pf, int r_end, const FObs *fobs, FObs *dst, int lane) {
+    if (pf.r < r_end) {
+        const int k = pf.k0() + lane;
+        if (k < pf.sbeg[pf.sp + 1])
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst + lane)), "l"(fobs + k) : "memory");
+        pf.advance();
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // Per-landmark completion of the linearise sweep (thread per landmark; in the epilogue of lin_obs_kernel when one
 // CTA owns the window, as lm_finish_kernel otherwise): H_ll = sum j.j and g_l = sum j.r over the landmark's
 // residual blocks in frame order (deterministic), Jacobi scale, w_l = 1 / (H_ll + mu clamp(.)) -- the pivot the
@@ -274,24 +298,26 @@ __global__ void __launch_bounds__(128) lm_finish_kernel(PipeArgs a) {
 }
 
 template <typename real>
-__host__ __device__ inline size_t lin_smem_layout(int N, int Mp, size_t *o_dta, size_t *o_seg, size_t *o_x, size_t *o_cl,
-                                                  size_t *o_skip) {
+__host__ __device__ inline size_t lin_smem_layout(int N, int Mp, int warps, size_t *o_dta, size_t *o_seg, size_t *o_x, size_t *o_cl,
+                                                  size_t *o_skip, size_t *o_ring) {
     const size_t nsp = (size_t)N * (N - 1) / 2;
     size_t off = sizeof(double) * 12 * (size_t)N;                              // frames: Rwc[9], c[3]
-    *o_dta = off; off += sizeof(double) * ((nsp + 1) * kDta + 8);              // direct blocks, cost
+    *o_dta = off; off += sizeof(double) * ((nsp + 1 + (size_t)N) * kDta + 8);  // direct blocks (pairs, then per frame), cost
     *o_x = off; off += sizeof(double) * 3 * (size_t)Mp;                        // world points (SoA)
     *o_seg = off; off += sizeof(int32_t) * kSegTab;
     off = (off + 15) & ~(size_t)15;
     *o_cl = off; off += sizeof(real) * 6 * (size_t)Mp;                         // d x / d rho and (real) x (SoA)
     off += sizeof(real) * 12 * (size_t)N;                                      // (real) Rwc of every frame
     *o_skip = off; off += (size_t)Mp;                                          // 1: landmark not linearised
-    return (off + 15) & ~(size_t)15;
+    off = (off + 15) & ~(size_t)15;
+    *o_ring = off; off += sizeof(FObs) * kRing * 32 * (size_t)warps;           // per-warp ring of table rows
+    return off;
 }
 
 template <typename real>
-__host__ __device__ inline size_t lin_smem_bytes(int N, int Mp) {
-    size_t a, b, c, d, e;
-    return lin_smem_layout<real>(N, Mp, &a, &b, &c, &d, &e);
+__host__ __device__ inline size_t lin_smem_bytes(int N, int Mp, int warps) {
+    size_t a, b, c, d, e, f;
+    return lin_smem_layout<real>(N, Mp, warps, &a, &b, &c, &d, &e, &f);
 }
 
 template <bool kLoss, typename real, int kWarps, int kMinBlocks>
@@ -309,11 +335,12 @@ lin_obs_kernel(PipeArgs a) {
     const int nsp = N * (N - 1) / 2;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    size_t o_dta, o_seg, o_x, o_cl, o_skip;
-    lin_smem_layout<real>(N, Mp, &o_dta, &o_seg, &o_x, &o_cl, &o_skip);
+    size_t o_dta, o_seg, o_x, o_cl, o_skip, o_ring;
+    lin_smem_layout<real>(N, Mp, kWarps, &o_dta, &o_seg, &o_x, &o_cl, &o_skip, &o_ring);
     double *Fs = reinterpret_cast<double *>(smem_raw);                       // [N][12]
     double *Dta = reinterpret_cast<double *>(smem_raw + o_dta);              // [nsp + 1][kDta]
-    double *cost_sm = Dta + (nsp + 1) * kDta;                                // [8]
+    double *Ddg = Dta + (nsp + 1) * kDta;                                    // [N][kDta] sum of the blocks touching frame f (signed gradient)
+    double *cost_sm = Ddg + N * kDta;                                        // [8]
     double *xs = reinterpret_cast<double *>(smem_raw + o_x);                 // [3][Mp]
     int32_t *sg = reinterpret_cast<int32_t *>(smem_raw + o_seg);             // seg_begin | seg_row
     real *cls = reinterpret_cast<real *>(smem_raw + o_cl);                   // [3][Mp] d x / d rho, [3][Mp] (real) x
@@ -330,7 +357,7 @@ lin_obs_kernel(PipeArgs a) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) Rs[tid * 12 + i] = (real)f.Rwc[i];
     }
-    for (int i = tid; i < (nsp + 1) * kDta + 8; i += kThreads) Dta[i] = 0.0;
+    for (int i = tid; i < (nsp + 1 + N) * kDta + 8; i += kThreads) Dta[i] = 0.0;
     for (int i = tid; i < kSegTab; i += kThreads) sg[i] = a.seg[(size_t)w * kSegTab + i];
     __syncthreads();
 
@@ -366,7 +393,6 @@ lin_obs_kernel(PipeArgs a) {
     const real W[4] = {(real)wc.sic[0], (real)wc.sic[1], (real)wc.sic[2], (real)wc.sic[3]};
     const real cb = (real)(wc.cauchy_a * wc.cauchy_a), inv_cb = (real)(1.0 / (wc.cauchy_a * wc.cauchy_a));
     const FObs *fobs = a.fobs + (size_t)w * a.Kcap;
-    const uint16_t *flm = a.fobs_lm + (size_t)w * a.Kcap;
     real *hs = reinterpret_cast<real *>(a.hs) + (size_t)w * a.Ncap * a.Mcap * 6;
     real2 *jr = reinterpret_cast<real2 *>(a.jr) + (size_t)w * a.Ncap * a.Mcap;
     const unsigned fixed = (unsigned)H.fixed_mask & ((1u << N) - 1u);
@@ -375,12 +401,12 @@ lin_obs_kernel(PipeArgs a) {
     const int nwt = gridDim.x * kWarps, wid = blockIdx.x * kWarps + wv;
     const int r_begin = (int)((long long)rows * wid / nwt), r_end = (int)((long long)rows * (wid + 1) / nwt);
 
+    RowCursor cs(sbeg, srow, r_begin, rows);
     real cost_acc = 0;
-    int sp = 0, t = 1, an = 0;                                   // segment of the current row
-    for (int r = r_begin; r < r_end;) {
-        while (srow[sp + 1] <= r) { ++sp; if (++an == t) { ++t; an = 0; } }
+    while (cs.r < r_end) {
+        const int sp = cs.sp, t = cs.t, an = cs.an;
         const int seg_end = sbeg[sp + 1];
-        const int r_stop = min(r_end, srow[sp + 1]);
+        const int r_stop = min(min(r_end, srow[sp + 1]), cs.r + 64);      // pieces of <= 64 rows: <= 64 terms per thread in `real`
         const bool need = (((fixed >> t) & (fixed >> an)) & 1u) == 0u;    // both blocks constant: only H_ll, g_l, cost
         FrameR<real> F;
         {
@@ -396,19 +422,28 @@ lin_obs_kernel(PipeArgs a) {
         real2 q[15];
 #pragma unroll
         for (int i = 0; i < 15; ++i) q[i] = mk2((real)0, (real)0);
-        // the table entries of the NEXT row are requested before the current row is evaluated
-        int k = sbeg[sp] + (r - srow[sp]) * 32 + lane;
+        // one reduction per (warp, segment piece); the cross-lane sum runs in fp64: lane e ends up with entry e of the 30 sums
+        auto flush_q = [&]() {
+            double qq[32];
+#pragma unroll
+            for (int i = 0; i < 15; ++i) { qq[2 * i] = (double)q[i].x; qq[2 * i + 1] = (double)q[i].y; q[i] = mk2((real)0, (real)0); }
+            qq[30] = 0.0; qq[31] = 0.0;
+            const double tot = transpose_reduce<double>(qq, lane);
+            const int e = kQSlot[lane];
+            if (e >= 0) atomicAdd(&Dta[sp * kDta + e], tot);          // +sum Y^T Y, Y^T r; the epilogue applies the signs
+        };
+        // the table entry of the NEXT row is requested before the current row is evaluated
+        int k = cs.k0() + lane;
         FObs o_nx;
-        o_nx.zx = 0.f; o_nx.zy = 0.f;
-        int l_nx = 0;
-        if (k < seg_end) { o_nx = fobs[k]; l_nx = flm[k]; }
-        for (; r < r_stop; ++r) {
+        o_nx.zx = 0.f; o_nx.zy = 0.f; o_nx.lm = 0; o_nx.pad = 0;
+        if (k < seg_end) o_nx = fobs[k];
+        for (; cs.r < r_stop; cs.advance()) {
             const FObs o = o_nx;
-            const int l = l_nx;
             const bool valid = k < seg_end;
             k += 32;
-            if (r + 1 < r_stop && k < seg_end) { o_nx = fobs[k]; l_nx = flm[k]; }
+            if (cs.r + 1 < r_stop && k < seg_end) o_nx = fobs[k];
             if (valid) {
+                const int l = o.lm;
                 if (!skip[l]) {
                     ObsL<real> ol;
                     linearize_blk<kLoss, real>(F, xs[l], xs[Mp + l], xs[2 * Mp + l], cls[3 * Mp + l], cls[4 * Mp + l],
@@ -443,15 +478,7 @@ lin_obs_kernel(PipeArgs a) {
                 }
             }
         }
-        if (need) {      // one reduction per (warp, segment): lane e ends up with entry e of the 30 sums
-            real qq[32];
-#pragma unroll
-            for (int i = 0; i < 15; ++i) { qq[2 * i] = q[i].x; qq[2 * i + 1] = q[i].y; }
-            qq[30] = (real)0; qq[31] = (real)0;
-            const real tot = transpose_reduce<real>(qq, lane);
-            const int slot = kQSlot[lane];
-            if (slot >= 0) atomicAdd(&Dta[sp * kDta + slot], (double)tot);       // +sum Y^T Y; the epilogue applies the signs
-        }
+        if (need) flush_q();
     }
 
     // ---- epilogue
@@ -466,41 +493,38 @@ lin_obs_kernel(PipeArgs a) {
         const int compute_scale = a.loop ? (a.ctrl[w].have_scale == 0) : a.compute_scale;
         for (int l = tid; l < ((M + 3) & ~3); l += kThreads) lm_finish<real>(a, w, l, N, M, fixed, mu, compute_scale);
     }
-    // direct part of the reduced system (schur_kernel subtracts the Schur sum from Hred / gred):
-    // Hdir[t,t] += D(t,a), Hdir[a,a] += D(t,a), Hdir[t,a] = -D(t,a);  g[t] += d(t,a), g[a] -= d(t,a)
+    // direct part of the reduced system (schur_kernel subtracts the Schur sum from Hred / gred).  D(t, a) enters the
+    // off-diagonal block (t, a) with a minus sign and BOTH diagonal blocks with a plus sign; its gradient part enters
+    // g[t] with a plus and g[a] with a minus sign: first the per-frame sums (thread per (frame, entry)), then the copies
+    for (int e = tid; e < N * kDta; e += kThreads) {
+        const int f = e / kDta, v = e - f * kDta;
+        double d = 0.0;
+        for (int g = 0; g < f; ++g) d += Dta[spair(f, g) * kDta + v];                       // f is the target
+        for (int g = f + 1; g < N; ++g) { const double x = Dta[spair(g, f) * kDta + v]; d += v < 21 ? x : -x; }   // f is the anchor
+        Ddg[e] = d;
+    }
+    __syncthreads();
     const int npairs_cap = a.Ncap * (a.Ncap + 1) / 2;
     double *Hred_o = a.Hred + (size_t)w * npairs_cap * 36;
     double *Hdd_o = a.Hdd + (size_t)w * a.Ncap * 36;
     double *gdir_o = a.gdir + (size_t)w * a.Ncap * 6;
     double *gred_o = a.gred + (size_t)w * a.Ncap * 6;
-    for (int e = tid; e < N * 36; e += kThreads) {                  // diagonal blocks: sum of the pair blocks touching f
+    for (int e = tid; e < N * 36; e += kThreads) {                  // diagonal blocks
         const int f = e / 36, ij = e - f * 36, i = ij / 6, j = ij - i * 6;
-        const int se = i <= j ? sym6(i, j) : sym6(j, i);
-        double d = 0.0;
-        for (int g = 0; g < N; ++g) {
-            if (g == f) continue;
-            d += Dta[(f > g ? spair(f, g) : spair(g, f)) * kDta + se];
-        }
+        const double d = Ddg[f * kDta + (i <= j ? sym6(i, j) : sym6(j, i))];
         if (exclusive) { Hdd_o[e] = d; Hred_o[pair_idx(f, f) * 36 + ij] = d; }
         else if (d != 0.0) { atomicAdd(&Hdd_o[e], d); atomicAdd(&Hred_o[pair_idx(f, f) * 36 + ij], d); }
     }
     for (int e = tid; e < nsp * 36; e += kThreads) {                // off-diagonal blocks (f > g): -D(f, g)
-        const int s = e / 36, ij = e - s * 36, i = ij / 6, j = ij - i * 6;
+        const int sq = e / 36, ij = e - sq * 36, i = ij / 6, j = ij - i * 6;
         int f = 1;
-        while ((f + 1) * f / 2 <= s) ++f;
-        const int g = s - f * (f - 1) / 2;
-        const int se = i <= j ? sym6(i, j) : sym6(j, i);
-        const double v = -Dta[s * kDta + se];
+        while ((f + 1) * f / 2 <= sq) ++f;
+        const int g = sq - f * (f - 1) / 2;
+        const double v = -Dta[sq * kDta + (i <= j ? sym6(i, j) : sym6(j, i))];
         if (exclusive) Hred_o[pair_idx(f, g) * 36 + ij] = v; else if (v != 0.0) atomicAdd(&Hred_o[pair_idx(f, g) * 36 + ij], v);
     }
-    for (int e = tid; e < N * 6; e += kThreads) {                   // gradients (f is the target when f > g)
-        const int f = e / 6, i = e - f * 6;
-        double d = 0.0;
-        for (int g = 0; g < N; ++g) {
-            if (g == f) continue;
-            const double v = Dta[(f > g ? spair(f, g) : spair(g, f)) * kDta + 21 + i];
-            d += (f > g) ? v : -v;
-        }
+    for (int e = tid; e < N * 6; e += kThreads) {                   // gradients
+        const double d = Ddg[(e / 6) * kDta + 21 + e % 6];
         if (exclusive) { gdir_o[e] = d; gred_o[e] = d; }
         else if (d != 0.0) { atomicAdd(&gdir_o[e], d); atomicAdd(&gred_o[e], d); }
     }

@@ -231,13 +231,16 @@ schur_kernel(PipeArgs a) {
             const real2 *wv = slot_w(i & 1);
             const real *buf = slot_h(i & 1);
             const real *pf = buf + (size_t)fi * FS, *pg0 = buf + (size_t)(2 * gp) * FS, *pg1 = buf + (size_t)gi1 * FS;
-            for (int s = kk; s < cnt; s += nsub) {
-                const int m = mk[s];
-                if ((((m >> bf) & 1) & ((m >> bg0) | (m >> bg1))) == 0) continue;
-                const real2 ws = wv[s];
-                const real2 *hf = reinterpret_cast<const real2 *>(pf + s * 6);
-                const real2 *g0 = reinterpret_cast<const real2 *>(pg0 + s * 6);
-                const real2 *g1 = reinterpret_cast<const real2 *>(pg1 + s * 6);
+            // running pointers: one add per stream step instead of index arithmetic per operand
+            const int32_t *mp = mk + kk;
+            const real2 *wp = wv + kk;
+            const real2 *hf = reinterpret_cast<const real2 *>(pf + kk * 6), *g0 = reinterpret_cast<const real2 *>(pg0 + kk * 6),
+                        *g1 = reinterpret_cast<const real2 *>(pg1 + kk * 6);
+            const unsigned need_f = 1u << bf, need_g = (1u << bg0) | (1u << bg1);
+            for (int s = kk; s < cnt; s += nsub, mp += nsub, wp += nsub, hf += 3 * nsub, g0 += 3 * nsub, g1 += 3 * nsub) {
+                const unsigned m = (unsigned)*mp;
+                if (!(m & need_f) || !(m & need_g)) continue;
+                const real2 ws = *wp;
                 const real2 f01 = hf[0], f23 = hf[1], f45 = hf[2];
                 const real2 gv[6] = {g0[0], g0[1], g0[2], g1[0], g1[1], g1[2]};
                 const real2 wf01 = bmul(ws.x, f01), wf23 = bmul(ws.x, f23), wf45 = bmul(ws.x, f45);

@@ -44,7 +44,7 @@ PVIO_HD int32_t lm_meta(int anchor, int victim, int n_obs, unsigned mask) {
 // blocks sorted by (target frame t, anchor frame a, landmark), segment sp = t (t - 1) / 2 + a.  A warp of the
 // linearise / update sweeps works on 32 consecutive entries of ONE segment ("row"), so the target frame is
 // warp-uniform (held in registers) and the per-(t, a) direct blocks are plain register sums.
-struct __align__(8) FObs { float zx, zy; };
+struct __align__(16) FObs { float zx, zy; int32_t lm, pad; };     // keypoint in the target frame, packed landmark index
 
 // per-landmark sums of the linearise sweep (H_ll, g_l), formed by the Schur kernel
 struct LmSum { double hll, gl; };

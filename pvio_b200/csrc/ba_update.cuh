@@ -27,7 +27,6 @@ struct UpdArgs {
     const LmAux *lm_aux;
     const void *hs;           // [W][Ncap][Mcap][6] real: unscaled h records of lin_obs_kernel (PipeArgs::hs)
     const FObs *fobs;         // frame-major table (ba_fobs.cuh)
-    const uint16_t *fobs_lm;
     const int32_t *seg;
     const double *dx_pose;    // [W][Ncap][15] pose/motion step in delta coordinates
     double *rho_cand;         // [W][Mcap]
@@ -47,18 +46,20 @@ struct UpdArgs {
 };
 
 template <typename real>
-__host__ __device__ inline size_t upd_smem_layout(int N, int Mp, size_t *o_dxi, size_t *o_x, size_t *o_seg, size_t *o_red) {
+__host__ __device__ inline size_t upd_smem_layout(int N, int Mp, int warps, size_t *o_dxi, size_t *o_x, size_t *o_seg, size_t *o_red, size_t *o_ring) {
     size_t off = sizeof(double) * 12 * (size_t)N;                  // candidate camera poses: Rwc[9], c[3]
     *o_dxi = off; off += sizeof(double) * 6 * (size_t)N;           // xi = T delta per frame
     *o_x = off; off += sizeof(double) * 3 * (size_t)Mp;            // candidate world points (SoA)
     *o_red = off; off += sizeof(double) * 8;
     *o_seg = off; off += sizeof(int32_t) * kSegTab;
-    return (off + 15) & ~(size_t)15;
+    off = (off + 15) & ~(size_t)15;
+    *o_ring = off; off += sizeof(FObs) * kRing * 32 * (size_t)warps;
+    return off;
 }
 template <typename real>
-__host__ __device__ inline size_t upd_smem_bytes(int N, int Mp) {
-    size_t a, b, c, d;
-    return upd_smem_layout<real>(N, Mp, &a, &b, &c, &d);
+__host__ __device__ inline size_t upd_smem_bytes(int N, int Mp, int warps) {
+    size_t a, b, c, d, e;
+    return upd_smem_layout<real>(N, Mp, warps, &a, &b, &c, &d, &e);
 }
 
 // Residual-only evaluation of one block (candidate cost): fp64 numerators, the rest in `real`.
@@ -100,8 +101,8 @@ update_obs_kernel(UpdArgs a) {
     const int nsp = N * (N - 1) / 2;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    size_t o_dxi, o_x, o_seg, o_red;
-    upd_smem_layout<real>(N, Mp, &o_dxi, &o_x, &o_seg, &o_red);
+    size_t o_dxi, o_x, o_seg, o_red, o_ring;
+    upd_smem_layout<real>(N, Mp, kWarps, &o_dxi, &o_x, &o_seg, &o_red, &o_ring);
     double *Fc = reinterpret_cast<double *>(smem_raw);                  // [N][12] candidate state
     double *dxi = reinterpret_cast<double *>(smem_raw + o_dxi);         // [N][6]
     double *xs = reinterpret_cast<double *>(smem_raw + o_x);            // [3][Mp]
@@ -247,14 +248,18 @@ update_obs_kernel(UpdArgs a) {
         const real W[4] = {(real)wc.sic[0], (real)wc.sic[1], (real)wc.sic[2], (real)wc.sic[3]};
         const real cb = (real)(wc.cauchy_a * wc.cauchy_a), inv_cb = (real)(1.0 / (wc.cauchy_a * wc.cauchy_a));
         const FObs *fobs = a.fobs + (size_t)w * a.Kcap;
-        const uint16_t *flm = a.fobs_lm + (size_t)w * a.Kcap;
         const int32_t *sbeg = sg, *srow = sg + kMaxSeg + 1;
         const int rows = srow[nsp];
         const int nwt = gridDim.x * kWarps, wid = blockIdx.x * kWarps + wv;
         const int r_begin = (int)((long long)rows * wid / nwt), r_end = (int)((long long)rows * (wid + 1) / nwt);
-        int sp = 0, t = 1, an = 0;
-        for (int r = r_begin; r < r_end;) {
-            while (srow[sp + 1] <= r) { ++sp; if (++an == t) { ++t; an = 0; } }
+        // rows through the per-warp cp.async ring, as in lin_obs_kernel
+        FObs *ring = reinterpret_cast<FObs *>(smem_raw + o_ring) + (size_t)wv * kRing * 32;
+        RowCursor pf(sbeg, srow, r_begin, rows), cs(sbeg, srow, r_begin, rows);
+#pragma unroll
+        for (int d = 0; d < kRing; ++d) row_prefetch(pf, r_end, fobs, ring + d * 32, lane);
+        int slot = 0;
+        while (cs.r < r_end) {
+            const int sp = cs.sp, t = cs.t;
             const int seg_end = sbeg[sp + 1];
             const int r_stop = min(r_end, srow[sp + 1]);
             double Rwc[9], c[3];
@@ -266,21 +271,20 @@ update_obs_kernel(UpdArgs a) {
                 for (int i = 0; i < 3; ++i) c[i] = Ft[9 + i];
             }
             real cacc = 0;
-            int k = sbeg[sp] + (r - srow[sp]) * 32 + lane;
-            FObs o_nx;
-            o_nx.zx = 0.f; o_nx.zy = 0.f;
-            int l_nx = 0;
-            if (k < seg_end) { o_nx = fobs[k]; l_nx = flm[k]; }
-            for (; r < r_stop; ++r) {            // the NEXT row's table entries are requested before this row is evaluated
-                const FObs o = o_nx;
-                const int l = l_nx;
-                const bool valid = k < seg_end;
-                k += 32;
-                if (r + 1 < r_stop && k < seg_end) { o_nx = fobs[k]; l_nx = flm[k]; }
-                if (valid) cacc += residual_cost_blk<kLoss, real>(Rwc, c, xs[l], xs[Mp + l], xs[2 * Mp + l], o.zx, o.zy, W, cb, inv_cb);
+            for (; cs.r < r_stop; cs.advance()) {
+                const int k = cs.k0() + lane;
+                asm volatile("cp.async.wait_group %0;" :: "n"(kRing - 1) : "memory");
+                const FObs o = ring[slot * 32 + lane];
+                row_prefetch(pf, r_end, fobs, ring + slot * 32, lane);
+                slot = slot + 1 == kRing ? 0 : slot + 1;
+                if (k < seg_end) {
+                    const int l = o.lm;
+                    cacc += residual_cost_blk<kLoss, real>(Rwc, c, xs[l], xs[Mp + l], xs[2 * Mp + l], o.zx, o.zy, W, cb, inv_cb);
+                }
             }
             s_cost += (double)cacc;
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     double v[8] = {s_cost, s_gdx, s_reg, s_gn, s_dx2, s_x2, s_g2, s_vrd};
 #pragma unroll

@@ -2,6 +2,8 @@
 reference's (never-instantiated) estimation/ceres/cost_function_validator.h:39-43,270-323:
 perturb through Plus() for manifold blocks and compare with the analytic local Jacobian.
 The reference ships no tests/golden vectors, so this is the available pin."""
+import os
+
 import numpy as np
 import pytest
 from oracle import ba_oracle as bo
@@ -176,3 +178,34 @@ def test_c_restatement_matches_numpy_oracle():
         assert abs(out['new_cost'] - cand) < 1e-8 * cand
     dxb, costs, used = c_oracle.gn_step_batch(w, st, 4, n_threads=2)
     assert used == 2 and np.allclose(dxb, out['dx'][None, :], rtol=0, atol=0)
+
+
+def test_c_restatement_full_window_solve_and_marginalise():
+    """The C restatement covers what the reference does per keyframe: IMU / prior / plane blocks, the TRADITIONAL_DOGLEG
+    trust-region loop and marginalize_frame -- against the NumPy oracle to round-off, iteration history included."""
+    from oracle import c_oracle
+
+    def rel(a, b):
+        return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+    for w, st, _ in (synth.make_cfg3(N=6, M=100), synth.make_cfg4(N=6, M=60, tracks_per_plane=20)):
+        ref = bo.gn_step(w, st, schur=True)
+        out = c_oracle.gn_step(w, st)
+        assert rel(out['dx'], ref['dx']) < 1e-9 and abs(out['cost'] - ref['cost']) < 1e-12 * ref['cost']
+        assert abs(out['new_cost'] - bo.total_cost(w, bo.apply_step(w, st, ref['dx']))) < 1e-9 * out['new_cost']
+    for (w, st, _), r0 in ((synth.make_cfg2(N=6, M=80, seed=21), 30.0), (synth.make_cfg3(N=6, M=100, seed=23), 50.0),
+                           (synth.make_cfg4(N=6, M=60, seed=24, tracks_per_plane=20), 20.0)):
+        rs, rsum = bo.solve(w, st, max_iter=8, radius0=r0)
+        fr, rho, sm = c_oracle.solve(w, st, max_iter=8, radius0=r0)
+        assert sm['iterations'] == rsum['iterations'] and sm['accepted_steps'] == sum(rsum['accepted'])
+        assert abs(sm['final_cost'] - rsum['final_cost']) < 1e-9 * rsum['final_cost']
+        assert np.abs(fr[:, 4:7] - rs.p).max() < 1e-10 and rel(rho, rs.rho) < 1e-10
+    w, st, _ = synth.make_cfg3(N=6, M=100)
+    S0, e0, H0, b0 = bo.marginalize(w, st, 0)
+    S, e, H, b = c_oracle.marginalize(w, st, 0)
+    hs = np.maximum(np.sqrt(np.abs(np.diag(H0))), 1e-3)
+    assert np.max(np.abs(H - H0) / np.outer(hs, hs)) < 1e-9 and np.max(np.abs(b - b0)) < 1e-9 * np.max(np.abs(b0))
+    assert np.max(np.abs(S.T @ S - S0.T @ S0) / np.outer(hs, hs)) < 1e-8
+    assert np.max(np.abs(S.T @ e - S0.T @ e0)) < 1e-8 * np.max(np.abs(S0.T @ e0))
+    used, units = c_oracle.batch("solve", w, st, 4, n_threads=2, max_iter=3)
+    assert used == 2 and units == 12
+    assert 1 <= c_oracle.usable_cores() <= (os.cpu_count() or 1)
