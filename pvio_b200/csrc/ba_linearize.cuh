@@ -433,15 +433,17 @@ lin_obs_kernel(PipeArgs a) {
             if (e >= 0) atomicAdd(&Dta[sp * kDta + e], tot);          // +sum Y^T Y, Y^T r; the epilogue applies the signs
         };
         // the table entry of the NEXT row is requested before the current row is evaluated
+        // (12 of the entry's 16 bytes are loaded: a 16-byte load would tie up a register for the padding word)
         int k = cs.k0() + lane;
-        FObs o_nx;
-        o_nx.zx = 0.f; o_nx.zy = 0.f; o_nx.lm = 0; o_nx.pad = 0;
-        if (k < seg_end) o_nx = fobs[k];
+        float2 z_nx = make_float2(0.f, 0.f);
+        int l_nx = 0;
+        if (k < seg_end) { z_nx = *reinterpret_cast<const float2 *>(&fobs[k]); l_nx = fobs[k].lm; }
         for (; cs.r < r_stop; cs.advance()) {
-            const FObs o = o_nx;
+            FObs o;
+            o.zx = z_nx.x; o.zy = z_nx.y; o.lm = l_nx;
             const bool valid = k < seg_end;
             k += 32;
-            if (cs.r + 1 < r_stop && k < seg_end) o_nx = fobs[k];
+            if (cs.r + 1 < r_stop && k < seg_end) { z_nx = *reinterpret_cast<const float2 *>(&fobs[k]); l_nx = fobs[k].lm; }
             if (valid) {
                 const int l = o.lm;
                 if (!skip[l]) {

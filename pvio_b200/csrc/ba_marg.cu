@@ -5,7 +5,7 @@
 //   reprojection factors of victim-seen tracks    :453-533   lin_obs_kernel<false, double> (no loss, quirk Q3; ba_linearize.cuh)
 //   landmark Schur (1/mat, isfinite skip)         :536-545   schur_kernel<double> (ba_schur.cuh)
 //   frame Schur with the explicit 15x15 inverse   :547-581   marg_reduce_kernel
-//   eigen factorisation, clamp lambda <= 1e-8     :583-590   marg_eig_kernel (parallel cyclic Jacobi)
+//   eigen factorisation, clamp lambda <= 1e-8     :583-590   marg_eig_kernel (Householder tridiagonalisation + implicit QL)
 // All dense algebra is fp64.  Runs once per keyframe (not per iteration): latency, not bandwidth.
 #include <cstring>
 #include <vector>
@@ -229,92 +229,158 @@ __global__ void __launch_bounds__(256) marg_reduce_kernel(const double *H, const
     }
 }
 
-// Symmetric eigen-decomposition by parallel cyclic Jacobi (round-robin pairing), fp64, one CTA.
-// A (d x d, overwritten) and V (d x d, columns = eigenvectors) live in global memory (L2).
-// Then S = sqrt(max(lambda,0 if <= 1e-8)) V^T and e = sqrt(1/lambda) V^T b   (:586-590).
-__global__ void __launch_bounds__(512) marg_eig_kernel(double *A, double *V, const double *bvec, int d,
-                                                      double *S, double *evec, int max_sweeps) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    __shared__ double cs[128][2];      // rotation (c, s) per pair of the current round
-    __shared__ int pp[128], qq[128];
-    __shared__ double off_sm, dia_sm;
-    const int m = (d + 1) / 2;         // pairs per round (pad with a dummy index when d is odd)
-    const int dd = 2 * m;
-    for (int e = tid; e < d * d; e += nt) V[e] = ((e / d) == (e % d)) ? 1.0 : 0.0;
+// Symmetric eigen-decomposition for the factorisation :583-590 (Eigen::SelfAdjointEigenSolver in the reference): Householder
+// tridiagonalisation + implicit QL with eigenvector accumulation (the EISPACK tred2 / tql2 pair), one CTA, the matrix
+// in SHARED memory (odd leading dimension: conflict-free rows and columns).  Every O(n^2) inner loop is spread over the
+// CTA; the scalar QL recurrence runs on one thread, which hands a batch of rotations to the CTA (thread k owns row k of
+// the eigenvector matrix and applies the batch in order: no barrier inside a sweep).
+// Then S = sqrt(max(lambda, 0 if <= 1e-8)) V^T and e = sqrt(1 / lambda) V^T b.
+// (The first version was a parallel cyclic Jacobi on global memory: 32 ms for d = 120, profiles/r02_latency.md.)
+__device__ __forceinline__ double block_sum(double v, double *red, int tid, int nt) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
-    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-        // convergence: off-diagonal Frobenius norm relative to the diagonal
-        if (tid == 0) { off_sm = 0.0; dia_sm = 0.0; }
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int k = 0; k < (nt >> 5); ++k) s += red[k];
+    return s;
+}
+
+__global__ void __launch_bounds__(256) marg_eig_kernel(const double *Ain, const double *bvec, int n, double *S, double *evec) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int ld = n | 1;
+    double *a = reinterpret_cast<double *>(smem_raw);       // [n][ld]: matrix -> eigenvectors (columns)
+    double *d = a + (size_t)n * ld;                         // [n]
+    double *e = d + n;                                      // [n]
+    double *rc = e + n;                                     // [n] rotation cosines of the current QL sweep
+    double *rs = rc + n;                                    // [n] sines
+    __shared__ double red[8];
+    __shared__ double sc_sm[4];
+    __shared__ int ctl[4];                                  // 0: m, 1: first rotation index, 2: last, 3: flags
+    for (int idx = tid; idx < n * n; idx += nt) a[(idx / n) * ld + idx % n] = Ain[idx];
+    __syncthreads();
+    // ---- tred2
+    for (int i = n - 1; i > 0; --i) {
+        const int l = i - 1;
+        double *ai = a + (size_t)i * ld;
+        if (l > 0) {
+            double sa = 0.0;
+            for (int k = tid; k <= l; k += nt) sa += fabs(ai[k]);
+            const double scale = block_sum(sa, red, tid, nt);
+            if (scale == 0.0) {
+                if (tid == 0) { e[i] = ai[l]; d[i] = 0.0; }
+                __syncthreads();
+                continue;
+            }
+            double sh = 0.0;
+            for (int k = tid; k <= l; k += nt) { const double v = ai[k] / scale; ai[k] = v; sh += v * v; }
+            double h = block_sum(sh, red, tid, nt);
+            if (tid == 0) {
+                const double f = ai[l], g = f >= 0 ? -sqrt(h) : sqrt(h);
+                e[i] = scale * g;
+                sc_sm[0] = h - f * g;
+                ai[l] = f - g;
+            }
+            __syncthreads();
+            h = sc_sm[0];
+            double sf = 0.0;
+            for (int j = tid; j <= l; j += nt) {             // e[j] = (A u)_j / h, u = row i
+                a[(size_t)j * ld + i] = ai[j] / h;
+                double g = 0.0;
+                const double *aj = a + (size_t)j * ld;
+                for (int k = 0; k <= j; ++k) g += aj[k] * ai[k];
+                for (int k = j + 1; k <= l; ++k) g += a[(size_t)k * ld + j] * ai[k];
+                e[j] = g / h;
+                sf += e[j] * ai[j];
+            }
+            const double f = block_sum(sf, red, tid, nt);
+            const double hh = f / (h + h);
+            for (int j = tid; j <= l; j += nt) e[j] -= hh * ai[j];
+            __syncthreads();
+            const int tri = (l + 1) * (l + 2) / 2;          // rank-2 update of the lower triangle
+            for (int idx = tid; idx < tri; idx += nt) {
+                int j = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+                while ((j + 1) * (j + 2) / 2 <= idx) ++j;
+                while (j * (j + 1) / 2 > idx) --j;
+                const int k = idx - j * (j + 1) / 2;
+                a[(size_t)j * ld + k] -= ai[j] * e[k] + e[j] * ai[k];
+            }
+            if (tid == 0) d[i] = h;
+        } else if (tid == 0) { e[i] = ai[l]; d[i] = 0.0; }
         __syncthreads();
-        double off = 0.0, dia = 0.0;
-        for (int e = tid; e < d * d; e += nt) {
-            const int i = e / d, j = e - i * d;
-            const double v = A[e];
-            if (i == j) dia += v * v; else off += v * v;
+    }
+    if (tid == 0) { d[0] = 0.0; e[0] = 0.0; }
+    __syncthreads();
+    for (int i = 0; i < n; ++i) {                            // accumulate the transformations
+        const int l = i - 1;
+        double *ai = a + (size_t)i * ld;
+        if (d[i] != 0.0) {
+            for (int j = tid; j <= l; j += nt) {
+                double g = 0.0;
+                for (int k = 0; k <= l; ++k) g += ai[k] * a[(size_t)k * ld + j];
+                for (int k = 0; k <= l; ++k) a[(size_t)k * ld + j] -= g * a[(size_t)k * ld + i];
+            }
         }
-        for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dia += __shfl_xor_sync(0xffffffffu, dia, o); }
-        if ((tid & 31) == 0) { atomicAdd(&off_sm, off); atomicAdd(&dia_sm, dia); }
         __syncthreads();
-        const bool conv = off_sm <= 1e-30 * dia_sm;
+        if (tid == 0) { d[i] = ai[i]; ai[i] = 1.0; }
+        for (int j = tid; j <= l; j += nt) { a[(size_t)j * ld + i] = 0.0; ai[j] = 0.0; }
         __syncthreads();
-        if (conv) break;
-        for (int round = 0; round < dd - 1; ++round) {
-            // round-robin tournament: position k in [0, dd): player(k) ; pairs (k, dd-1-k)
-            if (tid < m) {
-                auto player = [&](int pos) { return pos == 0 ? 0 : 1 + ((pos - 1 + round) % (dd - 1)); };
-                int p = player(tid), q = player(dd - 1 - tid);
-                if (p > q) { const int t = p; p = q; q = t; }
-                double c = 1.0, s = 0.0;
-                if (q < d) {
-                    const double apq = A[(size_t)p * d + q];
-                    if (fabs(apq) > 1e-300) {
-                        const double app = A[(size_t)p * d + p], aqq = A[(size_t)q * d + q];
-                        const double theta = (aqq - app) / (2.0 * apq);
-                        const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                        c = 1.0 / sqrt(t * t + 1.0);
-                        s = t * c;
+    }
+    // ---- tql2
+    if (tid == 0) { for (int i = 1; i < n; ++i) e[i - 1] = e[i]; e[n - 1] = 0.0; }
+    __syncthreads();
+    for (int l = 0; l < n; ++l) {
+        for (int iter = 0; iter < 64; ++iter) {
+            if (tid == 0) {                                  // scalar recurrence of one implicit QL sweep
+                int m = l;
+                for (; m < n - 1; ++m) { const double dd = fabs(d[m]) + fabs(d[m + 1]); if (fabs(e[m]) <= 2.3e-16 * dd) break; }
+                ctl[0] = m; ctl[1] = 0; ctl[2] = -1;
+                if (m != l) {
+                    double g = (d[l + 1] - d[l]) / (2.0 * e[l]), r = hypot(g, 1.0);
+                    g = d[m] - d[l] + e[l] / (g + (g >= 0 ? fabs(r) : -fabs(r)));
+                    double s = 1.0, c = 1.0, p = 0.0;
+                    int i = m - 1;
+                    bool broke = false;
+                    for (; i >= l; --i) {
+                        const double f = s * e[i], b = c * e[i];
+                        e[i + 1] = r = hypot(f, g);
+                        if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; broke = true; break; }
+                        s = f / r; c = g / r; g = d[i + 1] - p; r = (d[i] - g) * s + 2.0 * c * b; p = s * r; d[i + 1] = g + p; g = c * r - b;
+                        rc[i] = c; rs[i] = s;
                     }
-                } else { q = -1; }
-                pp[tid] = p; qq[tid] = q; cs[tid][0] = c; cs[tid][1] = s;
+                    ctl[1] = m - 1; ctl[2] = broke ? i + 1 : l;      // rotations i = m-1 .. ctl[2], in this order
+                    if (!broke) { d[l] -= p; e[l] = g; e[m] = 0.0; }
+                }
             }
             __syncthreads();
-            // rows: A <- J^T A  (rows p,q of every pair; pairs are disjoint)
-            for (int e = tid; e < m * d; e += nt) {
-                const int k = e / d, col = e - k * d;
-                const int p = pp[k], q = qq[k];
-                if (q < 0) continue;
-                const double c = cs[k][0], s = cs[k][1];
-                const double ap = A[(size_t)p * d + col], aq = A[(size_t)q * d + col];
-                A[(size_t)p * d + col] = c * ap - s * aq;
-                A[(size_t)q * d + col] = s * ap + c * aq;
-            }
-            __syncthreads();
-            // columns: A <- A J, V <- V J
-            for (int e = tid; e < m * d; e += nt) {
-                const int k = e / d, row = e - k * d;
-                const int p = pp[k], q = qq[k];
-                if (q < 0) continue;
-                const double c = cs[k][0], s = cs[k][1];
-                const double ap = A[(size_t)row * d + p], aq = A[(size_t)row * d + q];
-                A[(size_t)row * d + p] = c * ap - s * aq;
-                A[(size_t)row * d + q] = s * ap + c * aq;
-                const double vp = V[(size_t)row * d + p], vq = V[(size_t)row * d + q];
-                V[(size_t)row * d + p] = c * vp - s * vq;
-                V[(size_t)row * d + q] = s * vp + c * vq;
+            const int m = ctl[0], i_hi = ctl[1], i_lo = ctl[2];
+            __syncthreads();                                 // everybody has read the sweep record before it is rewritten
+            if (m == l) break;                               // uniform
+            for (int k = tid; k < n; k += nt) {              // row k of the eigenvector matrix takes the whole batch
+                double *zk = a + (size_t)k * ld;
+                double zi1 = zk[i_hi + 1];
+                for (int i = i_hi; i >= i_lo; --i) {
+                    const double zi = zk[i], c = rc[i], s = rs[i];
+                    zk[i + 1] = s * zi + c * zi1;
+                    zi1 = c * zi - s * zi1;
+                }
+                zk[i_lo] = zi1;
             }
             __syncthreads();
         }
     }
     __syncthreads();
-    // S = sqrt(lambda_clamped) V^T ; e = sqrt(1/lambda) V^T b
-    for (int i = tid; i < d; i += nt) {
-        const double lam = A[(size_t)i * d + i];
+    // S = sqrt(lambda_clamped) V^T ; e = sqrt(1 / lambda) V^T b
+    for (int i = tid; i < n; i += nt) {
+        const double lam = d[i];
         const bool pos = lam > 1.0e-8;
         const double sl = pos ? sqrt(lam) : 0.0, il = pos ? sqrt(1.0 / lam) : 0.0;
         double dot = 0.0;
-        for (int k = 0; k < d; ++k) {
-            const double v = V[(size_t)k * d + i];
-            S[(size_t)i * d + k] = sl * v;
+        for (int k = 0; k < n; ++k) {
+            const double v = a[(size_t)k * ld + i];
+            S[(size_t)i * n + k] = sl * v;
             dot += v * bvec[k];
         }
         evec[i] = il * dot;
@@ -341,7 +407,8 @@ int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state
     if (index < 0 || index >= N || N < 2) return fail(h, PVIO_B200_EINVAL, "marginalize: bad frame index");
     if (!w->use_inertial) return fail(h, PVIO_B200_EINVAL, "marginalize: the window must carry motion states");
     const int n = 15 * N, dk = n - 15;
-    if ((S_out || e_out) && dk > 256) return fail(h, PVIO_B200_EINVAL, "marginalize: window too large for the eigen-solver");
+    if ((S_out || e_out) && sizeof(double) * ((size_t)dk * (dk | 1) + 4 * (size_t)dk) > 224 * 1024)
+        return fail(h, PVIO_B200_EINVAL, "marginalize: window too large for the shared-memory eigen-solver (15 (N - 1) <= 165)");
     int rc = pack_and_upload(h, w, s);
     if (rc != 0) return rc;
     // dense buffers: sized once from the handle's frame capacity
@@ -370,7 +437,10 @@ int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state
     if (H_out) CK(h, cudaMemcpyAsync(H_out, dHk, sizeof(double) * dk * dk, cudaMemcpyDeviceToHost, h->stream));
     if (b_out) CK(h, cudaMemcpyAsync(b_out, dbk, sizeof(double) * dk, cudaMemcpyDeviceToHost, h->stream));
     if (S_out || e_out) {
-        marg_eig_kernel<<<1, 512, 0, h->stream>>>(dHk, dV, dbk, dk, dS, de, 30);
+        const size_t esm = sizeof(double) * ((size_t)dk * (dk | 1) + 4 * (size_t)dk);
+        static bool attr_set = false;
+        if (!attr_set) { CK(h, cudaFuncSetAttribute(marg_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); attr_set = true; }
+        marg_eig_kernel<<<1, 256, esm, h->stream>>>(dHk, dbk, dk, dS, de);
         ++h->launches;
         if (S_out) CK(h, cudaMemcpyAsync(S_out, dS, sizeof(double) * dk * dk, cudaMemcpyDeviceToHost, h->stream));
         if (e_out) CK(h, cudaMemcpyAsync(e_out, de, sizeof(double) * dk, cudaMemcpyDeviceToHost, h->stream));

@@ -21,6 +21,10 @@
 namespace pvio {
 
 constexpr int kSlab = 64;                       // landmarks per staged slab
+#ifndef PVIO_SCHUR_SLOTS
+#define PVIO_SCHUR_SLOTS 2
+#endif
+constexpr int kSlots = PVIO_SCHUR_SLOTS;        // slabs in flight per CTA (ring of bulk copies)
 constexpr int kFlushVals = 39;                  // staged values per thread and pass (78 = 72 tile + 6 gradient, two passes)
 
 template <typename real>
@@ -36,7 +40,7 @@ __host__ __device__ inline size_t schur_smem_layout(int N, size_t *o_g, size_t *
     const size_t npairs = (size_t)N * (N + 1) / 2;
     size_t off = sizeof(double) * npairs * 36;                                  // Ss
     *o_g = off; off += sizeof(double) * (size_t)N * 6;                          // gsc
-    *o_bar = off; off += 32;                                                    // 3 mbarriers
+    *o_bar = off; off += 8 * (kSlots + 1);                                      // one mbarrier per ring slot + one for the direct part
     *o_tab = off; off += sizeof(int32_t) * 80;                                  // per tile: f | g0 << 8 | g1 << 16 | flags << 24
     off = (off + 127) & ~(size_t)127;
     *o_ring = off;
@@ -48,7 +52,7 @@ __host__ __device__ inline size_t schur_smem_layout(int N, size_t *o_g, size_t *
 template <typename real>
 __host__ __device__ inline size_t schur_smem_bytes(int N, int nthreads, int nfree) {
     size_t a, b, c, d;
-    const size_t ring = 2 * schur_ring_slot_bytes<real>(nfree), stage = sizeof(real) * (size_t)nthreads * kFlushVals;
+    const size_t ring = kSlots * schur_ring_slot_bytes<real>(nfree), stage = sizeof(real) * (size_t)nthreads * kFlushVals;
     return schur_smem_layout<real>(N, &a, &b, &c, &d) + (ring > stage ? ring : stage);
 }
 
@@ -109,20 +113,21 @@ schur_kernel(PipeArgs a) {
     const int n_slab_all = (M + kSlab - 1) / kSlab;
     const int n_slab = (ntile > 0 && n_slab_all > (int)blockIdx.x) ? (n_slab_all - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     auto slab_id = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
-    auto issue = [&](int i) {                                       // one thread: bulk copies of slab i into ring slot i & 1
+    auto issue = [&](int i) {                                       // one thread: bulk copies of slab i into ring slot i % kSlots
         const int l0 = slab_id(i) * kSlab;
         const int cnt = min(kSlab, ((M - l0) + 3) & ~3);            // copy granule: 4 records (16 bytes of masks)
         const uint32_t hb = (uint32_t)(cnt * 6 * sizeof(real)), wb = (uint32_t)(cnt * 2 * sizeof(real)), mb = (uint32_t)(cnt * 4);
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[i & 1]);
+        const int sl = i % kSlots;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[sl]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(hb * (uint32_t)nfree + wb + mb) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"((uint32_t)__cvta_generic_to_shared(slot_msk(i & 1))), "l"(lm_msk + l0), "r"(mb), "r"(bar) : "memory");
+                     :: "r"((uint32_t)__cvta_generic_to_shared(slot_msk(sl))), "l"(lm_msk + l0), "r"(mb), "r"(bar) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"((uint32_t)__cvta_generic_to_shared(slot_w(i & 1))), "l"(lm_w + l0), "r"(wb), "r"(bar) : "memory");
+                     :: "r"((uint32_t)__cvta_generic_to_shared(slot_w(sl))), "l"(lm_w + l0), "r"(wb), "r"(bar) : "memory");
         unsigned fm = freem;
         for (int s = 0; s < nfree; ++s, fm &= fm - 1) {
             const int f = __ffs(fm) - 1;
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot_h(i & 1) + (size_t)s * FS);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot_h(sl) + (size_t)s * FS);
             const real *src = hs + ((size_t)f * a.Mcap + l0) * 6;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          :: "r"(dst), "l"(src), "r"(hb), "r"(bar) : "memory");
@@ -136,14 +141,14 @@ schur_kernel(PipeArgs a) {
     double *Hred_o = a.Hred + (size_t)w * npairs_cap * 36;
     double *gred_o = a.gred + (size_t)w * a.Ncap * 6;
     if (tid == 0) {
-        for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < kSlots + 1; ++j)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&bars[j])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (!exclusive) for (int i = tid; i < npairs * 36 + N * 6; i += kThreads) Ss[i] = 0.0;          // Ss, gsc contiguous
     __syncthreads();
     if (exclusive && tid == 0) {
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[2]);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[kSlots]);
         const uint32_t hb = (uint32_t)(npairs * 36 * sizeof(double)), gb = (uint32_t)(N * 6 * sizeof(double));
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(hb + gb) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -160,7 +165,7 @@ schur_kernel(PipeArgs a) {
     auto flush_point = [&](int p) { const int q = ((p + 1) * fl_mul) >> 16; return q * fl_every == p + 1 || p == n_slab - 1; };
     int next_issue = 0;
     auto issue_ahead = [&](int i) {                                  // thread 0, after slab i has been consumed (i = -1: start)
-        while (next_issue < n_slab && next_issue <= i + 2) {
+        while (next_issue < n_slab && next_issue <= i + kSlots) {
             bool blocked = false;
             for (int p = i + 1; p < next_issue; ++p) blocked |= flush_point(p);
             if (blocked) break;
@@ -178,7 +183,7 @@ schur_kernel(PipeArgs a) {
 
     auto flush = [&]() {                         // all threads: partial tiles -> fp64 sums in shared memory
         if (!d_ready) {                          // the direct part must have landed in Ss / gsc
-            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[2]);
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[kSlots]);
             uint32_t done = 0;
             while (!done)
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
@@ -218,8 +223,8 @@ schur_kernel(PipeArgs a) {
 
     for (int i = 0; i < n_slab; ++i) {
         {   // wait for slab i
-            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[i & 1]);
-            const uint32_t parity = (uint32_t)((i >> 1) & 1);
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[i % kSlots]);
+            const uint32_t parity = (uint32_t)((i / kSlots) & 1);
             uint32_t done = 0;
             while (!done)
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
@@ -227,9 +232,9 @@ schur_kernel(PipeArgs a) {
         }
         const int cnt = min(kSlab, M - slab_id(i) * kSlab);
         if (t_active) {
-            const int32_t *mk = slot_msk(i & 1);
-            const real2 *wv = slot_w(i & 1);
-            const real *buf = slot_h(i & 1);
+            const int32_t *mk = slot_msk(i % kSlots);
+            const real2 *wv = slot_w(i % kSlots);
+            const real *buf = slot_h(i % kSlots);
             const real *pf = buf + (size_t)fi * FS, *pg0 = buf + (size_t)(2 * gp) * FS, *pg1 = buf + (size_t)gi1 * FS;
             // running pointers: one add per stream step instead of index arithmetic per operand
             const int32_t *mp = mk + kk;
@@ -264,7 +269,7 @@ schur_kernel(PipeArgs a) {
     // ---- reduced system out: Ss / gsc hold D - S (one CTA per window) or -S (several)
     if (exclusive) {
         if (!d_ready) {                          // no slab at all: still wait for the copy before leaving
-            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[2]);
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[kSlots]);
             uint32_t done = 0;
             while (!done)
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
