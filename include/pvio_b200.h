@@ -239,6 +239,16 @@ int pvio_b200_klt_track_raw(pvio_b200_handle h, const uint8_t *prev, const uint8
                             int max_level, int max_iter, double eps, double clahe_clip, int tiles_x, int tiles_y,
                             uint8_t *prev_eq, uint8_t *next_eq);
 
+/* The call OpenCvImage::track_keypoints maps to in a running tracker (opencv_image.cpp:88-136, caller
+ * core/feature_tracker.cpp:92: prev is always the previous call's next): frames carry ids (!= 0) and the handle keeps the
+ * finished pyramids (CLAHE output + 4 levels) of the last two frames on the device, so a steady-state call uploads and
+ * builds ONE pyramid; an image whose id is cached may be passed as NULL.  clahe_clip > 0: raw frames, CLAHE on the
+ * device; 0: frames are already equalised.  border > 0: the 20-pixel border rejection of :106-108 runs on the device. */
+int pvio_b200_klt_track_cached(pvio_b200_handle h, uint64_t prev_id, const uint8_t *prev, uint64_t next_id, const uint8_t *next,
+                               int width, int height, int stride, const float *prev_pts, float *next_pts, uint8_t *status,
+                               float *err, int n_points, int max_level, int max_iter, double eps, double clahe_clip,
+                               int tiles_x, int tiles_y, int border);
+
 /* CLAHE of one frame (same kernels); dst is [height][width]. */
 int pvio_b200_clahe(pvio_b200_handle h, const uint8_t *src, int width, int height, int stride, double clip_limit,
                     int tiles_x, int tiles_y, uint8_t *dst);

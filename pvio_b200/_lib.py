@@ -71,7 +71,7 @@ EXPORTS = [
     "pvio_b200_batch_gn_step_host", "pvio_b200_sync", "pvio_b200_timer_start", "pvio_b200_timer_stop",
     "pvio_b200_last_kernel_ms", "pvio_b200_klt_track", "pvio_b200_pnp_solve", "pvio_b200_preintegrate",
     "pvio_b200_triangulate", "pvio_b200_klt_track_raw", "pvio_b200_clahe", "pvio_b200_batch_solve",
-    "pvio_b200_batch_download_state", "pvio_b200_batch_solve_host", "pvio_b200_selftest_lie",
+    "pvio_b200_batch_download_state", "pvio_b200_batch_solve_host", "pvio_b200_selftest_lie", "pvio_b200_klt_track_cached",
 ]
 
 _lib = None

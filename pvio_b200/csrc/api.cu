@@ -1223,6 +1223,17 @@ int pvio_b200_klt_track_raw(pvio_b200_handle hh, const uint8_t *prev, const uint
                           max_iter, eps, clahe_clip, tiles_x, tiles_y, prev_eq, next_eq);
 }
 
+int pvio_b200_klt_track_cached(pvio_b200_handle hh, uint64_t prev_id, const uint8_t *prev, uint64_t next_id, const uint8_t *next,
+                               int width, int height, int stride, const float *prev_pts, float *next_pts, uint8_t *status, float *err,
+                               int n_points, int max_level, int max_iter, double eps, double clahe_clip, int tiles_x, int tiles_y,
+                               int border) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !prev_pts || !next_pts || !status) return PVIO_B200_EINVAL;
+    if (clahe_clip < 0.0) return fail(h, PVIO_B200_EINVAL, "klt_track_cached: clahe_clip must be >= 0 (0: frames are already equalised)");
+    return klt_track_impl(h, prev, next, width, height, stride, prev_pts, next_pts, status, err, n_points, max_level,
+                          max_iter, eps, clahe_clip, tiles_x, tiles_y, nullptr, nullptr, prev_id, next_id, border);
+}
+
 int pvio_b200_clahe(pvio_b200_handle hh, const uint8_t *src, int width, int height, int stride, double clip_limit,
                     int tiles_x, int tiles_y, uint8_t *dst) {
     Handle *h = reinterpret_cast<Handle *>(hh);

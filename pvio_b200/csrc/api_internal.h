@@ -102,7 +102,7 @@ void drop_graphs(Handle *h);
 int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int width, int height, int stride,
                    const float *prev_pts, float *next_pts, uint8_t *status, float *err, int n_points,
                    int max_level, int max_iter, double eps, double clahe_clip = 0.0, int tiles_x = 0, int tiles_y = 0,
-                   uint8_t *prev_eq = nullptr, uint8_t *next_eq = nullptr);
+                   uint8_t *prev_eq = nullptr, uint8_t *next_eq = nullptr, uint64_t prev_id = 0, uint64_t next_id = 0, int border = 0);
 int clahe_impl(Handle *h, const uint8_t *src, int width, int height, int stride, double clip, int tiles_x, int tiles_y, uint8_t *dst);
 void klt_free(Handle *h);
 // pnp.cu

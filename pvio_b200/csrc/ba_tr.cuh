@@ -109,7 +109,11 @@ __device__ inline bool tr_decide(WinCtrl &c, const double *acc, double aux_cost)
         c.reuse = 1;
     }
     if (c.radius <= 1e-32) tr_terminate(c, PVIO_B200_TERM_CONVERGENCE);
-    else if (c.iteration >= c.max_iter) c.done = 1;
+    // iteration budget spent: after a REJECTED step nothing is left to do; after an accepted one ceres still evaluates
+    // cost, gradient and Jacobian at the new point (final_cost is that re-evaluated cost -- with the aliased bias
+    // linearisation point of quirk Q1 it differs from the candidate cost), which the next body's linearisation does
+    // before tr_after_backsub stops the window
+    else if (c.iteration >= c.max_iter && !accept) c.done = 1;
     return accept;
 }
 

@@ -34,7 +34,20 @@ struct KltState {
     uint8_t *h_img = nullptr;                 // pinned staging for both level-0 images
     float *h_pts = nullptr;                   // pinned: prev | next | err
     uint8_t *h_status = nullptr;
+    // image cache: pyr[i] holds the finished pyramid of the frame with id pyr_id[i] (0: none) built with pyr_clahe[i];
+    // the tracker calls with prev = the previous call's next (feature_tracker.cpp:92), so half the uploads and
+    // pyramid builds of a steady-state call are skipped
+    uint64_t pyr_id[2] = {0, 0};
+    double pyr_clahe[2] = {0.0, 0.0};
 };
+
+// 20-pixel border rejection of OpenCvImage::track_keypoints (opencv_image.cpp:106-108) on the device
+__global__ void klt_border_kernel(const float *pts, uint8_t *status, int n, int w, int h, int border) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = pts[2 * i], y = pts[2 * i + 1];
+    if (x < (float)border || x >= (float)(w - border) || y < (float)border || y >= (float)(h - border)) status[i] = 0;
+}
 
 struct KltLevels {
     const uint8_t *I[kMaxLevels];
@@ -316,7 +329,7 @@ void klt_free(Handle *h) {
 
 static int klt_prepare(Handle *h, int w, int hgt, int max_level, int n_points) {
     KltState *k = h->klt;
-    if (k && (k->w != w || k->h != hgt || k->levels != max_level + 1 || k->cap_pts < n_points)) { klt_free(h); k = nullptr; }
+    if (k && (k->w != w || k->h != hgt || k->levels != max_level + 1 || k->cap_pts < n_points)) { klt_free(h); k = nullptr; }   // (drops the image cache)
     if (k) return 0;
     k = new KltState();
     h->klt = k;
@@ -343,18 +356,18 @@ static int klt_prepare(Handle *h, int w, int hgt, int max_level, int n_points) {
 int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int width, int height, int stride,
                    const float *prev_pts, float *next_pts, uint8_t *status, float *err, int n_points,
                    int max_level, int max_iter, double eps, double clahe_clip, int tiles_x, int tiles_y,
-                   uint8_t *prev_eq, uint8_t *next_eq) {
-    if (width < 2 || height < 2 || stride < width || n_points < 0 || max_level < 0 || max_level >= kMaxLevels)
+                   uint8_t *prev_eq, uint8_t *next_eq, uint64_t prev_id, uint64_t next_id, int border) {
+    if (width < 2 || height < 2 || stride < width || n_points < 0 || max_level < 0 || max_level >= kMaxLevels || border < 0)
         return fail(h, PVIO_B200_EINVAL, "klt: bad arguments");
     const bool do_clahe = clahe_clip > 0.0;
     if (do_clahe && (tiles_x < 1 || tiles_y < 1 || width % tiles_x || height % tiles_y))
         return fail(h, PVIO_B200_EINVAL, "clahe: the image size must be a multiple of the tile grid");
     if (n_points == 0) return 0;
-    // buildOpticalFlowPyramid stops adding levels once a level is not larger than the window
+    // cv::buildOpticalFlowPyramid halves first and drops the NEW level if it is not larger than the window
     int levels = 1, lw = width, lh = height;
     while (levels <= max_level) {
-        if (lw <= kWin || lh <= kWin) break;
         lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+        if (lw <= kWin || lh <= kWin) break;
         ++levels;
     }
     if (levels - 1 < max_level) max_level = levels - 1;
@@ -362,9 +375,22 @@ int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int widt
     if (rc != 0) return rc;
     KltState *k = h->klt;
     const size_t img_bytes = (size_t)width * height;
-    for (int y = 0; y < height; ++y) {
-        memcpy(k->h_img + (size_t)y * width, prev + (size_t)y * stride, width);
-        memcpy(k->h_img + img_bytes + (size_t)y * width, next + (size_t)y * stride, width);
+    // which pyramid slot holds which frame: cached frames (same id, same preprocessing) are neither uploaded nor rebuilt
+    int sp = -1, sn = -1;
+    for (int i = 0; i < 2; ++i) {
+        if (prev_id && k->pyr_id[i] == prev_id && k->pyr_clahe[i] == clahe_clip) sp = i;
+        if (next_id && k->pyr_id[i] == next_id && k->pyr_clahe[i] == clahe_clip && i != sp) sn = i;
+    }
+    const bool have_prev = sp >= 0, have_next = sn >= 0;
+    if (!have_prev) sp = have_next ? 1 - sn : 0;
+    if (!have_next) sn = 1 - sp;
+    if ((!have_prev && !prev) || (!have_next && !next)) return fail(h, PVIO_B200_EINVAL, "klt: image not cached and no pixels given");
+    const uint8_t *src[2] = {prev, next};
+    const int slot[2] = {sp, sn};
+    const bool have[2] = {have_prev, have_next};
+    for (int i = 0; i < 2; ++i) {
+        if (have[i]) continue;
+        for (int y = 0; y < height; ++y) memcpy(k->h_img + i * img_bytes + (size_t)y * width, src[i] + (size_t)y * stride, width);
     }
     memcpy(k->h_pts, prev_pts, sizeof(float) * 2 * n_points);
     memcpy(k->h_pts + 2 * k->cap_pts, next_pts, sizeof(float) * 2 * n_points);
@@ -376,41 +402,47 @@ int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int widt
             CK(h, cudaMalloc(&k->lut, (size_t)tiles_x * tiles_y * 256));
             k->lut_tiles = tiles_x * tiles_y;
         }
-        for (int i = 0; i < 2; ++i) {
-            CK(h, cudaMemcpyAsync(k->raw[i], k->h_img + i * img_bytes, img_bytes, cudaMemcpyHostToDevice, h->stream));
-            clahe_device(h, k->raw[i], k->pyr[i], k->lut, width, height, clahe_clip, tiles_x, tiles_y);
-        }
-    } else {
-        CK(h, cudaMemcpyAsync(k->pyr[0], k->h_img, img_bytes, cudaMemcpyHostToDevice, h->stream));
-        CK(h, cudaMemcpyAsync(k->pyr[1], k->h_img + img_bytes, img_bytes, cudaMemcpyHostToDevice, h->stream));
     }
+    for (int i = 0; i < 2; ++i) {
+        if (have[i]) continue;
+        uint8_t *P = k->pyr[slot[i]];
+        if (do_clahe) {
+            CK(h, cudaMemcpyAsync(k->raw[i], k->h_img + i * img_bytes, img_bytes, cudaMemcpyHostToDevice, h->stream));
+            clahe_device(h, k->raw[i], P, k->lut, width, height, clahe_clip, tiles_x, tiles_y);
+        } else {
+            CK(h, cudaMemcpyAsync(P, k->h_img + i * img_bytes, img_bytes, cudaMemcpyHostToDevice, h->stream));
+        }
+        for (int l = 1; l <= max_level; ++l) {
+            dim3 b(32, 8), g((k->lw[l] + 31) / 32, (k->lh[l] + 7) / 8);
+            pyrdown_kernel<<<g, b, 0, h->stream>>>(P + k->off[l - 1], k->lw[l - 1], k->lh[l - 1], P + k->off[l], k->lw[l], k->lh[l]);
+            ++h->launches;
+        }
+    }
+    k->pyr_id[sp] = prev_id; k->pyr_clahe[sp] = clahe_clip;
+    k->pyr_id[sn] = next_id; k->pyr_clahe[sn] = clahe_clip;
     CK(h, cudaMemcpyAsync(k->d_prev, k->h_pts, sizeof(float) * 2 * n_points, cudaMemcpyHostToDevice, h->stream));
     CK(h, cudaMemcpyAsync(k->d_next, k->h_pts + 2 * k->cap_pts, sizeof(float) * 2 * n_points, cudaMemcpyHostToDevice, h->stream));
     KltLevels L;
     L.n = max_level + 1;
     for (int l = 0; l <= max_level; ++l) {
-        L.I[l] = k->pyr[0] + k->off[l]; L.J[l] = k->pyr[1] + k->off[l];
+        L.I[l] = k->pyr[sp] + k->off[l]; L.J[l] = k->pyr[sn] + k->off[l];
         L.w[l] = k->lw[l]; L.h[l] = k->lh[l];
-    }
-    for (int l = 1; l <= max_level; ++l) {
-        dim3 b(32, 8), g((k->lw[l] + 31) / 32, (k->lh[l] + 7) / 8);
-        for (int i = 0; i < 2; ++i) {
-            pyrdown_kernel<<<g, b, 0, h->stream>>>(k->pyr[i] + k->off[l - 1], k->lw[l - 1], k->lh[l - 1],
-                                                  k->pyr[i] + k->off[l], k->lw[l], k->lh[l]);
-            ++h->launches;
-        }
     }
     const int mi = std::min(std::max(max_iter, 0), 100);
     const double e = std::min(std::max(eps, 0.0), 10.0);
     klt_track_kernel<<<(n_points + kKltWarps - 1) / kKltWarps, 32 * kKltWarps, 0, h->stream>>>(
         L, k->d_prev, k->d_next, k->d_status, k->d_err, n_points, mi, e * e, 1e-4f);
     ++h->launches;
+    if (border > 0) {
+        klt_border_kernel<<<(n_points + 127) / 128, 128, 0, h->stream>>>(k->d_next, k->d_status, n_points, width, height, border);
+        ++h->launches;
+    }
     CK(h, cudaMemcpyAsync(k->h_pts + 2 * k->cap_pts, k->d_next, sizeof(float) * 2 * n_points, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaMemcpyAsync(k->h_pts + 4 * k->cap_pts, k->d_err, sizeof(float) * n_points, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaMemcpyAsync(k->h_status, k->d_status, n_points, cudaMemcpyDeviceToHost, h->stream));
     if (do_clahe && (prev_eq || next_eq)) {
-        CK(h, cudaMemcpyAsync(k->h_img, k->pyr[0], img_bytes, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(k->h_img + img_bytes, k->pyr[1], img_bytes, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(k->h_img, k->pyr[sp], img_bytes, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(k->h_img + img_bytes, k->pyr[sn], img_bytes, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaGetLastError());

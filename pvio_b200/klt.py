@@ -21,10 +21,15 @@ def clahe(ba, img, clip_limit=6.0, tiles=(8, 8)):
 
 
 def track_keypoints(ba, prev_img, next_img, curr_keypoints, next_keypoints=None, max_level=3, max_iter=30,
-                    eps=0.01, border=20, raw=False, clahe_clip=0.0, clahe_tiles=(8, 8)):
+                    eps=0.01, border=20, raw=False, clahe_clip=0.0, clahe_tiles=(8, 8), prev_id=0, next_id=0, shape=None):
     """ba: a BundleAdjustor (owns the device handle).  Images: uint8 [h, w].  Keypoints in pixels.
     clahe_clip > 0: the images are the RAW frames and CLAHE runs on the device first (OpenCvImage::preprocess).
+    prev_id / next_id != 0: frame ids for the device-side pyramid cache (pvio_b200_klt_track_cached): a frame whose id
+    is cached is not uploaded again (prev_img may then be None); the border test also runs on the device.
     Returns (next_keypoints float32 [n,2], status uint8 [n], err float32 [n])."""
+    if prev_id or next_id:
+        return _track_cached(ba, prev_img, next_img, curr_keypoints, next_keypoints, max_level, max_iter, eps,
+                             0 if raw else border, clahe_clip, clahe_tiles, prev_id, next_id, shape)
     prev_img = np.ascontiguousarray(prev_img, dtype=np.uint8)
     next_img = np.ascontiguousarray(next_img, dtype=np.uint8)
     h, w = prev_img.shape
@@ -52,3 +57,25 @@ def track_keypoints(ba, prev_img, next_img, curr_keypoints, next_keypoints=None,
         out = (nxt[:, 0] < border) | (nxt[:, 0] >= w - border) | (nxt[:, 1] < border) | (nxt[:, 1] >= h - border)
         status = np.where(out, 0, status).astype(np.uint8)      # opencv_image.cpp:106-108
     return nxt, status, err
+
+
+def _track_cached(ba, prev_img, next_img, curr_keypoints, next_keypoints, max_level, max_iter, eps, border, clahe_clip,
+                  clahe_tiles, prev_id, next_id, shape):
+    imgs = [None if im is None else np.ascontiguousarray(im, dtype=np.uint8) for im in (prev_img, next_img)]
+    ref = imgs[1] if imgs[1] is not None else imgs[0]
+    h, w = ref.shape if ref is not None else shape        # both frames cached: the caller names the frame size
+    cur = np.ascontiguousarray(curr_keypoints, dtype=np.float32).reshape(-1, 2)
+    nxt = cur.copy() if next_keypoints is None or len(next_keypoints) == 0 else \
+        np.array(next_keypoints, dtype=np.float32, copy=True).reshape(-1, 2)
+    n = len(cur)
+    status = np.zeros(max(n, 1), dtype=np.uint8)
+    err = np.zeros(max(n, 1), dtype=np.float32)
+    fn = ba.lib.pvio_b200_klt_track_cached
+    fn.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int,
+                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.c_int, C.c_int,
+                   C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]
+    ptr = lambda a: None if a is None else _lib._ptr(a, C.c_uint8)
+    ba._ck(fn(ba.h, prev_id, ptr(imgs[0]), next_id, ptr(imgs[1]), w, h, w, _lib._ptr(cur, C.c_float), _lib._ptr(nxt, C.c_float),
+              _lib._ptr(status, C.c_uint8), _lib._ptr(err, C.c_float), n, max_level, max_iter, eps, float(clahe_clip),
+              clahe_tiles[0], clahe_tiles[1], int(border)))
+    return nxt, status[:n], err[:n]

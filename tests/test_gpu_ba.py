@@ -494,3 +494,36 @@ def test_device_lie_group_helpers_across_taylor_branches(ba):
     # log(exp(w)) = w away from the branch point, in particular just below pi
     big = angles > 1e-6
     assert np.allclose(out[big, 4:7], wv[big], rtol=1e-9, atol=1e-12)
+
+
+def test_sequence_of_20_keyframes_marginalise_shift_solve(ba):
+    """Sequence-level parity (the plumbing of BASELINE config 1 without its images): 20 keyframes of
+    solve -> marginalize_frame(0) -> drop the oldest frame / append the next (core/sliding_window_tracker.cpp:79-125),
+    a GPU chain and a CPU-oracle chain side by side, each feeding its own states, re-anchored inverse depths
+    (map/track.cpp:42-49) and its own prior (S, e, linearisation point) forward.  The chains must not drift apart."""
+    from oracle import c_oracle
+    from synthetic.sequence import Run, Chain
+    from pvio_b200.window import State
+    run = Run(F=26, N=6, M=260, seed=700)
+    gpu, ref = Chain(run), Chain(run)
+    worst_cost = 0.0
+    for k in range(20):
+        wg, sg, ids_g = gpu.window(k)
+        wr, sr, ids_r = ref.window(k)
+        assert ids_g == ids_r
+        out, summ = ba.solve(wg, sg, max_iterations=6)
+        fr, rho, rsum = c_oracle.solve(wr, sr, max_iter=6)
+        ref_state = State(fr[:, 0:4], fr[:, 4:7], fr[:, 7:10], fr[:, 10:13], fr[:, 13:16], rho)
+        assert summ['iterations'] == rsum['iterations'] and summ['accepted_steps'] == rsum['accepted_steps'], k
+        worst_cost = max(worst_cost, abs(summ['final_cost'] - rsum['final_cost']) / rsum['final_cost'])
+        Sg, eg = ba.marginalize_frame(wg, out, index=0)
+        Sr, er, _, _ = c_oracle.marginalize(wr, ref_state, 0)
+        gpu.store(k, out, ids_g); gpu.set_prior(k, Sg, eg, out)
+        ref.store(k, ref_state, ids_r); ref.set_prior(k, Sr, er, ref_state)
+    path = np.linalg.norm(np.diff(run.truth.p[:26], axis=0), axis=1).sum()
+    drift_p = np.max(np.linalg.norm(gpu.p[:25] - ref.p[:25], axis=1))
+    drift_v = np.max(np.linalg.norm(gpu.v[:25] - ref.v[:25], axis=1))
+    drift_rho = np.max(np.abs(gpu.rho - ref.rho) / np.abs(ref.rho))
+    print(f"20 keyframes: path {path:.2f} m, max |dp| {drift_p:.3e} m, max |dv| {drift_v:.3e} m/s, max rel d rho {drift_rho:.3e}, "
+          f"worst final-cost rel diff {worst_cost:.3e}")
+    assert drift_p < 1e-5 * path and drift_v < 1e-4 and drift_rho < 1e-4 and worst_cost < 1e-5

@@ -83,3 +83,42 @@ def test_track_from_raw_frames_equals_track_of_equalised_frames(ba):
     a = klt.track_keypoints(ba, prev, nxt, pts, clahe_clip=6.0)
     b = klt.track_keypoints(ba, clahe_oracle.clahe(prev), clahe_oracle.clahe(nxt), pts)
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+
+
+def test_klt_pyramid_cache_matches_uncached_calls(ba):
+    """pvio_b200_klt_track_cached keeps the finished pyramids of the last two frames (prev of a call = next of the call
+    before, core/feature_tracker.cpp:92): a three-frame sequence through the cache -- the second call passes no pixels
+    for its prev frame -- gives bit for bit what the self-contained calls give, border rule included."""
+    a, b, pts, _ = synth.make_klt_pair(size=(320, 240), n_points=60, seed=5)
+    _, c, _, _ = synth.make_klt_pair(size=(320, 240), n_points=60, seed=6)
+    ref1 = klt.track_keypoints(ba, a, b, pts)
+    ref2 = klt.track_keypoints(ba, b, c, ref1[0])
+    l0 = ba.kernel_launches
+    got1 = klt.track_keypoints(ba, a, b, pts, prev_id=101, next_id=102)
+    l1 = ba.kernel_launches
+    got2 = klt.track_keypoints(ba, None, c, got1[0], prev_id=102, next_id=103)      # frame 102 is cached: no pixels needed
+    l2 = ba.kernel_launches
+    for r, g in ((ref1, got1), (ref2, got2)):
+        assert np.array_equal(r[1], g[1]) and np.array_equal(r[0], g[0]) and np.array_equal(r[2], g[2])
+    assert (l2 - l1) < (l1 - l0)            # the second call built one pyramid, not two
+    # CLAHE on the device goes through the same cache
+    r3 = klt.track_keypoints(ba, a, b, pts, clahe_clip=6.0)
+    g3 = klt.track_keypoints(ba, a, b, pts, clahe_clip=6.0, prev_id=7, next_id=8)
+    g4 = klt.track_keypoints(ba, None, None, pts, clahe_clip=6.0, prev_id=7, next_id=8, shape=a.shape)      # both cached
+    assert np.array_equal(r3[0], g3[0]) and np.array_equal(r3[1], g3[1]) and np.array_equal(g3[0], g4[0])
+
+
+def test_klt_small_image_pyramid_depth_matches_opencv(ba):
+    """cv::buildOpticalFlowPyramid halves first and drops the new level when it is not larger than the window: a
+    160 x 120 frame with maxLevel 3 has levels 0..2 (80 x 60, 40 x 30; 20 x 15 is dropped).  One level too many changes
+    the coarse initialisation and with it positions and status flags."""
+    cv2 = pytest.importorskip("cv2")
+    prev, nxt_img, pts, _ = synth.make_klt_pair(size=(160, 120), n_points=25, max_shift=6.0, seed=9)
+    nxt, st, err = klt.track_keypoints(ba, prev, nxt_img, pts, raw=True)
+    p1, s1, e1 = cv2.calcOpticalFlowPyrLK(prev, nxt_img, pts.reshape(-1, 1, 2).copy(), pts.reshape(-1, 1, 2).copy(),
+                                          winSize=(21, 21), maxLevel=3,
+                                          criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01),
+                                          flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+    assert np.array_equal(st, s1.ravel())
+    ok = st == 1
+    assert ok.sum() >= 3 and np.max(np.abs(nxt[ok] - p1.reshape(-1, 2)[ok])) < 1e-2
