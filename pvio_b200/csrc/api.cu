@@ -487,7 +487,7 @@ static int run_linearize(Handle *h, int n, const StepCfg &c, const BatchShape &b
         for (auto &e : h->kev) CK(h, cudaEventCreate(&e));
     }
     const int slot = (h->kev_count % 256) * 3;
-    const bool timed = !h->capturing;
+    const bool timed = !h->capturing && !c.loop && !c.stream;   // stage times are a property of the plain batched step
     if (timed) CK(h, cudaEventRecord(h->kev[slot], st));
     const int Mp = (b.M + 31) & ~31;
     const int sgx = std::min(gx, std::max(1, (b.M + kSlab - 1) / kSlab));
@@ -730,7 +730,8 @@ static void scatter_state(Handle *h, int i, double *frames, double *inv_depth) {
     if (inv_depth) {
         const double *r = h->rho_out.h + (size_t)i * h->Mcap;
         const std::vector<int32_t> &perm = h->perm[i];
-        for (int lp = 0; lp < M; ++lp) inv_depth[perm[lp]] = r[lp];
+        if (h->perm_identity[i]) memcpy(inv_depth, r, sizeof(double) * M);
+        else for (int lp = 0; lp < M; ++lp) inv_depth[perm[lp]] = r[lp];
     }
 }
 
@@ -840,6 +841,8 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     for (auto &e : h->ev_down) cudaEventDestroy(e);
     if (h->stream_up) cudaStreamDestroy(h->stream_up);
     if (h->stream_down) cudaStreamDestroy(h->stream_down);
+    for (auto &st : h->stream_c) cudaStreamDestroy(st);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -961,12 +964,19 @@ int pvio_b200_batch_download(pvio_b200_handle hh, int n, double *dx, int64_t dx_
 
 // sub-batch schedule of the pipelined host paths: small batches first and last (the first upload and the last
 // kernels + download are the only parts of the pipeline that nothing overlaps), 512-window batches in between
+#ifndef PVIO_PIPE_STREAMS
+#define PVIO_PIPE_STREAMS 6
+#endif
+#ifndef PVIO_PIPE_CHUNK
+#define PVIO_PIPE_CHUNK 512
+#endif
+static constexpr int kPipeStreams = PVIO_PIPE_STREAMS;   // sub-batches in flight on the SMs at once (each alone is latency-bound: one wave)
 static std::vector<int> sub_batches(int n) {
     std::vector<int> sizes;
     if (n < 1024) { sizes.push_back(n); return sizes; }
     int mid = n - 2 * (128 + 256);
     sizes.push_back(128); sizes.push_back(256);
-    while (mid > 0) { const int m = std::min(512, mid); sizes.push_back(m); mid -= m; }
+    while (mid > 0) { const int m = std::min(PVIO_PIPE_CHUNK, mid); sizes.push_back(m); mid -= m; }
     sizes.push_back(256); sizes.push_back(128);
     return sizes;
 }
@@ -982,6 +992,11 @@ static int ensure_pipeline_streams(Handle *h, int nsub) {
         CK(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
         CK(h, cudaEventCreateWithFlags(&c_, cudaEventDisableTiming));
         h->ev_up.push_back(a); h->ev_done.push_back(b); h->ev_down.push_back(c_);
+    }
+    if (h->stream_c.empty()) {
+        h->stream_c.resize(kPipeStreams);
+        for (auto &st : h->stream_c) CK(h, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     }
     return 0;
 }
@@ -1006,16 +1021,21 @@ int pvio_b200_batch_gn_step_host(pvio_b200_handle hh, int n, double mu, double *
     std::vector<int> starts(nsub, 0);
     for (int i = 1; i < nsub; ++i) starts[i] = starts[i - 1] + sizes[i - 1];
     TRY(ensure_pipeline_streams(h, nsub));
+    CK(h, cudaEventRecord(h->ev_fork, h->stream));
+    CK(h, cudaStreamWaitEvent(h->stream_up, h->ev_fork, 0));
+    for (auto &sc : h->stream_c) CK(h, cudaStreamWaitEvent(sc, h->ev_fork, 0));
     for (int i = 0; i < nsub; ++i) {
         const int w0 = starts[i], m = sizes[i];
+        cudaStream_t sc = h->stream_c[i % kPipeStreams];
         TRY(upload_range(h, w0, m, h->stream_up));
         CK(h, cudaEventRecord(h->ev_up[i], h->stream_up));
-        CK(h, cudaStreamWaitEvent(h->stream, h->ev_up[i], 0));
+        CK(h, cudaStreamWaitEvent(sc, h->ev_up[i], 0));
         StepCfg c;
-        c.mu = mu; c.apply = 0; c.compute_scale = 1; c.w0 = w0;
+        c.mu = mu; c.apply = 0; c.compute_scale = 1; c.w0 = w0; c.stream = sc;
         TRY(run_gn_step(h, m, c, batch_shape(h, w0, m, false)));
-        CK(h, cudaEventRecord(h->ev_done[i], h->stream));
+        CK(h, cudaEventRecord(h->ev_done[i], sc));
         CK(h, cudaStreamWaitEvent(h->stream_down, h->ev_done[i], 0));
+        CK(h, cudaStreamWaitEvent(h->stream, h->ev_done[i], 0));
         CK(h, cudaMemcpyAsync(h->dx_pose.h + (size_t)w0 * h->Ncap * 15, h->dx_pose.d + (size_t)w0 * h->Ncap * 15,
                               sizeof(double) * h->Ncap * 15 * m, cudaMemcpyDeviceToHost, h->stream_down));
         CK(h, cudaMemcpyAsync(h->dx_lm.h + (size_t)w0 * h->Mcap, h->dx_lm.d + (size_t)w0 * h->Mcap,
@@ -1079,31 +1099,48 @@ int pvio_b200_batch_solve_host(pvio_b200_handle hh, int n, const pvio_b200_optio
     std::vector<int> starts(nsub, 0);
     for (int i = 1; i < nsub; ++i) starts[i] = starts[i - 1] + sizes[i - 1];
     TRY(ensure_pipeline_streams(h, nsub));
+#ifdef PVIO_TUNE_TIMING
+    const auto tt0 = std::chrono::steady_clock::now();
+    auto stamp = [&](const char *what) { fprintf(stderr, "  [%s] %.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt0).count()); };
+#else
+    auto stamp = [&](const char *) {};
+#endif
+    // sub-batch i: upload on the copy stream, the whole trust-region loop on compute stream i % kPipeStreams (a sub-batch
+    // is at most one wave of CTAs, so alone it runs at the latency of its kernel chain; several in flight fill the SMs),
+    // download on the second copy stream; the windows of different sub-batches share nothing on the device
+    CK(h, cudaEventRecord(h->ev_fork, h->stream));
+    CK(h, cudaStreamWaitEvent(h->stream_up, h->ev_fork, 0));
+    for (auto &sc : h->stream_c) CK(h, cudaStreamWaitEvent(sc, h->ev_fork, 0));
     for (int i = 0; i < nsub; ++i) {
         const int w0 = starts[i], m = sizes[i];
+        cudaStream_t sc = h->stream_c[i % kPipeStreams];
         TRY(upload_range(h, w0, m, h->stream_up));
         CK(h, cudaEventRecord(h->ev_up[i], h->stream_up));
-        CK(h, cudaStreamWaitEvent(h->stream, h->ev_up[i], 0));
+        CK(h, cudaStreamWaitEvent(sc, h->ev_up[i], 0));
         StepCfg c;
-        c.mu = -1.0; c.loop = 1; c.alias_bias = alias; c.compute_scale = 0; c.w0 = w0;
+        c.mu = -1.0; c.loop = 1; c.alias_bias = alias; c.compute_scale = 0; c.w0 = w0; c.stream = sc;
         const BatchShape b = batch_shape(h, w0, m, false);
-        init_ctrl_kernel<<<m, 32, 0, h->stream>>>(h->ctrl.d, 1e-8, radius0, max_iter, opt ? opt->max_time : 0.0, w0);
+        init_ctrl_kernel<<<m, 32, 0, sc>>>(h->ctrl.d, 1e-8, radius0, max_iter, opt ? opt->max_time : 0.0, w0);
         ++h->launches;
         for (int it = 0; it < max_iter + 2; ++it) TRY(iteration_body(h, m, c, b));
-        CK(h, cudaEventRecord(h->ev_done[i], h->stream));
+        CK(h, cudaEventRecord(h->ev_done[i], sc));
         CK(h, cudaStreamWaitEvent(h->stream_down, h->ev_done[i], 0));
+        CK(h, cudaStreamWaitEvent(h->stream, h->ev_done[i], 0));      // later calls on the handle's stream see the result
         TRY(download_state_async(h, w0, m, h->stream_down));
         CK(h, cudaEventRecord(h->ev_down[i], h->stream_down));
     }
     h->n_uploaded = n;
+    stamp("enqueued");
     for (int i = 0; i < nsub; ++i) {
         CK(h, cudaEventSynchronize(h->ev_down[i]));
+        stamp("sub-batch landed");
         for (int k = starts[i]; k < starts[i] + sizes[i]; ++k) {
             scatter_state(h, k, frames ? frames + (size_t)k * frames_stride : nullptr, inv_depth ? inv_depth + (size_t)k * inv_depth_stride : nullptr);
             if (summaries) fill_summary(h->ctrl.h[k], &summaries[k]);
         }
     }
     CK(h, cudaStreamSynchronize(h->stream));
+    stamp("done");
     return 0;
 }
 

@@ -27,6 +27,8 @@ struct Handle {
     int Pcap = 4, Tcap = 0, Ocap = 0;            // planes / plane tracks / plane observations per window
     cudaStream_t stream = nullptr;
     cudaStream_t stream_up = nullptr, stream_down = nullptr;   // copy streams of the pipelined host path
+    std::vector<cudaStream_t> stream_c;                        // compute streams of the pipelined host path
+    cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_done, ev_down;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;

@@ -47,3 +47,17 @@ _, _, sm = ba.batch_solve_host(W, w.N, w.M, frames=fr, rho=rh)
 dt = time.time() - t
 its = sum(x.iterations for x in sm)
 print(f"e2e batch_solve_host: {dt*1e3:.2f} ms, {its} window-iterations -> {its/dt:.0f} window-iters/s")
+# e2e scaling: < 1024 windows take the single-shot path (upload, solve, download back to back), >= 1024 the pipelined one
+for n in (1000, 2048, W):
+    fr = np.zeros((n, w.N * 16)); rh = np.zeros((n, w.M))
+    ba.batch_solve_host(n, w.N, w.M, frames=fr, rho=rh)
+    t = time.time()
+    for _ in range(3):
+        _, _, sm = ba.batch_solve_host(n, w.N, w.M, frames=fr, rho=rh)
+    dt = (time.time() - t) / 3
+    print(f"e2e batch_solve_host n={n}: {dt*1e3:.2f} ms -> {sum(x.iterations for x in sm)/dt:.0f} window-iters/s")
+    ba.batch_upload(n); ba.sync()
+    t = time.time(); ba.batch_upload(n); ba.sync(); up = time.time() - t
+    t = time.time(); ba.batch_solve(n, max_iterations=10); ba.sync(); so = time.time() - t
+    t = time.time(); ba.batch_download_state(n, w.N, w.M); dn = time.time() - t
+    print(f"   parts: upload {up*1e3:.2f} ms, solve {so*1e3:.2f} ms, download+scatter {dn*1e3:.2f} ms")
