@@ -69,7 +69,11 @@ __device__ __forceinline__ float2 bfma(float a, float2 b, float2 c) { return __f
 __device__ __forceinline__ double2 bfma(double a, double2 b, double2 c) { return make_double2(fma(a, b.x, c.x), fma(a, b.y, c.y)); }
 __device__ __forceinline__ float2 bmul(float a, float2 b) { return __fmul2_rn(make_float2(a, a), b); }
 __device__ __forceinline__ double2 bmul(double a, double2 b) { return make_double2(a * b.x, a * b.y); }
-__device__ __forceinline__ float rsqrt_r(float x) { return rsqrtf(x); }
+__device__ __forceinline__ float rsqrt_r(float x) {        // rsqrt.approx: 1 ulp; the argument is 1 + s/b >= 1 (no denormal path)
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ double rsqrt_r(double x) { return 1.0 / sqrt(x); }
 __device__ __forceinline__ float log_r(float x) { return logf(x); }
 __device__ __forceinline__ double log_r(double x) { return log(x); }
@@ -91,7 +95,7 @@ struct ObsL {                // linearisation of one residual block in xi coordi
     typename Vec2<real>::type Y0[3], Y1[3];   // rows of Y = sqrt(rho') G X_l as pairs (0,1) (2,3) (4,5)
     real r0, r1;             // sqrt(rho') r
     real j0, j1;             // sqrt(rho') G c_l  (d r / d rho)
-    real cost;               // rho(s) / 2
+    real cost;               // with the loss: t = 1 + s / b (the caller accumulates b/2 log t); without: s / 2
 };
 
 // reprojection_error_cost.h:58-117 in xi coordinates (see ba_lin.cuh).  x: world point (fp64), xf = (real)x,
@@ -99,7 +103,7 @@ struct ObsL {                // linearisation of one residual block in xi coordi
 template <bool kLoss, typename real>
 __device__ __forceinline__ void linearize_blk(const FrameR<real> &F, double x0, double x1, double x2, real xf0, real xf1,
                                               real xf2, real c0, real c1, real c2, float zx, float zy, const real (&W)[4],
-                                              real cauchy_b, real inv_cauchy_b, ObsL<real> &o) {
+                                              bool diag_w, real inv_cauchy_b, ObsL<real> &o) {
     const double d0 = x0 - F.c[0], d1 = x1 - F.c[1], d2 = x2 - F.c[2];
     const double y0 = F.Rwc[0] * d0 + F.Rwc[3] * d1 + F.Rwc[6] * d2;
     const double y1 = F.Rwc[1] * d0 + F.Rwc[4] * d1 + F.Rwc[7] * d2;
@@ -108,25 +112,36 @@ __device__ __forceinline__ void linearize_blk(const FrameR<real> &F, double x0, 
     const double ny = y1 - (double)zy * y2;
     const real iz = rcp_r((real)y2);
     const real u0 = (real)nx * iz, u1 = (real)ny * iz;
-    real r0 = W[0] * u0 + W[1] * u1;
-    real r1 = W[2] * u0 + W[3] * u1;
     const real yx = (real)y0 * iz, yy = (real)y1 * iz;
-    // A = W dpi, dpi = [[iz, 0, -yx iz], [0, iz, -yy iz]];  G = A Rwc^T
-    const real A00 = W[0] * iz, A01 = W[1] * iz, A02 = -(W[0] * yx + W[1] * yy) * iz;
-    const real A10 = W[2] * iz, A11 = W[3] * iz, A12 = -(W[2] * yx + W[3] * yy) * iz;
-    real G0[3], G1[3];
+    // A = W dpi, dpi = [[iz, 0, -yx iz], [0, iz, -yy iz]];  G = A Rwc^T.  W = sqrt_inv_cov is diag(fx, fy) / sigma in the
+    // reference (core/core.cpp:114-116): the diagonal case (uniform per window) skips the zero products
+    real r0, r1, G0[3], G1[3];
+    if (diag_w) {
+        r0 = W[0] * u0; r1 = W[3] * u1;
+        const real A00 = W[0] * iz, A02 = -A00 * yx, A11 = W[3] * iz, A12 = -A11 * yy;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        G0[k] = A00 * F.R[3 * k] + A01 * F.R[3 * k + 1] + A02 * F.R[3 * k + 2];
-        G1[k] = A10 * F.R[3 * k] + A11 * F.R[3 * k + 1] + A12 * F.R[3 * k + 2];
+        for (int k = 0; k < 3; ++k) {
+            G0[k] = A00 * F.R[3 * k] + A02 * F.R[3 * k + 2];
+            G1[k] = A11 * F.R[3 * k + 1] + A12 * F.R[3 * k + 2];
+        }
+    } else {
+        r0 = W[0] * u0 + W[1] * u1;
+        r1 = W[2] * u0 + W[3] * u1;
+        const real A00 = W[0] * iz, A01 = W[1] * iz, A02 = -(W[0] * yx + W[1] * yy) * iz;
+        const real A10 = W[2] * iz, A11 = W[3] * iz, A12 = -(W[2] * yx + W[3] * yy) * iz;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            G0[k] = A00 * F.R[3 * k] + A01 * F.R[3 * k + 1] + A02 * F.R[3 * k + 2];
+            G1[k] = A10 * F.R[3 * k] + A11 * F.R[3 * k + 1] + A12 * F.R[3 * k + 2];
+        }
     }
     if (kLoss) {
         // ceres::CauchyLoss(a), b = a^2: rho = b log(1 + s/b), rho' = 1/(1 + s/b); rho'' < 0 so the Corrector
-        // scales r and J by sqrt(rho') (corrector.cc)
+        // scales r and J by sqrt(rho') (corrector.cc).  The caller turns t into the cost (b/2 log t).
         const real s = r0 * r0 + r1 * r1;
         const real t = (real)1 + s * inv_cauchy_b;
         const real sc = rsqrt_r(t);
-        o.cost = (real)0.5 * cauchy_b * log_r(t);
+        o.cost = t;
         r0 *= sc; r1 *= sc;
 #pragma unroll
         for (int k = 0; k < 3; ++k) { G0[k] *= sc; G1[k] *= sc; }
@@ -143,6 +158,63 @@ __device__ __forceinline__ void linearize_blk(const FrameR<real> &F, double x0, 
     o.j0 = G0[0] * c0 + G0[1] * c1 + G0[2] * c2;
     o.j1 = G1[0] * c0 + G1[1] * c1 + G1[2] * c2;
     o.r0 = r0; o.r1 = r1;
+}
+
+// sum of log(t_i), t_i >= 1.  fp32: the logarithm of a running product, folded at least every 4 terms (t itself carries
+// a rounding error of 6e-8, so log(t_1 t_2 t_3 t_4) loses nothing against four logf calls and costs a quarter of them);
+// a term that could overflow the product (t > 1e9: a residual of > 3e4 sigma) takes its own logarithm.
+template <typename real> struct LogAcc;
+template <> struct LogAcc<float> {
+    float prod = 1.f, sum = 0.f;
+    __device__ __forceinline__ void add(float t) { if (t > 1e9f) sum += logf(t); else prod *= t; }
+    __device__ __forceinline__ void fold() { sum += logf(prod); prod = 1.f; }
+    __device__ __forceinline__ float total() { return sum + logf(prod); }
+};
+template <> struct LogAcc<double> {
+    double sum = 0.0;
+    __device__ __forceinline__ void add(double t) { sum += log(t); }
+    __device__ __forceinline__ void fold() {}
+    __device__ __forceinline__ double total() { return sum; }
+};
+
+// Per-landmark record of the linearise sweep in shared memory, 48 bytes = three 16-byte loads by the lane that owns an
+// observation of the landmark: world point x (fp64), (real) x, c = d x / d rho.
+constexpr int kLmSm = 48;
+__device__ __forceinline__ void lm_sm_store(unsigned char *rec, double x0, double x1, double x2, float c0, float c1, float c2) {
+    reinterpret_cast<double2 *>(rec)[0] = make_double2(x0, x1);
+    reinterpret_cast<double *>(rec)[2] = x2;
+    reinterpret_cast<float2 *>(rec)[3] = make_float2((float)x0, (float)x1);
+    reinterpret_cast<float4 *>(rec)[2] = make_float4((float)x2, c0, c1, c2);
+}
+__device__ __forceinline__ void lm_sm_store(unsigned char *rec, double x0, double x1, double x2, double c0, double c1, double c2) {
+    reinterpret_cast<double2 *>(rec)[0] = make_double2(x0, x1);
+    reinterpret_cast<double2 *>(rec)[1] = make_double2(x2, c0);
+    reinterpret_cast<double2 *>(rec)[2] = make_double2(c1, c2);
+}
+// rec: shared-space address of the record (three ld.shared.v*: the address is one multiply-add from an opaque base)
+__device__ __forceinline__ void lm_sm_load(unsigned rec, double (&x)[3], float (&xf)[3], float (&c)[3]) {
+    double bx, by;
+    float d0, d1, d2, d3;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x[0]), "=d"(x[1]) : "r"(rec));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(bx), "=d"(by) : "r"(rec));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];" : "=f"(d0), "=f"(d1), "=f"(d2), "=f"(d3) : "r"(rec));
+    x[2] = bx;
+    xf[0] = __int_as_float(__double2loint(by)); xf[1] = __int_as_float(__double2hiint(by)); xf[2] = d0;
+    c[0] = d1; c[1] = d2; c[2] = d3;
+}
+__device__ __forceinline__ void lm_sm_load(unsigned rec, double (&x)[3], double (&xf)[3], double (&c)[3]) {
+    double bx, by, dx, dy;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x[0]), "=d"(x[1]) : "r"(rec));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(bx), "=d"(by) : "r"(rec));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+32];" : "=d"(dx), "=d"(dy) : "r"(rec));
+    x[2] = bx; xf[0] = x[0]; xf[1] = x[1]; xf[2] = bx;
+    c[0] = by; c[1] = dx; c[2] = dy;
+}
+// read-ahead of [p, p + bytes) into L2 by the whole CTA (the sweeps are latency-bound: 16 warps per SM)
+__device__ __forceinline__ void l2_prefetch(const void *p, size_t bytes, int tid, int nthreads) {
+    const char *c = reinterpret_cast<const char *>(p);
+    for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)nthreads * 128)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(c + off));
 }
 
 // Sum over the 32 lanes of q[i] for i = 0..31; lane i returns the total of entry i.  Transpose-reduction:
@@ -298,26 +370,22 @@ __global__ void __launch_bounds__(128) lm_finish_kernel(PipeArgs a) {
 }
 
 template <typename real>
-__host__ __device__ inline size_t lin_smem_layout(int N, int Mp, int warps, size_t *o_dta, size_t *o_seg, size_t *o_x, size_t *o_cl,
-                                                  size_t *o_skip, size_t *o_ring) {
+__host__ __device__ inline size_t lin_smem_layout(int N, int Mp, size_t *o_dta, size_t *o_seg, size_t *o_rec, size_t *o_rs, size_t *o_skip) {
     const size_t nsp = (size_t)N * (N - 1) / 2;
     size_t off = sizeof(double) * 12 * (size_t)N;                              // frames: Rwc[9], c[3]
     *o_dta = off; off += sizeof(double) * ((nsp + 1 + (size_t)N) * kDta + 8);  // direct blocks (pairs, then per frame), cost
-    *o_x = off; off += sizeof(double) * 3 * (size_t)Mp;                        // world points (SoA)
     *o_seg = off; off += sizeof(int32_t) * kSegTab;
     off = (off + 15) & ~(size_t)15;
-    *o_cl = off; off += sizeof(real) * 6 * (size_t)Mp;                         // d x / d rho and (real) x (SoA)
-    off += sizeof(real) * 12 * (size_t)N;                                      // (real) Rwc of every frame
-    *o_skip = off; off += (size_t)Mp;                                          // 1: landmark not linearised
-    off = (off + 15) & ~(size_t)15;
-    *o_ring = off; off += sizeof(FObs) * kRing * 32 * (size_t)warps;           // per-warp ring of table rows
-    return off;
+    *o_rec = off; off += (size_t)kLmSm * Mp;                                   // landmark records (lm_sm_store)
+    *o_rs = off; off += sizeof(real) * 12 * (size_t)N;                         // (real) Rwc of every frame
+    *o_skip = off; off += (size_t)Mp;                                          // 1: landmark not linearised (victim-only sweeps)
+    return (off + 15) & ~(size_t)15;
 }
 
 template <typename real>
-__host__ __device__ inline size_t lin_smem_bytes(int N, int Mp, int warps) {
-    size_t a, b, c, d, e, f;
-    return lin_smem_layout<real>(N, Mp, warps, &a, &b, &c, &d, &e, &f);
+__host__ __device__ inline size_t lin_smem_bytes(int N, int Mp, int /*warps*/) {
+    size_t a, b, c, d, e;
+    return lin_smem_layout<real>(N, Mp, &a, &b, &c, &d, &e);
 }
 
 template <bool kLoss, typename real, int kWarps, int kMinBlocks>
@@ -335,18 +403,22 @@ lin_obs_kernel(PipeArgs a) {
     const int nsp = N * (N - 1) / 2;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    size_t o_dta, o_seg, o_x, o_cl, o_skip, o_ring;
-    lin_smem_layout<real>(N, Mp, kWarps, &o_dta, &o_seg, &o_x, &o_cl, &o_skip, &o_ring);
+    size_t o_dta, o_seg, o_rec, o_rs, o_skip;
+    lin_smem_layout<real>(N, Mp, &o_dta, &o_seg, &o_rec, &o_rs, &o_skip);
     double *Fs = reinterpret_cast<double *>(smem_raw);                       // [N][12]
     double *Dta = reinterpret_cast<double *>(smem_raw + o_dta);              // [nsp + 1][kDta]
     double *Ddg = Dta + (nsp + 1) * kDta;                                    // [N][kDta] sum of the blocks touching frame f (signed gradient)
     double *cost_sm = Ddg + N * kDta;                                        // [8]
-    double *xs = reinterpret_cast<double *>(smem_raw + o_x);                 // [3][Mp]
     int32_t *sg = reinterpret_cast<int32_t *>(smem_raw + o_seg);             // seg_begin | seg_row
-    real *cls = reinterpret_cast<real *>(smem_raw + o_cl);                   // [3][Mp] d x / d rho, [3][Mp] (real) x
-    real *Rs = cls + 6 * (size_t)Mp;                                         // [N][12] (real) Rwc
+    unsigned char *recs = smem_raw + o_rec;                                  // [Mp] landmark records
+    real *Rs = reinterpret_cast<real *>(smem_raw + o_rs);                    // [N][12] (real) Rwc
     unsigned char *skip = smem_raw + o_skip;
 
+    if (gridDim.x == 1) {          // everything this CTA will read from HBM, requested before the first dependent load
+        l2_prefetch(a.fobs + (size_t)w * a.Kcap, sizeof(FObs) * (size_t)H.K, tid, kThreads);
+        l2_prefetch(a.lms + (size_t)w * a.Mcap, sizeof(LmRec) * (size_t)M, tid, kThreads);
+        l2_prefetch(a.rho + (size_t)w * a.Mcap, sizeof(double) * (size_t)M, tid, kThreads);
+    }
     if (tid < N) {
         FrameSm f;
         make_frame(a.frames + ((size_t)w * a.Ncap + tid) * kFrameStride, wc, f);
@@ -382,16 +454,16 @@ lin_obs_kernel(PipeArgs a) {
                 sk = 0;
             }
         }
-        xs[l] = x0; xs[Mp + l] = x1; xs[2 * Mp + l] = x2;
-        cls[l] = c0; cls[Mp + l] = c1; cls[2 * Mp + l] = c2;
-        cls[3 * Mp + l] = (real)x0; cls[4 * Mp + l] = (real)x1; cls[5 * Mp + l] = (real)x2;
+        lm_sm_store(recs + (size_t)l * kLmSm, x0, x1, x2, c0, c1, c2);
         skip[l] = sk;
     }
     __syncthreads();
 
     // ---- phase 1: rows of the frame-major table
     const real W[4] = {(real)wc.sic[0], (real)wc.sic[1], (real)wc.sic[2], (real)wc.sic[3]};
-    const real cb = (real)(wc.cauchy_a * wc.cauchy_a), inv_cb = (real)(1.0 / (wc.cauchy_a * wc.cauchy_a));
+    const real inv_cb = (real)(1.0 / (wc.cauchy_a * wc.cauchy_a));
+    const bool diag_w = wc.sic[1] == 0.0 && wc.sic[2] == 0.0;
+    const bool vo = a.victim_only != 0;      // only then can a landmark of the table be left out (skip[])
     const FObs *fobs = a.fobs + (size_t)w * a.Kcap;
     real *hs = reinterpret_cast<real *>(a.hs) + (size_t)w * a.Ncap * a.Mcap * 6;
     real2 *jr = reinterpret_cast<real2 *>(a.jr) + (size_t)w * a.Ncap * a.Mcap;
@@ -401,8 +473,11 @@ lin_obs_kernel(PipeArgs a) {
     const int nwt = gridDim.x * kWarps, wid = blockIdx.x * kWarps + wv;
     const int r_begin = (int)((long long)rows * wid / nwt), r_end = (int)((long long)rows * (wid + 1) / nwt);
 
+    unsigned recs_a = (unsigned)__cvta_generic_to_shared(recs);
+    asm volatile("" : "+r"(recs_a));           // opaque: ptxas would otherwise re-derive the base from (N, Mp) in every row
     RowCursor cs(sbeg, srow, r_begin, rows);
     real cost_acc = 0;
+    LogAcc<real> la;
     while (cs.r < r_end) {
         const int sp = cs.sp, t = cs.t, an = cs.an;
         const int seg_end = sbeg[sp + 1];
@@ -417,8 +492,7 @@ lin_obs_kernel(PipeArgs a) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) F.c[i] = Ft[9 + i];
         }
-        real *hs_t = hs + (size_t)t * a.Mcap * 6;                 // this segment's slice of the record arrays
-        real2 *jr_t = jr + (size_t)t * a.Mcap;
+        const unsigned tM = (unsigned)t * (unsigned)a.Mcap;       // this segment's slice of the record arrays
         real2 q[15];
 #pragma unroll
         for (int i = 0; i < 15; ++i) q[i] = mk2((real)0, (real)0);
@@ -435,28 +509,34 @@ lin_obs_kernel(PipeArgs a) {
         // the table entry of the NEXT row is requested before the current row is evaluated
         // (12 of the entry's 16 bytes are loaded: a 16-byte load would tie up a register for the padding word)
         int k = cs.k0() + lane;
+        const FObs *pk = fobs + k;
         float2 z_nx = make_float2(0.f, 0.f);
         int l_nx = 0;
-        if (k < seg_end) { z_nx = *reinterpret_cast<const float2 *>(&fobs[k]); l_nx = fobs[k].lm; }
-        for (; cs.r < r_stop; cs.advance()) {
+        if (k < seg_end) { z_nx = *reinterpret_cast<const float2 *>(pk); l_nx = pk->lm; }
+        const int nrow = r_stop - cs.r;
+        for (int i = 0; i < nrow; ++i) {
             FObs o;
             o.zx = z_nx.x; o.zy = z_nx.y; o.lm = l_nx;
             const bool valid = k < seg_end;
-            k += 32;
-            if (cs.r + 1 < r_stop && k < seg_end) { z_nx = *reinterpret_cast<const float2 *>(&fobs[k]); l_nx = fobs[k].lm; }
+            k += 32; pk += 32;
+            if (i + 1 < nrow && k < seg_end) { z_nx = *reinterpret_cast<const float2 *>(pk); l_nx = pk->lm; }
             if (valid) {
                 const int l = o.lm;
-                if (!skip[l]) {
+                if (!(vo && skip[l])) {
                     ObsL<real> ol;
-                    linearize_blk<kLoss, real>(F, xs[l], xs[Mp + l], xs[2 * Mp + l], cls[3 * Mp + l], cls[4 * Mp + l],
-                                               cls[5 * Mp + l], cls[l], cls[Mp + l], cls[2 * Mp + l], o.zx, o.zy, W, cb, inv_cb, ol);
-                    cost_acc += ol.cost;
-                    jr_t[l] = mk2(ol.j0 * ol.j0 + ol.j1 * ol.j1, ol.j0 * ol.r0 + ol.j1 * ol.r1);
+                    double x[3];
+                    real xf[3], cl[3];
+                    lm_sm_load(recs_a + (unsigned)l * kLmSm, x, xf, cl);
+                    linearize_blk<kLoss, real>(F, x[0], x[1], x[2], xf[0], xf[1], xf[2], cl[0], cl[1], cl[2], o.zx, o.zy, W,
+                                               diag_w, inv_cb, ol);
+                    if (kLoss) la.add(ol.cost); else cost_acc += ol.cost;
+                    const unsigned rec = tM + (unsigned)l;
+                    jr[rec] = mk2(ol.j0 * ol.j0 + ol.j1 * ol.j1, ol.j0 * ol.r0 + ol.j1 * ol.r1);
                     if (need) {
                         real2 h[3];
 #pragma unroll
                         for (int p = 0; p < 3; ++p) h[p] = bfma(ol.j1, ol.Y1[p], bmul(ol.j0, ol.Y0[p]));
-                        real2 *dst = reinterpret_cast<real2 *>(hs_t + l * 6);
+                        real2 *dst = reinterpret_cast<real2 *>(hs) + (size_t)rec * 3;
                         dst[0] = h[0]; dst[1] = h[1]; dst[2] = h[2];
                         const real y0[6] = {ol.Y0[0].x, ol.Y0[0].y, ol.Y0[1].x, ol.Y0[1].y, ol.Y0[2].x, ol.Y0[2].y};
                         const real y1[6] = {ol.Y1[0].x, ol.Y1[0].y, ol.Y1[1].x, ol.Y1[1].y, ol.Y1[2].x, ol.Y1[2].y};
@@ -479,11 +559,15 @@ lin_obs_kernel(PipeArgs a) {
                     }
                 }
             }
+            if (kLoss && (i & 3) == 3) la.fold();
         }
+        if (kLoss && (nrow & 3)) la.fold();         // never more than 4 factors in the product
+        cs.r = r_stop; cs.seek();
         if (need) flush_q();
     }
 
     // ---- epilogue
+    if (kLoss) cost_acc = (real)0.5 * (real)(wc.cauchy_a * wc.cauchy_a) * la.total();
     double cd = (double)cost_acc;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cd += __shfl_xor_sync(0xffffffffu, cd, off);
