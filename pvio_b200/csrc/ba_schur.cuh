@@ -41,7 +41,7 @@ __host__ __device__ inline size_t schur_smem_layout(int N, size_t *o_g, size_t *
     size_t off = sizeof(double) * npairs * 36;                                  // Ss
     *o_g = off; off += sizeof(double) * (size_t)N * 6;                          // gsc
     *o_bar = off; off += 8 * (kSlots + 1);                                      // one mbarrier per ring slot + one for the direct part
-    *o_tab = off; off += sizeof(int32_t) * 80;                                  // per tile: f | g0 << 8 | g1 << 16 | flags << 24
+    *o_tab = off; off += sizeof(int32_t) * (80 + 8);                            // per tile: f | g0 << 8 | g1 << 16 | flags << 24; then the ring's release counters
     off = (off + 127) & ~(size_t)127;
     *o_ring = off;
     return off;
@@ -78,6 +78,7 @@ schur_kernel(PipeArgs a) {
     double *gsc = reinterpret_cast<double *>(smem_raw + o_g);       // [N][6]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + o_bar);
     int32_t *ttab = reinterpret_cast<int32_t *>(smem_raw + o_tab);  // [ntile]
+    int32_t *rel = ttab + 80;                                       // [kSlots] warps that are done with the slab in the slot
     real *stage = reinterpret_cast<real *>(smem_raw + o_ring);      // [kThreads][kFlushVals], aliases the ring
 
     const unsigned allm = (1u << N) - 1u;
@@ -145,6 +146,7 @@ schur_kernel(PipeArgs a) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&bars[j])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < kSlots) rel[tid] = 0;
     if (!exclusive) for (int i = tid; i < npairs * 36 + N * 6; i += kThreads) Ss[i] = 0.0;          // Ss, gsc contiguous
     __syncthreads();
     if (exclusive && tid == 0) {
@@ -159,20 +161,15 @@ schur_kernel(PipeArgs a) {
     bool d_ready = !exclusive;
     // Partial sums stay in `real` for at most 128 terms per thread: flush (-> fp64) after every fl_every-th slab and at the
     // end.  The staging buffer of a flush aliases the ring, so no copy may be in flight or resident across a flush
-    // point: slab j is issued only when no flush point lies between the slab being consumed and j.
+    // point.  Slab j is therefore issued at the later of two events: its slot is free (every warp is done with slab
+    // j - kSlots: the LAST warp to leave that slab issues the copy -- the warps of a CTA are not held together by a barrier
+    // per slab, they drift up to kSlots slabs apart) and the last flush before j is over (thread 0 issues it after the flush).
     const int fl_every = steps_per_slab > 0 ? max(1, 128 / steps_per_slab) : 1;
     const int fl_mul = (65536 + fl_every - 1) / fl_every;           // (p + 1) % fl_every == 0 without a division (p + 1 < 2^10)
     auto flush_point = [&](int p) { const int q = ((p + 1) * fl_mul) >> 16; return q * fl_every == p + 1 || p == n_slab - 1; };
-    int next_issue = 0;
-    auto issue_ahead = [&](int i) {                                  // thread 0, after slab i has been consumed (i = -1: start)
-        while (next_issue < n_slab && next_issue <= i + kSlots) {
-            bool blocked = false;
-            for (int p = i + 1; p < next_issue; ++p) blocked |= flush_point(p);
-            if (blocked) break;
-            issue(next_issue++);
-        }
-    };
-    if (tid == 0) issue_ahead(-1);
+    auto no_flush_in = [&](int lo, int hi) { bool b = false; for (int p = lo; p < hi; ++p) b |= flush_point(p); return !b; };
+    if (tid == 0)
+        for (int j = 0; j < kSlots && j < n_slab; ++j) if (no_flush_in(0, j)) issue(j);
 
     real2 acc[36];                               // acc[i * 6 + p]: row i of w h_f x column pair p of (h_g0 | h_g1)
     real2 accg[3];
@@ -259,11 +256,27 @@ schur_kernel(PipeArgs a) {
                 }
             }
         }
-        __syncthreads();                                            // slab i consumed by everybody
-        if (flush_point(i)) flush();
-        if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_ahead(i);
+        if (flush_point(i)) {
+            __syncthreads();                                        // slab i consumed by everybody, nothing in flight
+            flush();
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                for (int j = i + 1; j <= i + kSlots && j < n_slab; ++j) if (no_flush_in(i + 1, j)) issue(j);
+            }
+        } else {
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                const int sl = i % kSlots;
+                __threadfence_block();
+                if (atomicAdd(&rel[sl], 1) == kThreads / 32 - 1) {  // last warp out of slab i: its slot takes slab i + kSlots
+                    rel[sl] = 0;
+                    const int j = i + kSlots;
+                    if (j < n_slab && no_flush_in(i + 1, j)) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue(j);
+                    }
+                }
+            }
         }
     }
     // ---- reduced system out: Ss / gsc hold D - S (one CTA per window) or -S (several)

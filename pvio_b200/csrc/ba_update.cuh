@@ -65,7 +65,7 @@ __host__ __device__ inline size_t upd_smem_bytes(int N, int Mp, int warps) {
 // Residual-only evaluation of one block (candidate cost): fp64 numerators, the rest in `real`.
 template <bool kLoss, typename real>
 __device__ __forceinline__ real residual_cost_blk(const double (&Rwc)[9], const double (&c)[3], double x0, double x1, double x2,
-                                                  float zx, float zy, const real (&W)[4], real cauchy_b, real inv_cauchy_b) {
+                                                  float zx, float zy, const real (&W)[4], bool diag_w, real inv_cauchy_b) {
     const double d0 = x0 - c[0], d1 = x1 - c[1], d2 = x2 - c[2];
     const double y0 = Rwc[0] * d0 + Rwc[3] * d1 + Rwc[6] * d2;
     const double y1 = Rwc[1] * d0 + Rwc[4] * d1 + Rwc[7] * d2;
@@ -73,9 +73,10 @@ __device__ __forceinline__ real residual_cost_blk(const double (&Rwc)[9], const 
     const double nx = y0 - (double)zx * y2, ny = y1 - (double)zy * y2;
     const real iz = rcp_r((real)y2);
     const real u0 = (real)nx * iz, u1 = (real)ny * iz;
-    const real r0 = W[0] * u0 + W[1] * u1, r1 = W[2] * u0 + W[3] * u1;
+    real r0 = W[0] * u0, r1 = W[3] * u1;
+    if (!diag_w) { r0 += W[1] * u1; r1 += W[2] * u0; }
     const real s = r0 * r0 + r1 * r1;
-    return kLoss ? (real)0.5 * cauchy_b * log_r((real)1 + s * inv_cauchy_b) : (real)0.5 * s;
+    return kLoss ? (real)1 + s * inv_cauchy_b : (real)0.5 * s;      // with the loss: t (the caller accumulates b/2 log t, LogAcc)
 }
 
 // Back-substitution (thread per landmark, coalesced reads of the frame-major h records), Plus, and the
@@ -247,6 +248,7 @@ update_obs_kernel(UpdArgs a) {
     if (kMode != 1) {
         const real W[4] = {(real)wc.sic[0], (real)wc.sic[1], (real)wc.sic[2], (real)wc.sic[3]};
         const real cb = (real)(wc.cauchy_a * wc.cauchy_a), inv_cb = (real)(1.0 / (wc.cauchy_a * wc.cauchy_a));
+        const bool diag_w = wc.sic[1] == 0.0 && wc.sic[2] == 0.0;
         const FObs *fobs = a.fobs + (size_t)w * a.Kcap;
         const int32_t *sbeg = sg, *srow = sg + kMaxSeg + 1;
         const int rows = srow[nsp];
@@ -271,6 +273,8 @@ update_obs_kernel(UpdArgs a) {
                 for (int i = 0; i < 3; ++i) c[i] = Ft[9 + i];
             }
             real cacc = 0;
+            LogAcc<real> la;
+            int nfold = 0;
             for (; cs.r < r_stop; cs.advance()) {
                 const int k = cs.k0() + lane;
                 asm volatile("cp.async.wait_group %0;" :: "n"(kRing - 1) : "memory");
@@ -279,9 +283,12 @@ update_obs_kernel(UpdArgs a) {
                 slot = slot + 1 == kRing ? 0 : slot + 1;
                 if (k < seg_end) {
                     const int l = o.lm;
-                    cacc += residual_cost_blk<kLoss, real>(Rwc, c, xs[l], xs[Mp + l], xs[2 * Mp + l], o.zx, o.zy, W, cb, inv_cb);
+                    const real v = residual_cost_blk<kLoss, real>(Rwc, c, xs[l], xs[Mp + l], xs[2 * Mp + l], o.zx, o.zy, W, diag_w, inv_cb);
+                    if (kLoss) la.add(v); else cacc += v;
                 }
+                if (kLoss && (++nfold & 3) == 0) la.fold();
             }
+            if (kLoss) cacc = (real)0.5 * cb * la.total();
             s_cost += (double)cacc;
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
