@@ -66,9 +66,9 @@ static int ensure_inertial(Handle *h) {
     TRY(alloc(h, h->prior_x0, W * N * kFrameStride, true));
     // windows with motion states run the fp64 pipeline: h records of 8-byte elements
     release(h->hs); release(h->jr); release(h->lm_w);
-    TRY(alloc(h, h->hs, W * N * (size_t)h->Mcap * 6 * sizeof(double), false));
-    TRY(alloc(h, h->jr, W * N * (size_t)h->Mcap * 2 * sizeof(double), false));
-    TRY(alloc(h, h->lm_w, W * (size_t)h->Mcap * 2 * sizeof(double), false));
+    TRY(alloc(h, h->hs, 2 * W * N * (size_t)h->Mcap * 6 * sizeof(double), false));      // two buffer sets (LinBufs)
+    TRY(alloc(h, h->jr, 2 * W * N * (size_t)h->Mcap * 2 * sizeof(double), false));
+    TRY(alloc(h, h->lm_w, 2 * W * (size_t)h->Mcap * 2 * sizeof(double), false));
     h->hs_double = true;
     h->have_inertial = true;
     return 0;
@@ -436,9 +436,19 @@ static BatchShape batch_shape(Handle *h, int w0, int n, bool by_capacity) {
     return b;
 }
 
+static LinBufs lin_bufs(Handle *h) {
+    const size_t W = h->W, N = h->Ncap, M = h->Mcap, es = h->hs_double ? sizeof(double) : sizeof(float);
+    LinBufs b;
+    b.hs = W * N * M * 6 * es; b.jr = W * N * M * 2 * es; b.lm_w = W * M * 2 * es;
+    b.lm_msk = W * M; b.lm_aux = W * M;
+    b.Hred = h->sys_set; b.Hdd = h->sys_set; b.g = h->sys_set; b.cost = h->sys_set;
+    return b;
+}
+
 static PipeArgs make_pipe_args(Handle *h, const StepCfg &c) {
     PipeArgs a;
     memset(&a, 0, sizeof(a));
+    a.bufs = lin_bufs(h); a.frames_cand = h->frames_cand.d; a.rho_cand = h->rho_cand.d;
     a.hdr = h->hdr.d; a.cst = h->cst.d; a.fobs = h->fobs.d; a.seg = h->seg.d; a.lms = h->lms.d;
     a.rho = h->rho.d; a.frames = h->frames.d; a.ctrl = h->ctrl.d; a.lm_scale = h->lm_scale.d; a.lm_aux = h->lm_aux.d;
     a.jr = h->jr.d; a.hs = h->hs.d; a.lm_w = h->lm_w.d; a.lm_msk = h->lm_msk.d;
@@ -476,12 +486,71 @@ static size_t schur_launch_smem(int N, int nfree) { return schur_smem_bytes<real
     } while (0)
 
 // linearise + Schur stage of windows [w0, w0 + n)
-static int run_linearize(Handle *h, int n, const StepCfg &c, const BatchShape &b, bool loss = true, bool victim_only = false) {
+// zeroes the direct / reduced system of the buffer set a sweep is about to accumulate into with atomics (several CTAs
+// per window: the latency path)
+static __global__ void zero_system_kernel(PipeArgs a_in, int npairs_cap) {
+    PipeArgs a = a_in;
+    const int w = blockIdx.x + a.w0;
+    const int bsel = pipe_buffer(a, w);
+    if (bsel < 0) return;
+    pipe_select(a, bsel);
+    double *Hred = a.Hred + (size_t)w * npairs_cap * 36, *Hdd = a.Hdd + (size_t)w * a.Ncap * 36;
+    double *gdir = a.gdir + (size_t)w * a.Ncap * 6, *gred = a.gred + (size_t)w * a.Ncap * 6;
+    for (int i = threadIdx.x; i < npairs_cap * 36; i += blockDim.x) Hred[i] = 0.0;
+    for (int i = threadIdx.x; i < a.Ncap * 36; i += blockDim.x) Hdd[i] = 0.0;
+    for (int i = threadIdx.x; i < a.Ncap * 6; i += blockDim.x) { gdir[i] = 0.0; gred[i] = 0.0; }
+    if (threadIdx.x == 0) a.cost_vis[w] = 0.0;
+}
+
+// linearise sweep (+ per-landmark completion as its own launch when several CTAs share a window).  spec: the
+// speculative sweep of the trust-region loop over the CANDIDATE, into the window's other buffer set (ba_tr.cuh).
+static int launch_lin(Handle *h, int n, const StepCfg &c, const BatchShape &b, bool loss, bool victim_only, bool spec) {
     cudaStream_t st = c.stream ? c.stream : h->stream;
     const int gx = sweep_grid_x(h, n);
     PipeArgs a = make_pipe_args(h, c);
     a.victim_only = victim_only ? 1 : 0;
-    if (gx > 1) CK(h, cudaMemsetAsync(h->Hred.d, 0, sizeof(double) * h->Hred.n, st));    // several CTAs accumulate one window's system with atomics
+    a.spec = spec ? 1 : 0;
+    if (gx > 1) {
+        zero_system_kernel<<<n, 256, 0, st>>>(a, h->Ncap * (h->Ncap + 1) / 2);
+        ++h->launches;
+        LAUNCH_CK(h, "zero_system_kernel");
+    }
+    const int Mp = (b.M + 31) & ~31;
+    if (!h->hs_double) {
+        if (!loss) return fail(h, PVIO_B200_EINVAL, "the loss-free sweep runs in fp64");
+        lin_obs_kernel<true, float, kLinWarps, kLinBlocks><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<float>(b.N, Mp, kLinWarps), st>>>(a);
+        LAUNCH_CK(h, "lin_obs_kernel<float>");
+        if (gx > 1) { lm_finish_kernel<float><<<dim3((b.M + 127) / 128, n), 128, 0, st>>>(a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<float>"); }
+    } else {
+        if (loss) lin_obs_kernel<true, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp, kLinWarps), st>>>(a);
+        else lin_obs_kernel<false, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp, kLinWarps), st>>>(a);
+        LAUNCH_CK(h, "lin_obs_kernel<double>");
+        if (gx > 1) { lm_finish_kernel<double><<<dim3((b.M + 127) / 128, n), 128, 0, st>>>(a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<double>"); }
+    }
+    ++h->launches;
+    return 0;
+}
+
+static int launch_schur(Handle *h, int n, const StepCfg &c, const BatchShape &b, bool victim_only) {
+    cudaStream_t st = c.stream ? c.stream : h->stream;
+    const int gx = sweep_grid_x(h, n);
+    PipeArgs a = make_pipe_args(h, c);
+    a.victim_only = victim_only ? 1 : 0;
+    const int sgx = std::min(gx, std::max(1, (b.M + kSlab - 1) / kSlab));
+    if (!h->hs_double) {
+        schur_kernel<float, kSchurThreads, kSchurBlocks><<<dim3(sgx, n), kSchurThreads, schur_launch_smem<float>(b.N, b.nfree), st>>>(a);
+        LAUNCH_CK(h, "schur_kernel<float>");
+    } else {
+        schur_kernel<double, kSchurThreads, 1><<<dim3(sgx, n), kSchurThreads, schur_launch_smem<double>(b.N, b.nfree), st>>>(a);
+        LAUNCH_CK(h, "schur_kernel<double>");
+    }
+    ++h->launches;
+    return 0;
+}
+
+// the linearise + Schur stage at the state; its two halves are timed by events when it is the plain batched step
+static int run_linearize(Handle *h, int n, const StepCfg &c, const BatchShape &b, bool loss = true, bool victim_only = false) {
+    cudaStream_t st = c.stream ? c.stream : h->stream;
     if (h->kev.empty()) {
         h->kev.resize(3 * 256);
         for (auto &e : h->kev) CK(h, cudaEventCreate(&e));
@@ -489,28 +558,10 @@ static int run_linearize(Handle *h, int n, const StepCfg &c, const BatchShape &b
     const int slot = (h->kev_count % 256) * 3;
     const bool timed = !h->capturing && !c.loop && !c.stream;   // stage times are a property of the plain batched step
     if (timed) CK(h, cudaEventRecord(h->kev[slot], st));
-    const int Mp = (b.M + 31) & ~31;
-    const int sgx = std::min(gx, std::max(1, (b.M + kSlab - 1) / kSlab));
-    const bool dbl = h->hs_double;
-    if (!dbl) {
-        if (!loss) return fail(h, PVIO_B200_EINVAL, "the loss-free sweep runs in fp64");
-        lin_obs_kernel<true, float, kLinWarps, kLinBlocks><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<float>(b.N, Mp, kLinWarps), st>>>(a);
-        LAUNCH_CK(h, "lin_obs_kernel<float>");
-        if (gx > 1) { lm_finish_kernel<float><<<dim3((b.M + 127) / 128, n), 128, 0, st>>>(a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<float>"); }
-        if (timed) CK(h, cudaEventRecord(h->kev[slot + 1], st));
-        schur_kernel<float, kSchurThreads, kSchurBlocks><<<dim3(sgx, n), kSchurThreads, schur_launch_smem<float>(b.N, b.nfree), st>>>(a);
-        LAUNCH_CK(h, "schur_kernel<float>");
-    } else {
-        if (loss) lin_obs_kernel<true, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp, kLinWarps), st>>>(a);
-        else lin_obs_kernel<false, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp, kLinWarps), st>>>(a);
-        LAUNCH_CK(h, "lin_obs_kernel<double>");
-        if (gx > 1) { lm_finish_kernel<double><<<dim3((b.M + 127) / 128, n), 128, 0, st>>>(a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<double>"); }
-        if (timed) CK(h, cudaEventRecord(h->kev[slot + 1], st));
-        schur_kernel<double, kSchurThreads, 1><<<dim3(sgx, n), kSchurThreads, schur_launch_smem<double>(b.N, b.nfree), st>>>(a);
-        LAUNCH_CK(h, "schur_kernel<double>");
-    }
+    TRY(launch_lin(h, n, c, b, loss, victim_only, false));
+    if (timed) CK(h, cudaEventRecord(h->kev[slot + 1], st));
+    TRY(launch_schur(h, n, c, b, victim_only));
     if (timed) { CK(h, cudaEventRecord(h->kev[slot + 2], st)); ++h->kev_count; }
-    h->launches += 2;
     return 0;
 }
 
@@ -534,6 +585,7 @@ static int run_solve(Handle *h, int n, const StepCfg &c, const BatchShape &b) {
     a.pose_scale = h->pose_scale.d; a.dx_pose = h->dx_pose.d; a.v_pose = h->v_pose.d;
     a.Hfull = c.dump ? h->Hfull.d : nullptr; a.gfull = c.dump ? h->gfull.d : nullptr;
     a.Ncap = h->Ncap; a.compute_scale = c.compute_scale; a.mu_override = c.mu; a.w0 = c.w0; a.loop = c.loop;
+    a.bufs = lin_bufs(h);
     cudaStream_t st = c.stream ? c.stream : h->stream;
     // visual-only batches: the lean kernel (no IMU / prior / plane code, no full staging), a narrow CTA
     // per window so that many windows are resident per SM; otherwise the full kernel with a wide CTA
@@ -558,6 +610,7 @@ static CostArgs make_cost_args(Handle *h, const StepCfg &c) {
     k.w0 = c.w0;
     k.ctrl = h->ctrl.d; k.acc = h->acc.d; k.frames_state = h->frames.d; k.rho_state = h->rho.d; k.rho_cand = h->rho_cand.d;
     k.Mcap = h->Mcap; k.loop = c.loop; k.apply = c.apply; k.beta = c.beta;
+    k.cost_vis = h->cost_vis.d; k.cost_stride = h->sys_set;
     return k;
 }
 
@@ -570,6 +623,7 @@ static UpdArgs make_upd_args(Handle *h, const StepCfg &c) {
     u.rho_cand = h->rho_cand.d; u.frames_cand = h->frames_cand.d; u.dx_lm = h->dx_lm.d; u.lm_v = h->lm_v.d; u.acc = h->acc.d;
     u.Ncap = h->Ncap; u.Mcap = h->Mcap; u.Kcap = h->Kcap; u.mu_override = c.mu; u.w0 = c.w0;
     u.step_a = 0.0; u.step_b = c.beta; u.v_pose = h->v_pose.d; u.loop = c.loop;
+    u.bufs = lin_bufs(h);
     return u;
 }
 
@@ -578,9 +632,13 @@ static int launch_update(Handle *h, int n, const StepCfg &c, const BatchShape &b
     cudaStream_t st = c.stream ? c.stream : h->stream;
     const UpdArgs u = make_upd_args(h, c);
     const int Mp = (b.M + 31) & ~31;
-    constexpr int kW = kMode == 1 ? 8 : kUpdWarps;
-    constexpr int kB = kMode == 1 ? 2 : 4, kBf = kMode == 1 ? 2 : kUpdBlocks;
-    if (!h->hs_double) update_obs_kernel<true, float, kW, kBf, kMode><<<dim3(gx, n), kW * 32, upd_smem_bytes<float>(b.N, Mp, kW), st>>>(u);
+    constexpr int kW = kUpdWarps;
+    constexpr int kB = 4, kBf = kUpdBlocks;
+    if (kMode == 1 && n * 2 < h->sm_count) {        // latency path: one wide CTA per window for the back-substitution
+        if (!h->hs_double) update_obs_kernel<true, float, 8, 2, 1><<<dim3(gx, n), 256, upd_smem_bytes<float>(b.N, Mp, 8), st>>>(u);
+        else update_obs_kernel<true, double, 8, 2, 1><<<dim3(gx, n), 256, upd_smem_bytes<double>(b.N, Mp, 8), st>>>(u);
+    }
+    else if (!h->hs_double) update_obs_kernel<true, float, kW, kBf, kMode><<<dim3(gx, n), kW * 32, upd_smem_bytes<float>(b.N, Mp, kW), st>>>(u);
     else update_obs_kernel<true, double, kW, kB, kMode><<<dim3(gx, n), kW * 32, upd_smem_bytes<double>(b.N, Mp, kW), st>>>(u);
     ++h->launches;
     LAUNCH_CK(h, "update_obs_kernel");
@@ -608,7 +666,7 @@ static int run_gn_step(Handle *h, int n, const StepCfg &c, const BatchShape &b) 
     return 0;
 }
 
-// One iteration of the device-side trust-region loop (ba_tr.cuh): 8 launches, no host decision.
+// One iteration of the device-side trust-region loop (ba_tr.cuh): 9 launches, no host decision.
 static int iteration_body(Handle *h, int n, const StepCfg &c, const BatchShape &b) {
     cudaStream_t st = c.stream ? c.stream : h->stream;
     TRY(run_linearize(h, n, c, b));
@@ -625,7 +683,8 @@ static int iteration_body(Handle *h, int n, const StepCfg &c, const BatchShape &
         LAUNCH_CK(h, "jv_aux_kernel");
         h->launches += 2;
     }
-    TRY(launch_update<2>(h, n, c, b, sweep_grid_x(h, n)));
+    TRY(launch_update<2>(h, n, c, b, 1));
+    TRY(launch_lin(h, n, c, b, true, false, true));      // the candidate's linearisation: its cost decides, its Jacobians stay
     TRY(launch_aux_cost(h, n, c));
     return 0;
 }
@@ -770,9 +829,10 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     TRY(alloc(h, h->rho, W * M, true)); TRY(alloc(h, h->frames, W * N * kFrameStride, true));
     TRY(alloc(h, h->ctrl, W, true));
     TRY(alloc(h, h->rho_cand, W * M, false)); TRY(alloc(h, h->frames_cand, W * N * kFrameStride, false));
-    TRY(alloc(h, h->lm_scale, W * M, false)); TRY(alloc(h, h->lm_aux, W * M, false));
-    TRY(alloc(h, h->hs, W * N * M * 6 * sizeof(float), false)); TRY(alloc(h, h->jr, W * N * M * 2 * sizeof(float), false));
-    TRY(alloc(h, h->lm_w, W * M * 2 * sizeof(float), false)); TRY(alloc(h, h->lm_msk, W * M, false));
+    // the linearisation lives in two buffer sets (LinBufs, ba_types.h): everything below up to the reduced system is doubled
+    TRY(alloc(h, h->lm_scale, W * M, false)); TRY(alloc(h, h->lm_aux, 2 * W * M, false));
+    TRY(alloc(h, h->hs, 2 * W * N * M * 6 * sizeof(float), false)); TRY(alloc(h, h->jr, 2 * W * N * M * 2 * sizeof(float), false));
+    TRY(alloc(h, h->lm_w, 2 * W * M * 2 * sizeof(float), false)); TRY(alloc(h, h->lm_msk, 2 * W * M, false));
     {   // landing area of downloaded states: host only
         CK(h, cudaMallocHost(&h->frames_out.h, sizeof(double) * W * N * kFrameStride));
         CK(h, cudaMallocHost(&h->rho_out.h, sizeof(double) * W * M));
@@ -783,11 +843,12 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
     {   // the reduced-system outputs of the linearise kernel live in ONE allocation so that the
         // multi-CTA-per-window mode (atomic accumulation) needs a single memset per launch
         const size_t n_sys = W * (npc * 36 + N * 36 + N * 6 + N * 6 + 1);
-        TRY(alloc(h, h->Hred, n_sys, false));
+        TRY(alloc(h, h->Hred, 2 * n_sys, false));
         h->Hdd.d = h->Hred.d + W * npc * 36; h->Hdd.n = 0;
         h->gdir.d = h->Hdd.d + W * N * 36; h->gdir.n = 0;
         h->gred.d = h->gdir.d + W * N * 6; h->gred.n = 0;
         h->cost_vis.d = h->gred.d + W * N * 6; h->cost_vis.n = 0;
+        h->sys_set = n_sys;                                   // set 1 of each array lies n_sys elements behind set 0
     }
     TRY(alloc(h, h->acc, W * kAcc, true)); TRY(alloc(h, h->aux_cost, W, false));
     TRY(alloc(h, h->Hfull, (15 * N) * (15 * N), true)); TRY(alloc(h, h->gfull, 15 * N, true));
@@ -801,7 +862,9 @@ int pvio_b200_create(int device, int max_windows, int max_frames, int max_landma
         CK(h, cudaFuncSetAttribute(schur_kernel<float, kSchurThreads, kSchurBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         CK(h, cudaFuncSetAttribute(schur_kernel<double, kSchurThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         CK(h, cudaFuncSetAttribute(update_obs_kernel<true, float, kUpdWarps, kUpdBlocks, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(update_obs_kernel<true, float, kUpdWarps, kUpdBlocks, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         CK(h, cudaFuncSetAttribute(update_obs_kernel<true, float, 8, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CK(h, cudaFuncSetAttribute(update_obs_kernel<true, double, kUpdWarps, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         CK(h, cudaFuncSetAttribute(update_obs_kernel<true, float, kUpdWarps, kUpdBlocks, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         CK(h, cudaFuncSetAttribute(update_obs_kernel<true, double, kUpdWarps, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         CK(h, cudaFuncSetAttribute(update_obs_kernel<true, double, 8, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));

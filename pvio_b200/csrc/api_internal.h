@@ -33,6 +33,7 @@ struct Handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     int64_t launches = 0;
+    size_t sys_set = 0;                           // elements between the two buffer sets of the reduced-system arrays (LinBufs)
     int sm_count = 148;
 
     // vision (always allocated)

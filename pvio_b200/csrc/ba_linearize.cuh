@@ -57,7 +57,30 @@ struct PipeArgs {
     double mu_override;          // >= 0: use this mu instead of ctrl->mu
     int w0;                      // first window of this launch
     int loop;                    // 1: iteration of the device-side trust-region loop (ba_tr.cuh): obey the window's flags
+    int spec;                    // loop only. 1: linearise the CANDIDATE (frames_cand, rho_cand) into the window's other buffer set
+    const double *frames_cand, *rho_cand;
+    LinBufs bufs;
 };
+
+__device__ __forceinline__ void pipe_select(PipeArgs &a, int b) {
+    if (!b) return;
+    a.hs = reinterpret_cast<char *>(a.hs) + a.bufs.hs; a.jr = reinterpret_cast<char *>(a.jr) + a.bufs.jr;
+    a.lm_w = reinterpret_cast<char *>(a.lm_w) + a.bufs.lm_w; a.lm_msk += a.bufs.lm_msk; a.lm_aux += a.bufs.lm_aux;
+    a.Hred += a.bufs.Hred; a.Hdd += a.bufs.Hdd; a.gdir += a.bufs.g; a.gred += a.bufs.g; a.cost_vis += a.bufs.cost;
+}
+// which buffer set a sweep of window w works on, or -1: nothing to do for this window
+__device__ __forceinline__ int pipe_buffer(const PipeArgs &a, int w) {
+    if (!a.loop) return 0;
+    const WinCtrl &c = a.ctrl[w];
+    if (a.spec) return (c.done || c.skip) ? -1 : 1 - c.buf;
+    return (c.done || c.have_lin) ? -1 : c.buf;
+}
+// the pivots of a speculative sweep use the mu the next iteration will have IF its step is accepted (tr_decide)
+__device__ __forceinline__ double pipe_mu(const PipeArgs &a, int w) {
+    if (a.mu_override >= 0.0) return a.mu_override;
+    const double mu = a.ctrl[w].mu;
+    return a.spec ? fmax(1e-8, 2.0 * mu / 10.0) : mu;
+}
 
 // ---- packed pairs: fma.rn.f32x2 (FFMA2 with a scalar-broadcast operand) for float, two DFMA for double
 template <typename real> struct Vec2;
@@ -358,13 +381,16 @@ __device__ __forceinline__ void lm_finish(const PipeArgs &a, int w, int l, int N
 }
 
 template <typename real>
-__global__ void __launch_bounds__(128) lm_finish_kernel(PipeArgs a) {
+__global__ void __launch_bounds__(128) lm_finish_kernel(PipeArgs a_in) {
+    PipeArgs a = a_in;
     const int w = blockIdx.y + a.w0;
-    if (a.loop && (a.ctrl[w].done || a.ctrl[w].reuse)) return;
+    const int bsel = pipe_buffer(a, w);
+    if (bsel < 0) return;
+    pipe_select(a, bsel);
     const WinHdr &H = a.hdr[w];
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= ((H.M + 3) & ~3)) return;
-    const double mu = a.mu_override >= 0.0 ? a.mu_override : a.ctrl[w].mu;
+    const double mu = pipe_mu(a, w);
     const int compute_scale = a.loop ? (a.ctrl[w].have_scale == 0) : a.compute_scale;
     lm_finish<real>(a, w, l, H.N, H.M, (unsigned)H.fixed_mask & ((1u << H.N) - 1u), mu, compute_scale);
 }
@@ -390,11 +416,15 @@ __host__ __device__ inline size_t lin_smem_bytes(int N, int Mp, int /*warps*/) {
 
 template <bool kLoss, typename real, int kWarps, int kMinBlocks>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
-lin_obs_kernel(PipeArgs a) {
+lin_obs_kernel(PipeArgs a_in) {
     typedef typename Vec2<real>::type real2;
     constexpr int kThreads = kWarps * 32;
+    PipeArgs a = a_in;
     const int w = blockIdx.y + a.w0;
-    if (a.loop && (a.ctrl[w].done || a.ctrl[w].reuse)) return;
+    const int bsel = pipe_buffer(a, w);
+    if (bsel < 0) return;
+    pipe_select(a, bsel);
+    if (a.spec) { a.frames = a.frames_cand; a.rho = a.rho_cand; }
     const WinHdr &H = a.hdr[w];
     const WinConst &wc = a.cst[w];
     const int N = H.N, M = H.M;
@@ -575,7 +605,7 @@ lin_obs_kernel(PipeArgs a) {
     __syncthreads();
     const bool exclusive = (gridDim.x == 1);
     if (exclusive) {       // this CTA wrote every record of the window: complete the landmarks here
-        const double mu = a.mu_override >= 0.0 ? a.mu_override : a.ctrl[w].mu;
+        const double mu = pipe_mu(a, w);
         const int compute_scale = a.loop ? (a.ctrl[w].have_scale == 0) : a.compute_scale;
         for (int l = tid; l < ((M + 3) & ~3); l += kThreads) lm_finish<real>(a, w, l, N, M, fixed, mu, compute_scale);
     }

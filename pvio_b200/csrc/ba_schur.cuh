@@ -61,10 +61,15 @@ __host__ __device__ inline int schur_tiles(int nf) { int t = 0; for (int f = 0; 
 
 template <typename real, int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-schur_kernel(PipeArgs a) {
+schur_kernel(PipeArgs a_in) {
     typedef typename Vec2<real>::type real2;
+    PipeArgs a = a_in;
     const int w = blockIdx.y + a.w0;
-    if (a.loop && (a.ctrl[w].done || a.ctrl[w].reuse)) return;
+    if (a.loop) {
+        const WinCtrl &c = a.ctrl[w];
+        if (c.done || c.reuse) return;
+        pipe_select(a, c.buf);
+    }
     const WinHdr &H = a.hdr[w];
     const int N = H.N, M = H.M;
     const int tid = threadIdx.x;

@@ -58,6 +58,7 @@ struct SolveArgs {
     int w0;
     double mu_override;
     int loop;                  // 1: iteration of the device-side trust-region loop (ba_tr.cuh): obey the window's flags
+    LinBufs bufs;
 };
 
 // The dense system is stored as packed lower-triangular 4x4 TILES (tile (I,J), J <= I, at
@@ -451,6 +452,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     const double *frames = a.frames + (size_t)w * a.Ncap * kFrameStride;
     WinCtrl &ctrl = a.ctrl[w];
     if (a.loop && (ctrl.done || ctrl.reuse)) return;         // finished, or the rejected step's linearisation is still valid
+    const size_t bsel = a.loop ? (size_t)ctrl.buf : 0;       // buffer set holding the linearisation of the state (LinBufs)
     const int compute_scale = a.loop ? (ctrl.have_scale == 0) : a.compute_scale;
     const double mu = a.mu_override >= 0.0 ? a.mu_override : ctrl.mu;
 
@@ -494,10 +496,10 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     if (!kFull) {
         // Lean path (batched visual-only windows): no full staging of the xi blocks -- groups of 6 threads
         // pull one 6x6 block at a time through a small shared buffer, so that ~9 windows fit per SM.
-        const double *Hred = a.Hred + (size_t)w * npairs_cap * 36;
-        const double *Hdd = a.Hdd + (size_t)w * a.Ncap * 36;
-        const double *gdir = a.gdir + (size_t)w * a.Ncap * 6;
-        const double *gred = a.gred + (size_t)w * a.Ncap * 6;
+        const double *Hred = a.Hred + bsel * a.bufs.Hred + (size_t)w * npairs_cap * 36;
+        const double *Hdd = a.Hdd + bsel * a.bufs.Hdd + (size_t)w * a.Ncap * 36;
+        const double *gdir = a.gdir + bsel * a.bufs.g + (size_t)w * a.Ncap * 6;
+        const double *gred = a.gred + bsel * a.bufs.g + (size_t)w * a.Ncap * 6;
         double *Ms = scr + Dp;                       // [G][36]
         for (int e = tid; e < nfr * 6; e += nt) {    // direct diagonal diag(T_f^T Xd T_f)
             const int cf = e / 6, i = e - cf * 6;
@@ -564,10 +566,10 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     // ---- vision blocks: H_delta[f,gf] = T_f^T X T_g.  Stage the xi-coordinate blocks in shared
     // memory (coalesced), X <- X T_g in place, then T_f^T (X T_g) into the packed system.
     {
-        const double *Hred = a.Hred + (size_t)w * npairs_cap * 36;
-        const double *Hdd = a.Hdd + (size_t)w * a.Ncap * 36;
-        const double *gdir = a.gdir + (size_t)w * a.Ncap * 6;
-        const double *gred = a.gred + (size_t)w * a.Ncap * 6;
+        const double *Hred = a.Hred + bsel * a.bufs.Hred + (size_t)w * npairs_cap * 36;
+        const double *Hdd = a.Hdd + bsel * a.bufs.Hdd + (size_t)w * a.Ncap * 36;
+        const double *gdir = a.gdir + bsel * a.bufs.g + (size_t)w * a.Ncap * 6;
+        const double *gred = a.gred + bsel * a.bufs.g + (size_t)w * a.Ncap * 6;
         double *Xs = scr;                        // [npairs][36]
         double *Xd = Xs + npairs * 36;           // [N][36]
         double *gx = Xd + N * 36;                // [2][N][6]
@@ -871,8 +873,10 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             ctrl.dxnorm2 = dx2;
             ctrl.xnorm2 = x2;
             ctrl.gmax = gmax;
-            ctrl.cost_vis = a.cost_vis[w];
-            ctrl.cost = a.cost_vis[w] + cost_sm[1] + cost_sm[2] + cost_sm[3];
+            const double cv = a.cost_vis[bsel * a.bufs.cost + w];
+            ctrl.cost_vis = cv;
+            ctrl.cost = cv + cost_sm[1] + cost_sm[2] + cost_sm[3];
+            ctrl.have_lin = 1;
             ctrl.solve_failed = ok ? 0 : 1;
             if (compute_scale) ctrl.have_scale = 1;
             ctrl.fresh = 1;
@@ -910,6 +914,8 @@ struct CostArgs {
     const double *rho_cand;
     int Mcap;
     int loop;                      // 1: tr_decide (device-side trust-region loop); 0: plain Gauss-Newton step, `apply` decides
+    const double *cost_vis;        // loop: [2][W] reprojection cost of the sweeps; the candidate's is in the window's OTHER buffer set
+    size_t cost_stride;
     int apply;
     double beta;                   // loop == 0: the step was beta * dx_gn (model change of the truncated step)
 };
@@ -991,7 +997,12 @@ static __global__ void aux_cost_kernel(CostArgs a) {
         a.out[w] = acc;
         const double *av = a.acc + (size_t)w * kAcc;
         bool accept;
-        if (a.loop) accept = tr_decide(ctrl, av, acc);
+        if (a.loop) {
+            WinCtrl c = ctrl;                   // one round trip of the record instead of a dependent chain of global accesses
+            accept = tr_decide(c, av, a.cost_vis[(size_t)(1 - c.buf) * a.cost_stride + w], acc);
+            if (accept) c.buf ^= 1;             // the candidate's linearisation becomes the state's
+            ctrl = c;
+        }
         else {
             ctrl.cand_cost_vis = av[0];
             ctrl.cand_cost = av[0] + acc;
@@ -1033,7 +1044,7 @@ static __global__ void jv_aux_kernel(JvAuxArgs ja) {
     double *ev = reinterpret_cast<double *>(smem_raw);      // [15 n_prior] E v
     WinCtrl &ctrl = a.ctrl[w];
     if (a.loop && (ctrl.done || ctrl.skip)) return;
-    if (a.loop && !ctrl.need_jv) { if (tid == 0) tr_after_jv(ctrl, ja.acc + (size_t)w * kAcc); return; }
+    if (a.loop && !ctrl.need_jv) { if (tid == 0) { WinCtrl c = ctrl; tr_after_jv(c, ja.acc + (size_t)w * kAcc); ctrl = c; } return; }
     if (tid == 0) acc = 0.0;
     __syncthreads();
     if (H.use_inertial) {
@@ -1101,7 +1112,7 @@ static __global__ void jv_aux_kernel(JvAuxArgs ja) {
     if (tid == 0) {
         double *av = ja.acc + (size_t)w * kAcc;
         if (acc != 0.0) av[10] += acc;           // one CTA per window owns slot 10
-        if (a.loop) tr_after_jv(ctrl, av);
+        if (a.loop) { WinCtrl c = ctrl; tr_after_jv(c, av); ctrl = c; }
     }
 }
 

@@ -4,10 +4,15 @@
 // trust_region_minimizer.cc / dogleg_strategy.cc), one decision record (WinCtrl) per window.
 //
 // One iteration is a FIXED kernel sequence (api.cu: iteration_body), every kernel looks at its window's flags first:
-//   lin_obs, schur, solve      skipped when the previous step was rejected (`reuse`: same linearisation, same GN step)
+//   lin_obs (state)            only when the window has no valid linearisation (first iteration, retry after a failed
+//                              linear solve with mu * 10): into the window's buffer set WinCtrl::buf
+//   schur, solve               skipped when the previous step was rejected (`reuse`: same linearisation, same GN step)
 //   backsub  (+ tr_after_backsub)   GN step of the inverse depths; is the GN step inside the trust region?
 //   jv_vision, jv_aux (+ tr_after_jv)   only when it is not: |J v|^2 for the Cauchy point, dogleg interpolation
-//   candidate                  Plus(x, step), reprojection cost at the candidate
+//   candidate                  Plus(x, step)
+//   lin_obs (candidate)        the FULL linearisation of the candidate into the other buffer set: its cost is the
+//                              reprojection cost the decision needs; on acceptance the buffer sets swap, so the
+//                              residual-only evaluation of ceres and the relinearisation after it are one sweep
 //   aux_cost (+ tr_decide)     IMU / prior / plane cost at the candidate; accept / reject, radius, mu, termination
 // so a whole solve is max_iterations identical bodies captured in ONE CUDA graph: no device -> host read, no host
 // decision, one launch per solve (single window) or per batch (per-window termination).
@@ -37,7 +42,7 @@ __device__ inline void tr_after_backsub(WinCtrl &c, const double *acc) {
     if (c.max_time_ns > 0.0 && global_ns() - c.t_start_ns > c.max_time_ns) { c.done = 1; return; }
     if (c.iteration >= c.max_iter) { c.done = 1; return; }
     if (c.solve_failed) {
-        c.mu *= 10.0; c.reuse = 0; c.skip = 1;
+        c.mu *= 10.0; c.reuse = 0; c.skip = 1; c.have_lin = 0;      // the pivots depend on mu: linearise the state again
         if (c.mu > 1.0) { c.usable = 0; tr_terminate(c, PVIO_B200_TERM_FAILURE); }
         return;
     }
@@ -84,11 +89,11 @@ __device__ inline void tr_after_jv(WinCtrl &c, const double *acc) {
 
 // After the candidate sweeps: step acceptance (trust_region_minimizer.cc).  Returns true when the candidate
 // becomes the state (the caller copies it).
-__device__ inline bool tr_decide(WinCtrl &c, const double *acc, double aux_cost) {
+__device__ inline bool tr_decide(WinCtrl &c, const double *acc, double cand_vis, double aux_cost) {
     c.fresh = 0;
     if (c.done || c.skip) return false;
-    c.cand_cost_vis = acc[0];
-    c.cand_cost = acc[0] + aux_cost;
+    c.cand_cost_vis = cand_vis;
+    c.cand_cost = cand_vis + aux_cost;
     const double cost = c.cost;
     const double x_norm = sqrt(c.xnorm2 + acc[5]);
     const double step_amb = sqrt(acc[6] + acc[4]);
@@ -122,7 +127,7 @@ static __global__ void init_ctrl_kernel(WinCtrl *ctrl, double mu, double radius,
     if (threadIdx.x == 0) {
         c.mu = mu; c.radius = radius; c.iteration = 0; c.accepted = 0; c.done = 0;
         c.termination = PVIO_B200_TERM_NO_CONVERGENCE; c.solve_failed = 0; c.have_scale = 0; c.usable = 1;
-        c.reuse = 0; c.need_jv = 0; c.skip = 0; c.fresh = 0; c.max_iter = max_iter;
+        c.reuse = 0; c.need_jv = 0; c.skip = 0; c.fresh = 0; c.max_iter = max_iter; c.buf = 0; c.have_lin = 0;
         c.step_a = 0.0; c.step_b = 1.0; c.step_norm = 0.0; c.initial_cost = 0.0; c.cost = 0.0; c.cand_cost = 0.0;
         c.max_time_ns = max_time_s > 0.0 && max_time_s < 1e5 ? max_time_s * 1e9 : 0.0;
         c.t_start_ns = global_ns();

@@ -68,7 +68,7 @@ struct WinConst {                   // per-window doubles
     double pad;
 };
 
-struct WinCtrl {                    // per-window solver state (device resident)
+struct __align__(16) WinCtrl {      // per-window solver state (device resident)
     double mu, radius;
     double cost, cand_cost;         // 0.5 * sum rho(s): current / candidate
     double cost_vis, cand_cost_vis; // reprojection part accumulated by the sweeps
@@ -83,6 +83,18 @@ struct WinCtrl {                    // per-window solver state (device resident)
     int32_t iteration, accepted, done, termination;
     int32_t solve_failed, have_scale, usable, reuse;   // reuse: the next iteration keeps linearisation and GN solve
     int32_t need_jv, skip, max_iter, fresh;            // skip: the rest of this iteration's kernels do nothing
+    int32_t buf, have_lin, pad0, pad1;                 // buf: buffer set (LinBufs) holding the linearisation of the STATE;
+                                                       // have_lin: it is valid for the current state and mu
+};
+
+// The linearisation of a window (records, pivots, direct blocks, reduced system, reprojection cost) lives in one of two
+// buffer sets.  An iteration of the trust-region loop linearises its CANDIDATE into the other set: the cost of that
+// sweep decides the step, and when the step is accepted the Jacobians of the new state are already there (WinCtrl::buf
+// flips) -- the residual-only evaluation ceres does for the decision and the relinearisation that follows it are ONE
+// sweep here.  Offsets of set 1 from set 0: bytes for the type-erased arrays, elements for the others.
+struct LinBufs {
+    size_t hs, jr, lm_w;            // bytes
+    size_t lm_msk, lm_aux, Hred, Hdd, g, cost;   // elements
 };
 
 // per-landmark Schur scalars written by the linearise kernel, read by the update kernel

@@ -43,6 +43,7 @@ struct UpdArgs {
     double step_a, step_b;
     const double *v_pose;     // [W][Ncap][15] from solve_kernel
     int loop;                 // jv_vision_kernel: 1 = only windows whose GN step left the trust region (WinCtrl::need_jv)
+    LinBufs bufs;             // loop: hs / lm_aux of the window's current buffer set (WinCtrl::buf)
 };
 
 template <typename real>
@@ -86,7 +87,8 @@ __device__ __forceinline__ real residual_cost_blk(const double (&Rwc)[9], const 
 //            belongs to CTA (l / 32) mod gridDim.x, the rows are cut as in lin_obs_kernel).
 //   kMode 1  back-substitution only (gridDim.x = 1): GN step of the inverse depths and its scalars, then the
 //            trust-region test of the step (tr_after_backsub): first half of an iteration of the device-side loop.
-//   kMode 2  candidate only: Plus(x, step_b dx_gn - step_a v) with the step chosen by tr_after_jv, candidate cost.
+//   kMode 2  candidate only: Plus(x, step_b dx_gn - step_a v) with the step chosen by tr_after_jv (its cost comes from
+//            the speculative linearise sweep that follows, ba_tr.cuh).
 template <bool kLoss, typename real, int kWarps, int kMinBlocks, int kMode>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 update_obs_kernel(UpdArgs a) {
@@ -155,15 +157,16 @@ update_obs_kernel(UpdArgs a) {
         }
     }
     if (tid < 8) red[tid] = 0.0;
-    if (kMode != 1) for (int i = tid; i < kSegTab; i += kThreads) sg[i] = a.seg[(size_t)w * kSegTab + i];
+    if (kMode == 0) for (int i = tid; i < kSegTab; i += kThreads) sg[i] = a.seg[(size_t)w * kSegTab + i];
     __syncthreads();
 
     const double mu = a.mu_override >= 0.0 ? a.mu_override : ctrl.mu;
     const LmRec *lms = a.lms + (size_t)w * a.Mcap;
     const double *rho = a.rho + (size_t)w * a.Mcap;
     const double *lm_scale = a.lm_scale + (size_t)w * a.Mcap;
-    const LmAux *aux = a.lm_aux + (size_t)w * a.Mcap;
-    const real *hs = reinterpret_cast<const real *>(a.hs) + (size_t)w * a.Ncap * a.Mcap * 6;
+    const size_t bsel = a.loop ? (size_t)ctrl.buf : 0;
+    const LmAux *aux = a.lm_aux + bsel * a.bufs.lm_aux + (size_t)w * a.Mcap;
+    const real *hs = reinterpret_cast<const real *>(reinterpret_cast<const char *>(a.hs) + bsel * a.bufs.hs) + (size_t)w * a.Ncap * a.Mcap * 6;
     double *rho_c = a.rho_cand + (size_t)w * a.Mcap;
     double *dxl = a.dx_lm + (size_t)w * a.Mcap;
     double *lmv = a.lm_v + (size_t)w * a.Mcap;
@@ -230,7 +233,7 @@ update_obs_kernel(UpdArgs a) {
             if (kMode == 2 && n_obs > 0) { drho = dxl[l]; vl = lmv[l]; }
             drho = step_b * drho - step_a * vl;
             if (mine) { s_dx2 += drho * drho; rho_c[l] = rl + drho; dxl[l] = drho; }
-            if (n_obs > 0) {
+            if (kMode != 2 && n_obs > 0) {
                 const double *Fa = Fc + anchor * 12;
                 const double ir = 1.0 / (rl + drho);
                 const double zx = (double)lr.zrx, zy = (double)lr.zry;
@@ -239,13 +242,13 @@ update_obs_kernel(UpdArgs a) {
                 x2 = (Fa[6] * zx + Fa[7] * zy + Fa[8]) * ir + Fa[11];
             }
         }
-        if (kMode != 1) { xs[l] = x0; xs[Mp + l] = x1; xs[2 * Mp + l] = x2; }
+        if (kMode == 0) { xs[l] = x0; xs[Mp + l] = x1; xs[2 * Mp + l] = x2; }
     }
     __syncthreads();
 
     // ---- phase 2: candidate cost over the rows of the frame-major table
     double s_cost = 0.0;
-    if (kMode != 1) {
+    if (kMode == 0) {
         const real W[4] = {(real)wc.sic[0], (real)wc.sic[1], (real)wc.sic[2], (real)wc.sic[3]};
         const real cb = (real)(wc.cauchy_a * wc.cauchy_a), inv_cb = (real)(1.0 / (wc.cauchy_a * wc.cauchy_a));
         const bool diag_w = wc.sic[1] == 0.0 && wc.sic[2] == 0.0;
@@ -313,10 +316,10 @@ update_obs_kernel(UpdArgs a) {
             acc[tid] = o;
         }
         __syncthreads();
-        if (tid == 0) tr_after_backsub(ctrl, acc);
+        if (tid == 0) { WinCtrl c = ctrl; tr_after_backsub(c, acc); ctrl = c; }
     } else if (tid < 8) {
         const int slot = tid < 6 ? tid : tid + 1;            // slot 6 is the frames' ambient step norm
-        if (kMode == 2 && !(tid == 0 || tid == 4)) return;   // the GN scalars were written by the back-substitution
+        if (kMode == 2 && tid != 4) return;                  // the GN scalars were written by the back-substitution
         if (red[tid] != 0.0) atomicAdd(acc + slot, red[tid]);
     }
 }
@@ -356,7 +359,7 @@ jv_vision_kernel(UpdArgs a) {
     const LmRec *lms = a.lms + (size_t)w * a.Mcap;
     const double *rho = a.rho + (size_t)w * a.Mcap;
     const double *lm_scale = a.lm_scale + (size_t)w * a.Mcap;
-    const LmAux *aux = a.lm_aux + (size_t)w * a.Mcap;
+    const LmAux *aux = a.lm_aux + (a.loop ? (size_t)a.ctrl[w].buf * a.bufs.lm_aux : 0) + (size_t)w * a.Mcap;
     double acc = 0.0;
     for (int ci = wv;; ci += 8) {
         const int ch = ci * gridDim.x + blockIdx.x;
