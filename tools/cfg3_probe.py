@@ -11,3 +11,8 @@ t = time.perf_counter()
 for _ in range(5):
     o, sm = ba.solve(w, st, max_iterations=10)
 print("cfg3 solve ms", (time.perf_counter() - t) / 5 * 1e3, sm["iterations"], sm["solve_seconds"] * 1e3)
+if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
+    w4, st4, _ = synth.make_cfg4()
+    for _ in range(3):
+        o, sm = ba.solve(w4, st4, max_iterations=10)
+    print("cfg4 solve", sm["iterations"], sm["solve_seconds"] * 1e3)
