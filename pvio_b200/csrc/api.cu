@@ -97,8 +97,9 @@ static int ensure_planes(Handle *h, int T, int O) {
             memcpy(tz.h + i * On * 2, h->pt_z.h + i * h->Ocap * 2, sizeof(float) * h->Ocap * 2);
         }
     }
-    release(h->plane_param); release(h->pt_plane); release(h->pt_begin); release(h->pt_frame); release(h->pt_z);
+    release(h->plane_param); release(h->pt_plane); release(h->pt_begin); release(h->pt_frame); release(h->pt_z); release(h->pt_J);
     h->plane_param = pp; h->pt_plane = tp; h->pt_begin = tb; h->pt_frame = tf; h->pt_z = tz;
+    TRY(alloc(h, h->pt_J, W * Tn * (6 * (size_t)h->Ncap + 2), false));      // device scratch of solve_kernel's plane block
     h->Tcap = Tn; h->Ocap = On;
     h->have_planes = true;
     return 0;
@@ -581,7 +582,7 @@ static int run_solve(Handle *h, int n, const StepCfg &c, const BatchShape &b) {
     a.prior_frames = h->prior_frames.d; a.prior_S = h->prior_S.d; a.prior_L = h->prior_L.d; a.prior_e = h->prior_e.d;
     a.prior_x0 = h->prior_x0.d;
     a.plane_param = h->plane_param.d; a.pt_plane = h->pt_plane.d; a.pt_begin = h->pt_begin.d; a.pt_frame = h->pt_frame.d;
-    a.pt_z = h->pt_z.d; a.Pcap = h->Pcap; a.Tcap = h->Tcap; a.Ocap = h->Ocap;
+    a.pt_z = h->pt_z.d; a.Pcap = h->Pcap; a.Tcap = h->Tcap; a.Ocap = h->Ocap; a.pt_J = h->pt_J.d;
     a.pose_scale = h->pose_scale.d; a.dx_pose = h->dx_pose.d; a.v_pose = h->v_pose.d;
     a.Hfull = c.dump ? h->Hfull.d : nullptr; a.gfull = c.dump ? h->gfull.d : nullptr;
     a.Ncap = h->Ncap; a.compute_scale = c.compute_scale; a.mu_override = c.mu; a.w0 = c.w0; a.loop = c.loop;
@@ -895,7 +896,7 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     release(h->Hfull); release(h->gfull);
     release(h->imu_idx); release(h->imu_data); release(h->prior_frames); release(h->prior_S); release(h->prior_L);
     release(h->prior_e); release(h->prior_x0);
-    release(h->plane_param); release(h->pt_plane); release(h->pt_begin); release(h->pt_frame); release(h->pt_z);
+    release(h->pt_J); release(h->plane_param); release(h->pt_plane); release(h->pt_begin); release(h->pt_frame); release(h->pt_z);
     drop_graphs(h);
     for (auto &e : h->kev) cudaEventDestroy(e);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);

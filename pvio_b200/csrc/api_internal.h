@@ -65,6 +65,7 @@ struct Handle {
     DevBuf<double> plane_param;
     DevBuf<int32_t> pt_plane, pt_begin, pt_frame;
     DevBuf<float> pt_z;
+    DevBuf<double> pt_J;                          // [W][Tcap][6 Ncap + 2] scratch of the plane block of solve_kernel
     // host bookkeeping per slot
     std::vector<std::vector<int32_t>> perm;      // packed landmark -> caller landmark
     std::vector<int> slot_M, slot_N, slot_K;

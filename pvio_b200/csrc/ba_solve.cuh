@@ -47,6 +47,7 @@ struct SolveArgs {
     const int32_t *pt_frame;       // [W][Ocap]
     const float *pt_z;             // [W][Ocap][2]  (observations are stored fp32 like the reprojection table)
     int Pcap, Tcap, Ocap;
+    double *pt_J;                  // [W][Tcap][6 Ncap + 2] scratch: corrected Jacobian rows of the plane tracks
     // scaling / outputs
     double *pose_scale;        // [W][15*Ncap]
     double *dx_pose;           // [W][Ncap][15]
@@ -742,6 +743,12 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         const int32_t *ptf = a.pt_frame + (size_t)w * a.Ocap;
         const float *ptz = a.pt_z + (size_t)w * a.Ocap * 2;
         const double cb = wc.cauchy_a * wc.cauchy_a;
+        // thread per track: the corrected 1 x 6K Jacobian row, spread over the window's frames (zeros where the track has
+        // no observation), and the corrected residual go to a scratch row; then thread per ENTRY of the pose block of the
+        // system sums over the tracks -- no atomics (fp64 atomicAdd on shared memory is a compare-and-swap loop, and all
+        // tracks of a plane hit the same frames: the atomic version took 600 us of the kernel's 820 on cfg4)
+        const int PW = 6 * a.Ncap + 2;                              // row: [6 N] Jacobian, residual
+        double *PJ = a.pt_J + (size_t)w * a.Tcap * PW;
         for (int t = tid; t < H.n_ptracks; t += nt) {
             const int b0 = ptb[t], K = ptb[t + 1] - b0;
             double r, J[6 * kMaxFrames];
@@ -749,17 +756,30 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             const double s = r * r, tt = 1.0 + s / cb;
             const double sc = sqrt(1.0 / tt);
             atomicAdd(&cost_sm[3], 0.5 * cb * log(tt));
-            r *= sc;
-            for (int i = 0; i < 6 * K; ++i) J[i] *= sc;
-            for (int i = 0; i < 6 * K; ++i) {
-                const int gi = ptf[b0 + i / 6] * stride + (i % 6);
-                atomicAdd(&g[gi], J[i] * r);
-                atomicAdd(&gu[gi], J[i] * r);
-                for (int j = 0; j <= i; ++j) {
-                    const int gj = ptf[b0 + j / 6] * stride + (j % 6);
-                    atomicAdd(&A[gi >= gj ? tri(gi, gj) : tri(gj, gi)], J[i] * J[j]);
-                }
+            double *row = PJ + (size_t)t * PW;
+            for (int i = 0; i < 6 * N; ++i) row[i] = 0.0;
+            for (int i = 0; i < 6 * K; ++i) row[ptf[b0 + i / 6] * 6 + (i % 6)] = J[i] * sc;
+            row[6 * N] = r * sc;
+        }
+        __syncthreads();
+        const int P6 = 6 * N, T = H.n_ptracks;
+        for (int e = tid; e < P6 * (P6 + 1) / 2 + P6; e += nt) {
+            if (e >= P6 * (P6 + 1) / 2) {                            // gradient entries
+                const int i = e - P6 * (P6 + 1) / 2;
+                double sg = 0.0;
+                for (int t = 0; t < T; ++t) sg += __ldcg(PJ + (size_t)t * PW + i) * __ldcg(PJ + (size_t)t * PW + P6);
+                const int gi = (i / 6) * stride + (i % 6);
+                g[gi] += sg; gu[gi] += sg;
+                continue;
             }
+            int i = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+            while ((i + 1) * (i + 2) / 2 <= e) ++i;
+            while (i * (i + 1) / 2 > e) --i;
+            const int j = e - i * (i + 1) / 2;                       // j <= i
+            double sh = 0.0;
+            for (int t = 0; t < T; ++t) sh += __ldcg(PJ + (size_t)t * PW + i) * __ldcg(PJ + (size_t)t * PW + j);
+            const int gi = (i / 6) * stride + (i % 6), gj = (j / 6) * stride + (j % 6);
+            A[tri(gi, gj)] += sh;                                    // gi >= gj since i >= j
         }
         __syncthreads();
     }
