@@ -412,7 +412,7 @@ static size_t solve_smem_one(const WinHdr &H, bool lean) {
     size_t scr = lean ? Dp + 10 * 36 + 36 : std::max<size_t>(Dp, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);
     if (H.use_inertial) scr = std::max<size_t>(scr, 2 * (4 * 450 + 64));
     if (H.n_prior > 0) scr = std::max<size_t>(scr, 3 * 15 * (size_t)H.n_prior + 9 * (size_t)H.n_prior);
-    return sizeof(double) * ((nb + 1) * (nb + 2) / 2 * 16 + 4 * Dp + nb * 16 + (size_t)H.N * 36 + scr);
+    return sizeof(double) * ((nb + 1) * (nb + 2) / 2 * 18 + 4 * Dp + (size_t)H.N * 36 + scr);   // tiles of kTP = 18 doubles (ba_solve.cuh)
 }
 
 static BatchShape batch_shape(Handle *h, int w0, int n, bool by_capacity) {

@@ -64,9 +64,13 @@ struct SolveArgs {
 
 // The dense system is stored as packed lower-triangular 4x4 TILES (tile (I,J), J <= I, at
 // I(I+1)/2 + J, 16 doubles row-major) so that the factorisation works on register-sized blocks.
+// A tile occupies kTP = 18 doubles: the same element of consecutive tiles then lies 4 banks apart, so a warp whose
+// lanes work on consecutive tiles reads 16 bytes per lane without bank conflicts (at a pitch of 16 every lane hit the
+// same four banks: the factorisation was shared-memory-bandwidth bound, 5.7 K cycles per block column at D = 135).
+constexpr int kTP = 18;
+__device__ __forceinline__ int tile_off(int I, int J) { return (I * (I + 1) / 2 + J) * kTP; }
 __device__ __forceinline__ int tri(int i, int j) {   // element (i,j), j <= i
-    const int I = i >> 2, J = j >> 2;
-    return ((I * (I + 1) / 2 + J) << 4) + ((i & 3) << 2) + (j & 3);
+    return tile_off(i >> 2, j >> 2) + ((i & 3) << 2) + (j & 3);
 }
 
 // ---- IMU factor: raw residual and Jacobian (before whitening); J is [15][30] row-major.
@@ -317,66 +321,80 @@ __device__ inline void plane_factor(int K, const int32_t *fr, const float *z, co
 // nb block rows of 4 (padding rows carry an identity diagonal).  The right-hand side is block row
 // nb of the packed tile array (row 0 of its tiles), so the panel / trailing phases carry out the
 // forward substitution for free.  Per block column kb:
-//   (a) one thread factors the 4x4 diagonal tile and stores inv(L_kk);
-//   (b) one thread per panel tile (incl. the rhs row): A_Ik <- A_Ik L_kk^-T;
-//   (c) one thread per trailing tile: A_IJ -= A_Ik A_Jk^T   (64 independent FMAs).
-// 3 barriers per block column (15 block columns for D = 60) instead of 2-3 per scalar column.
-// The back substitution L^T x = y runs on warp 0 with warp-level barriers only.
-// A must hold (nb+1)(nb+2)/2 tiles; Linv: [nb][16] scratch.  Returns false (uniformly) if a pivot is
+//   (b) one thread per panel tile row (incl. the rhs row): A_Ik <- A_Ik L_kk^-T;
+//   (c) trailing tiles A_IJ -= A_Ik A_Jk^T: one thread per tile (kPerTile: wide CTAs, 64 FMAs from 48 loads) or per
+//       tile row (narrow CTAs of the batched visual kernel);
+//   (a) LOOK-AHEAD: the owner(s) of the next diagonal tile update it first and thread 0 factors it (4x4 Cholesky +
+//       inverse of the factor, a serial chain of ~500 cycles) WHILE the other threads finish the trailing update.
+// 2 barriers per block column.  The back substitution L^T x = y runs on warp 0 with warp-level barriers only.
+// A must hold (nb+1)(nb+2)/2 tiles of kTP doubles.  Returns false (uniformly) if a pivot is
 // not positive / finite (the system must be positive definite, as for ceres' Cholesky-based SPARSE_SCHUR).
-__device__ inline bool chol_solve_tiled(double *A, double *x, int nb, double *Linv, int *flag_sm) {
+// L_kk itself is not needed once its inverse is known (panel and back substitution multiply by inv(L_kk)): the inverse
+// overwrites the diagonal tile, no separate array
+__device__ __forceinline__ void chol_factor4(double *Akk, int *flag_sm) {
+    double L[16], Li[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { L[e] = Akk[e]; Li[e] = 0.0; }
+    bool good = true;
+    double idg[4];                       // reciprocals of the diagonal of L (no divisions below)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double d = L[c * 4 + c];
+#pragma unroll
+        for (int m = 0; m < c; ++m) d -= L[c * 4 + m] * L[c * 4 + m];
+        if (!(d > 0.0) || !isfinite(d)) { good = false; d = 1.0; }
+        const double id = rsqrt(d);
+        idg[c] = id;
+        L[c * 4 + c] = d * id;
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r) {
+            double v = L[r * 4 + c];
+#pragma unroll
+            for (int m = 0; m < c; ++m) v -= L[r * 4 + m] * L[c * 4 + m];
+            L[r * 4 + c] = v * id;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        Li[c * 4 + c] = idg[c];
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r) {
+            double v = 0.0;
+#pragma unroll
+            for (int m = c; m < r; ++m) v -= L[r * 4 + m] * Li[m * 4 + c];
+            Li[r * 4 + c] = v * idg[r];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) Akk[e] = Li[e];
+    if (!good) *flag_sm = 0;
+}
+
+// lower-triangle tile index e -> (ii, jj), jj <= ii
+__device__ __forceinline__ void tri_unrank(int e, int &ii, int &jj) {
+    ii = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+    while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+    while (ii * (ii + 1) / 2 > e) --ii;
+    jj = e - ii * (ii + 1) / 2;
+}
+
+template <bool kPerTile>
+__device__ inline bool chol_solve_tiled(double *A, double *x, int nb, int *flag_sm) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    double *R = A + ((nb * (nb + 1) / 2) << 4);          // rhs block row: tiles (nb, J), row 0 used
-    for (int i = tid; i < nb * 16; i += nt) R[i] = ((i & 15) < 4) ? x[(i >> 4) * 4 + (i & 3)] : 0.0;
+    double *R = A + tile_off(nb, 0);                       // rhs block row: tiles (nb, J), row 0 used
+    for (int i = tid; i < nb * kTP; i += nt) { const int J = i / kTP, o = i - J * kTP; R[i] = (o < 4) ? x[J * 4 + o] : 0.0; }
     if (tid == 0) *flag_sm = 1;
     __syncthreads();
+    if (tid == 0) chol_factor4(A + tile_off(0, 0), flag_sm);
+    __syncthreads();
     for (int kb = 0; kb < nb; ++kb) {
-        double *Akk = A + ((kb * (kb + 1) / 2 + kb) << 4);
-        if (tid == 0) {
-            double L[16], Li[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) { L[e] = Akk[e]; Li[e] = 0.0; }
-            bool good = true;
-            double idg[4];                       // reciprocals of the diagonal of L (no divisions below)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                double d = L[c * 4 + c];
-#pragma unroll
-                for (int m = 0; m < c; ++m) d -= L[c * 4 + m] * L[c * 4 + m];
-                if (!(d > 0.0) || !isfinite(d)) { good = false; d = 1.0; }
-                const double id = rsqrt(d);
-                idg[c] = id;
-                L[c * 4 + c] = d * id;
-#pragma unroll
-                for (int r = c + 1; r < 4; ++r) {
-                    double v = L[r * 4 + c];
-#pragma unroll
-                    for (int m = 0; m < c; ++m) v -= L[r * 4 + m] * L[c * 4 + m];
-                    L[r * 4 + c] = v * id;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                Li[c * 4 + c] = idg[c];
-#pragma unroll
-                for (int r = c + 1; r < 4; ++r) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int m = c; m < r; ++m) v -= L[r * 4 + m] * Li[m * 4 + c];
-                    Li[r * 4 + c] = v * idg[r];
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < 16; ++e) { Akk[e] = L[e]; Linv[kb * 16 + e] = Li[e]; }
-            if (!good) *flag_sm = 0;
-        }
-        __syncthreads();
         if (*flag_sm == 0) break;                      // uniform
         // (b) panel tiles incl. the rhs block row (I = nb): X <- X * Linv^T, one thread per tile ROW
         for (int e = tid; e < (nb - kb) * 4; e += nt) {
             const int I = kb + 1 + (e >> 2), r = e & 3;
-            double *X = A + ((I * (I + 1) / 2 + kb) << 4) + r * 4;
-            const double *Li = Linv + kb * 16;
+            if (I == nb && r != 0) continue;           // only row 0 of the rhs tiles carries data
+            double *X = A + tile_off(I, kb) + r * 4;
+            const double *Li = A + tile_off(kb, kb);
             const double x0 = X[0], x1 = X[1], x2 = X[2], x3 = X[3];
             X[0] = x0 * Li[0];
             X[1] = x0 * Li[4] + x1 * Li[5];
@@ -384,32 +402,56 @@ __device__ inline bool chol_solve_tiled(double *A, double *x, int nb, double *Li
             X[3] = x0 * Li[12] + x1 * Li[13] + x2 * Li[14] + x3 * Li[15];
         }
         __syncthreads();
-        // (c) trailing tiles (I,J), kb < J <= I, plus the rhs row (I = nb, kb < J < nb); one thread per tile ROW
+        // (c) trailing tiles (I,J), kb < J <= I < nb, plus the rhs row (I = nb, kb < J < nb); tile 0 is the next diagonal tile
         const int n = nb - kb - 1, ntile = n * (n + 1) / 2;
-        for (int e4 = tid; e4 < (ntile + n) * 4; e4 += nt) {
-            const int e = e4 >> 2, r = e4 & 3;
-            int I, J;
-            if (e < ntile) {
-                int ii = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-                while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
-                while (ii * (ii + 1) / 2 > e) --ii;
-                I = kb + 1 + ii; J = kb + 1 + (e - ii * (ii + 1) / 2);
-            } else { I = nb; J = kb + 1 + (e - ntile); }
-            const double *P = A + ((I * (I + 1) / 2 + kb) << 4) + r * 4, *Q = A + ((J * (J + 1) / 2 + kb) << 4);
-            double *C = A + ((I * (I + 1) / 2 + J) << 4) + r * 4;
-            const double p0 = P[0], p1 = P[1], p2 = P[2], p3 = P[3];
+        if (kPerTile) {
+            for (int e = tid; e < ntile + n; e += nt) {
+                int I, J;
+                if (e < ntile) { int ii, jj; tri_unrank(e, ii, jj); I = kb + 1 + ii; J = kb + 1 + jj; }
+                else { I = nb; J = kb + 1 + (e - ntile); }
+                const double *P = A + tile_off(I, kb), *Q = A + tile_off(J, kb);
+                double *C = A + tile_off(I, J);
+                double q[16];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) C[c] -= p0 * Q[c * 4] + p1 * Q[c * 4 + 1] + p2 * Q[c * 4 + 2] + p3 * Q[c * 4 + 3];
+                for (int k = 0; k < 16; ++k) q[k] = Q[k];
+                const int rows = (I == nb) ? 1 : 4;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (r >= rows) break;
+                    const double p0 = P[r * 4], p1 = P[r * 4 + 1], p2 = P[r * 4 + 2], p3 = P[r * 4 + 3];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) C[r * 4 + c] -= p0 * q[c * 4] + p1 * q[c * 4 + 1] + p2 * q[c * 4 + 2] + p3 * q[c * 4 + 3];
+                }
+                if (e == 0) chol_factor4(C, flag_sm);     // look-ahead: tile (kb+1, kb+1) is complete
+            }
+        } else {
+            for (int e4 = tid; e4 < (ntile + n) * 4; e4 += nt) {
+                const int e = e4 >> 2, r = e4 & 3;
+                int I, J;
+                if (e < ntile) { int ii, jj; tri_unrank(e, ii, jj); I = kb + 1 + ii; J = kb + 1 + jj; }
+                else { I = nb; J = kb + 1 + (e - ntile); }
+                if (!(I == nb && r != 0)) {
+                    const double *P = A + tile_off(I, kb) + r * 4, *Q = A + tile_off(J, kb);
+                    double *C = A + tile_off(I, J) + r * 4;
+                    const double p0 = P[0], p1 = P[1], p2 = P[2], p3 = P[3];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) C[c] -= p0 * Q[c * 4] + p1 * Q[c * 4 + 1] + p2 * Q[c * 4 + 2] + p3 * Q[c * 4 + 3];
+                }
+                if (e4 < 4 && n > 0) {                 // threads 0..3 hold the four rows of tile (kb+1, kb+1): look-ahead
+                    __syncwarp(0xFu);
+                    if (e4 == 0) chol_factor4(A + tile_off(kb + 1, kb + 1), flag_sm);
+                }
+            }
         }
         __syncthreads();
     }
     if (*flag_sm == 0) return false;
     // y = L^-1 b now sits in row 0 of the rhs tiles; back substitution x = L^-T y on warp 0
     if (tid < 32) {
-        for (int i = tid; i < nb * 4; i += 32) x[i] = R[(i >> 2) * 16 + (i & 3)];
+        for (int i = tid; i < nb * 4; i += 32) x[i] = R[(i >> 2) * kTP + (i & 3)];
         __syncwarp();
         for (int kb = nb - 1; kb >= 0; --kb) {
-            const double *Li = Linv + kb * 16;
+            const double *Li = A + tile_off(kb, kb);
             double o = 0.0;
             if (tid < 4) {
 #pragma unroll
@@ -420,7 +462,7 @@ __device__ inline bool chol_solve_tiled(double *A, double *x, int nb, double *Li
             __syncwarp();
             for (int e = tid; e < kb * 4; e += 32) {
                 const int J = e >> 2, c = e & 3;
-                const double *X = A + ((kb * (kb + 1) / 2 + J) << 4);      // tile (kb, J)
+                const double *X = A + tile_off(kb, J);      // tile (kb, J)
                 x[e] -= X[c] * x[kb * 4] + X[4 + c] * x[kb * 4 + 1] + X[8 + c] * x[kb * 4 + 2] + X[12 + c] * x[kb * 4 + 3];
             }
             __syncwarp();
@@ -459,14 +501,13 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nb = (D + 3) >> 2, Dp = nb * 4;               // block rows of 4; rows >= D are identity padding
-    const int nA = (nb + 1) * (nb + 2) / 2 * 16;            // + the rhs block row
+    const int nA = (nb + 1) * (nb + 2) / 2 * kTP;           // + the rhs block row
     double *A = reinterpret_cast<double *>(smem_raw);       // packed lower 4x4 tiles
     double *g = A + nA;                                     // [Dp] reduced gradient
     double *gu = g + Dp;                                    // [Dp] unreduced gradient (for |g|_inf)
     double *hcorr = gu + Dp;                                // [Dp] direct - reduced diagonal
     double *xs = hcorr + Dp;                                // [Dp] solution
-    double *Linv = xs + Dp;                                 // [nb][16] inverses of the diagonal tiles
-    double *T = Linv + nb * 16;                             // [N][36] change of variables
+    double *T = xs + Dp;                                    // [N][36] change of variables
     double *scr = T + N * 36;                               // scratch: staging / IMU slabs / prior vectors / reg copy
     __shared__ double cost_sm[4];
     __shared__ int flag_sm;
@@ -833,7 +874,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         xs[i] = -g[i];
     }
     __syncthreads();
-    const bool ok = chol_solve_tiled(A, xs, nb, Linv, &flag_sm);
+    const bool ok = chol_solve_tiled<kFull>(A, xs, nb, &flag_sm);
 
     // ---- outputs
     double *dxo = a.dx_pose + (size_t)w * a.Ncap * 15;
