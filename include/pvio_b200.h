@@ -165,6 +165,38 @@ int pvio_b200_ba_gn_step(pvio_b200_handle h, const pvio_b200_window *w, const pv
 int pvio_b200_ba_marginalize(pvio_b200_handle h, const pvio_b200_window *w, const pvio_b200_state *s,
                              int index, double *S_out, double *e_out, double *H_out, double *b_out);
 
+/* ---- resident sliding window ----------------------------------- */
+/* The window persists in the handle between keyframes instead of being rebuilt from Map / Frame / Track at every
+ * solve (bundle_adjustor.cpp:75-242): the shim reports what CHANGED.  The marginalisation prior stays ON THE DEVICE:
+ * pvio_b200_window_drop_victim leaves S, e and the linearisation point where the solve kernels read them.
+ * One resident window per handle.  Frame arguments are window indices (0 = oldest). */
+/* Start an empty window.  Of `constants` the scalar members are kept (extrinsics, sqrt_inv_cov, fx, fy, cauchy_a,
+ * use_inertial); its arrays are ignored. */
+int pvio_b200_window_reset(pvio_b200_handle h, const pvio_b200_window *constants);
+/* sliding_window_tracker.cpp:113-118.  state [PVIO_B200_FRAME_STRIDE]; imu_record [PVIO_B200_IMU_STRIDE]: the
+ * pre-integration factor (previous frame, this frame), NULL for the first frame / a visual-only window. */
+int pvio_b200_window_append_frame(pvio_b200_handle h, const double *state, int fixed, const double *imu_record);
+/* New tracks, each with its first observation z [n][2] in frame[i] and an initial inverse depth (the shim's
+ * triangulation, track.cpp:83-106).  ids_out [n] (may be NULL): handles for the calls below. */
+int pvio_b200_window_add_tracks(pvio_b200_handle h, int n, const int32_t *frame, const double *z,
+                                const double *inv_depth, int32_t *ids_out);
+/* Track::add_keypoint (track.cpp:32-37): observations arrive in increasing frame order per track. */
+int pvio_b200_window_add_observations(pvio_b200_handle h, int n, const int32_t *track, const int32_t *frame, const double *z);
+int pvio_b200_window_remove_track(pvio_b200_handle h, int32_t track);
+/* A prior given by the caller over frames 0 .. n_prior-1 (the 1e15 gauge prior of the first window,
+ * sliding_window_tracker.cpp:100-112); later priors come from pvio_b200_window_drop_victim. */
+int pvio_b200_window_set_prior(pvio_b200_handle h, int n_prior, const double *S, const double *e, const double *state0);
+/* BundleAdjustor::solve on the resident window (tracks with >= 2 observations take part); states and inverse
+ * depths are updated in the handle. */
+int pvio_b200_window_solve(pvio_b200_handle h, const pvio_b200_options *opt, pvio_b200_summary *summary);
+/* Map::marginalize_frame(0) (map.cpp:76-88): marginaliser -> new prior (device resident), the victim's observations
+ * leave their tracks, tracks anchored in it are re-anchored from the current estimate (track.cpp:42-49). */
+int pvio_b200_window_drop_victim(pvio_b200_handle h);
+/* Read back: frames [n_frames][PVIO_B200_FRAME_STRIDE]; per queried track its inverse depth, anchor frame (-1: gone)
+ * and observation count.  Any output pointer may be NULL. */
+int pvio_b200_window_get(pvio_b200_handle h, int32_t *n_frames, double *frames, int n_tracks, const int32_t *tracks,
+                         double *inv_depth, int32_t *anchor_frame, int32_t *n_observations);
+
 /* Mean pixel reprojection error over all observations of the window's landmarks. */
 int pvio_b200_reprojection_error(pvio_b200_handle h, const pvio_b200_window *w,
                                  const pvio_b200_state *s, double *error);

@@ -300,7 +300,11 @@ static int pack_window(Handle *h, int slot, const pvio_b200_window *w, const pvi
         if (n_imu > 0) memcpy(h->imu_data.h + (size_t)slot * h->Ncap * kImuStride, w->imu_data, sizeof(double) * n_imu * kImuStride);
         const size_t dcap = 15 * (size_t)h->Ncap, d = 15 * (size_t)n_prior;
         for (int n = 0; n < n_prior; ++n) h->prior_frames.h[(size_t)slot * h->Ncap + n] = w->prior_frames[n];
-        if (d > 0) {
+        if (d > 0 && !w->prior_S) {         // prior left on the device by marginalize_impl(keep_on_device): slot 0 only
+            if (slot != 0 || !h->prior_resident || h->prior_resident_n != n_prior)
+                return fail(h, PVIO_B200_EINVAL, "prior_S == NULL: no device-resident prior of that size");
+        } else if (d > 0) {
+            if (slot == 0) h->prior_resident = false;
             memcpy(h->prior_S.h + (size_t)slot * dcap * dcap, w->prior_S, sizeof(double) * d * d);   // dense d x d, row-major
             memcpy(h->prior_e.h + (size_t)slot * dcap, w->prior_e, sizeof(double) * d);
             memcpy(h->prior_x0.h + (size_t)slot * h->Ncap * kFrameStride, w->prior_state0, sizeof(double) * n_prior * kFrameStride);
@@ -345,9 +349,11 @@ static int upload_range(Handle *h, int w0, int n, cudaStream_t st) {
         TRY(h2d(h, h->imu_idx, N * 2, w0, n, st));
         TRY(h2d(h, h->imu_data, N * kImuStride, w0, n, st));
         TRY(h2d(h, h->prior_frames, N, w0, n, st));
-        TRY(h2d(h, h->prior_S, dcap * dcap, w0, n, st));
-        TRY(h2d(h, h->prior_e, dcap, w0, n, st));
-        TRY(h2d(h, h->prior_x0, N * kFrameStride, w0, n, st));
+        if (!(w0 == 0 && n == 1 && h->prior_resident)) {     // a device-resident prior (marginalize_impl) is never re-uploaded
+            TRY(h2d(h, h->prior_S, dcap * dcap, w0, n, st));
+            TRY(h2d(h, h->prior_e, dcap, w0, n, st));
+            TRY(h2d(h, h->prior_x0, N * kFrameStride, w0, n, st));
+        }
         for (int i = w0; i < w0 + n; ++i) any_prior |= h->hdr.h[i].n_prior > 0;
         if (any_prior) {
             prior_lambda_kernel<<<dim3(n, n < 64 ? 32 : 1), 256, 0, st>>>(h->hdr.d, h->prior_S.d, h->prior_L.d, h->Ncap, w0);
@@ -410,7 +416,7 @@ static size_t solve_smem_one(const WinHdr &H, bool lean) {
     const size_t nb = (D + 3) / 4, Dp = nb * 4;
     const size_t np_ = (size_t)H.N * (H.N + 1) / 2;
     size_t scr = lean ? Dp + 10 * 36 + 36 : std::max<size_t>(Dp, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);
-    if (H.use_inertial) scr = std::max<size_t>(scr, 2 * (4 * 450 + 64));
+    if (H.use_inertial) scr = std::max<size_t>(scr, 2 * (8 * 450 + 8 * 16));      // kImuRound factors: raw + whitened J, r
     if (H.n_prior > 0) scr = std::max<size_t>(scr, 3 * 15 * (size_t)H.n_prior + 9 * (size_t)H.n_prior);
     return sizeof(double) * ((nb + 1) * (nb + 2) / 2 * 18 + 4 * Dp + (size_t)H.N * 36 + scr);   // tiles of kTP = 18 doubles (ba_solve.cuh)
 }
@@ -888,6 +894,7 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     if (h->pnp_host) cudaFreeHost(h->pnp_host);
     klt_free(h);
     marg_free(h);
+    resident_free(h);
     release(h->hdr); release(h->cst); release(h->obs); release(h->lms); release(h->rho); release(h->frames);
     release(h->fobs); release(h->seg); release(h->jr); release(h->lm_w); release(h->lm_msk); release(h->frames_out); release(h->rho_out); release(h->lm_v); release(h->valid); release(h->quality);
     release(h->ctrl); release(h->rho_cand); release(h->frames_cand); release(h->lm_scale); release(h->lm_aux); release(h->hs);
@@ -1294,7 +1301,7 @@ int pvio_b200_ba_marginalize(pvio_b200_handle hh, const pvio_b200_window *w, con
                              double *S_out, double *e_out, double *H_out, double *b_out) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (!h || !w || !s) return PVIO_B200_EINVAL;
-    return marginalize_impl(h, w, s, index, S_out, e_out, H_out, b_out);
+    return marginalize_impl(h, w, s, index, false, S_out, e_out, H_out, b_out);
 }
 
 int pvio_b200_pnp_solve(pvio_b200_handle hh, const pvio_b200_pnp_problem *problem, double *frame,

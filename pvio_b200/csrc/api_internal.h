@@ -33,6 +33,9 @@ struct Handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     int64_t launches = 0;
+    bool prior_resident = false;                  // slot 0's prior (S, e, x0) was written on the device by the marginaliser
+    int prior_resident_n = 0;                     // its frame count
+    struct ResidentWindow *resident = nullptr;    // resident.cu
     size_t sys_set = 0;                           // elements between the two buffer sets of the reduced-system arrays (LinBufs)
     int sm_count = 148;
 
@@ -113,7 +116,8 @@ void klt_free(Handle *h);
 int pnp_solve_impl(Handle *h, const pvio_b200_pnp_problem *pb, double *frame, const pvio_b200_options *opt,
                    pvio_b200_summary *summary);
 // ba_marg.cu
-int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s, int index,
+void resident_free(Handle *h);     // resident.cu
+int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s, int index, bool keep_on_device,
                      double *S_out, double *e_out, double *H_out, double *b_out);
 void marg_free(Handle *h);
 // selftest.cu

@@ -401,13 +401,17 @@ void marg_free(Handle *h) {
     }
 }
 
-int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s, int index,
+// keep_on_device (index 0 only): the new prior -- S, e and its linearisation point, the CURRENT states of the frames that
+// stay -- is written straight into slot 0's prior arrays on the device; the next solve of the shifted window names it
+// with prior_S == NULL (pack_window) and nothing of it crosses PCIe.
+int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s, int index, bool keep_on_device,
                      double *S_out, double *e_out, double *H_out, double *b_out) {
     const int N = w->n_frames;
     if (index < 0 || index >= N || N < 2) return fail(h, PVIO_B200_EINVAL, "marginalize: bad frame index");
     if (!w->use_inertial) return fail(h, PVIO_B200_EINVAL, "marginalize: the window must carry motion states");
     const int n = 15 * N, dk = n - 15;
-    if ((S_out || e_out) && sizeof(double) * ((size_t)dk * (dk | 1) + 4 * (size_t)dk) > 224 * 1024)
+    if (keep_on_device && index != 0) return fail(h, PVIO_B200_EINVAL, "marginalize: the resident prior is defined for index 0");
+    if ((S_out || e_out || keep_on_device) && sizeof(double) * ((size_t)dk * (dk | 1) + 4 * (size_t)dk) > 224 * 1024)
         return fail(h, PVIO_B200_EINVAL, "marginalize: window too large for the shared-memory eigen-solver (15 (N - 1) <= 165)");
     int rc = pack_and_upload(h, w, s);
     if (rc != 0) return rc;
@@ -436,7 +440,7 @@ int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state
     h->launches += 2;
     if (H_out) CK(h, cudaMemcpyAsync(H_out, dHk, sizeof(double) * dk * dk, cudaMemcpyDeviceToHost, h->stream));
     if (b_out) CK(h, cudaMemcpyAsync(b_out, dbk, sizeof(double) * dk, cudaMemcpyDeviceToHost, h->stream));
-    if (S_out || e_out) {
+    if (S_out || e_out || keep_on_device) {
         const size_t esm = sizeof(double) * ((size_t)dk * (dk | 1) + 4 * (size_t)dk);
         static bool attr_set = false;
         if (!attr_set) { CK(h, cudaFuncSetAttribute(marg_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); attr_set = true; }
@@ -444,9 +448,15 @@ int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state
         ++h->launches;
         if (S_out) CK(h, cudaMemcpyAsync(S_out, dS, sizeof(double) * dk * dk, cudaMemcpyDeviceToHost, h->stream));
         if (e_out) CK(h, cudaMemcpyAsync(e_out, de, sizeof(double) * dk, cudaMemcpyDeviceToHost, h->stream));
+        if (keep_on_device) {       // slot 0: dense dk x dk S, e, x0 = states of frames 1 .. N - 1 (read by the kernels above: stream order)
+            CK(h, cudaMemcpyAsync(h->prior_S.d, dS, sizeof(double) * dk * dk, cudaMemcpyDeviceToDevice, h->stream));
+            CK(h, cudaMemcpyAsync(h->prior_e.d, de, sizeof(double) * dk, cudaMemcpyDeviceToDevice, h->stream));
+            CK(h, cudaMemcpyAsync(h->prior_x0.d, h->frames.d + kFrameStride, sizeof(double) * (N - 1) * kFrameStride, cudaMemcpyDeviceToDevice, h->stream));
+        }
     }
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaGetLastError());
+    if (keep_on_device) { h->prior_resident = true; h->prior_resident_n = N - 1; }
     return 0;
 }
 

@@ -473,6 +473,7 @@ __device__ inline bool chol_solve_tiled(double *A, double *x, int nb, int *flag_
 }
 
 constexpr int kSolveImuSlab = 15 * 30 + 16;     // raw J + r per factor
+constexpr int kImuRound = 8;                    // IMU factors linearised concurrently by solve_kernel
 
 template <bool kFull>
 static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
@@ -675,12 +676,12 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     if (kFull && inertial && H.n_imu > 0) {
         const int32_t *idx = a.imu_idx + (size_t)w * a.Ncap * 2;
         const double *recs = a.imu_data + (size_t)w * a.Ncap * kImuStride;
-        for (int n0 = 0; n0 < H.n_imu; n0 += 4) {           // 4 factors per round (scratch = 4 slabs of raw + whitened J)
-            const int nb = min(4, H.n_imu - n0);
-            double *Jraw = scr;                              // [4][450], r at [4*450 + n*16]
-            double *rraw = scr + 4 * 450;
-            double *Jw = rraw + 4 * 16;                      // [4][450]
-            double *rw = Jw + 4 * 450;                       // [4][16]
+        for (int n0 = 0; n0 < H.n_imu; n0 += kImuRound) {  // up to kImuRound factors per round (scratch: raw + whitened J of each)
+            const int nb = min(kImuRound, H.n_imu - n0);
+            double *Jraw = scr;                              // [R][450], r at [R*450 + n*16]
+            double *rraw = scr + kImuRound * 450;
+            double *Jw = rraw + kImuRound * 16;              // [R][450]
+            double *rw = Jw + kImuRound * 450;               // [R][16]
             if (tid < nb) {
                 const int n = n0 + tid;
                 imu_factor_raw(frames + idx[2 * n] * kFrameStride, frames + idx[2 * n + 1] * kFrameStride,
@@ -696,10 +697,23 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
                 else { for (int k = 0; k < 15; ++k) s += Wm[k] * rraw[n * 16 + k]; rw[n * 16 + row] = s; }
             }
             __syncthreads();
-            for (int n = 0; n < nb; ++n) {                   // factors share frames: accumulate one at a time
-                const int fi = idx[2 * (n0 + n)], fj = idx[2 * (n0 + n) + 1];
-                for (int e = tid; e < 30 * 31; e += nt) {
-                    const int ra = e / 31, cb_ = e - ra * 31;
+            // accumulate.  Two factors touch the same entries of the system only if they share a frame; the reference's
+            // factors form a chain (frame n, n + 1), so the factors at even positions of the round go first, all at once,
+            // then the odd ones.  A round whose factors are not such a chain falls back to one factor at a time.
+            bool chain = true;                               // no two factors of equal parity share a frame
+            for (int n = 0; n < nb && chain; ++n)
+                for (int m = n + 2; m < nb; m += 2) {
+                    const int a0 = idx[2 * (n0 + n)], a1 = idx[2 * (n0 + n) + 1], b0 = idx[2 * (n0 + m)], b1 = idx[2 * (n0 + m) + 1];
+                    chain &= (a0 != b0 && a0 != b1 && a1 != b0 && a1 != b1);
+                }
+            const int phases = chain ? 2 : nb;
+            for (int ph = 0; ph < phases; ++ph) {
+                const int first = ph, step = chain ? 2 : nb, cnt = chain ? (nb - ph + 1) / 2 : 1;
+                for (int e = tid; e < cnt * 30 * 31; e += nt) {
+                    const int q = e / (30 * 31), rem = e - q * 30 * 31;
+                    const int n = first + q * step;
+                    const int fi = idx[2 * (n0 + n)], fj = idx[2 * (n0 + n) + 1];
+                    const int ra = rem / 31, cb_ = rem - ra * 31;
                     const int ga = (ra < 15 ? fi * 15 + ra : fj * 15 + ra - 15);
                     double s = 0.0;
                     if (cb_ < 30) {
@@ -712,9 +726,14 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
                         g[ga] += s; gu[ga] += s;
                     }
                 }
-                if (tid == 0) { double c = 0.0; for (int k = 0; k < 15; ++k) c += rw[n * 16 + k] * rw[n * 16 + k]; cost_sm[1] += 0.5 * c; }
                 __syncthreads();
             }
+            if (tid == 0) {
+                double c = 0.0;
+                for (int n = 0; n < nb; ++n) for (int k = 0; k < 15; ++k) c += rw[n * 16 + k] * rw[n * 16 + k];
+                cost_sm[1] += 0.5 * c;
+            }
+            __syncthreads();
         }
     }
 
@@ -732,10 +751,12 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         double *Ji = vv + d;              // [n][9] Jr^-1
         if (tid < n) prior_frame_raw(frames + pf[tid] * kFrameStride, x0 + tid * kFrameStride, r0 + 15 * tid, Ji + 9 * tid);
         __syncthreads();
-        for (int i = tid; i < d; i += nt) {
-            double s = ev[i];
-            for (int k = 0; k < d; ++k) s += S[(size_t)i * d + k] * r0[k];
-            rr[i] = s;                                         // marginalization_error_cost.h:91
+        for (int i = tid >> 5; i < d; i += nt >> 5) {          // warp per row: coalesced reads of S
+            double s = 0.0;
+            for (int k = tid & 31; k < d; k += 32) s += S[(size_t)i * d + k] * r0[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if ((tid & 31) == 0) rr[i] = ev[i] + s;            // marginalization_error_cost.h:91
         }
         __syncthreads();
         for (int i = tid; i < d; i += nt) {
