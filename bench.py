@@ -370,6 +370,36 @@ def run_gpu(args):
         except Exception as e:          # an extra never takes the headline line down
             extras[name] = {"error": str(e)}
 
+    # ---- a keyframe cycle (solve, marginalise the oldest frame, shift) with the window RESIDENT in
+    # the handle (prior left on the device) against re-packing the whole window and carrying S / e through the host
+    try:
+        from synthetic.sequence import Run, Chain, ResidentPlayer
+        run = Run(F=30, N=9, M=420, seed=701)
+        br = BundleAdjustor(device=local_rank, max_windows=1, max_frames=10, max_landmarks=512, max_obs=4096)
+        bp = BundleAdjustor(device=local_rank, max_windows=1, max_frames=10, max_landmarks=512, max_obs=4096)
+        player, chain, t_repack, nkf = ResidentPlayer(br, run), Chain(run), 0.0, 16
+        for k in range(nkf + 2):
+            wk, sk, lmk = chain.window(k)
+            t0 = time.perf_counter()
+            outk, _ = bp.solve(wk, sk, max_iterations=10, postpass=False)
+            Sk, ek = bp.marginalize_frame(wk, outk, index=0)
+            if k >= 2:
+                t_repack += time.perf_counter() - t0
+            chain.store(k, outk, lmk); chain.set_prior(k, Sk, ek, outk)
+            if k == 2:
+                player.seconds = 0.0
+            player.solve(10)
+            player.shift(k)
+        extras["keyframe_cycle"] = {"frames": int(run.N), "landmarks_in_window": int(wk.M), "keyframes": nkf,
+                                    "resident_ms_per_keyframe": player.seconds / nkf * 1e3,
+                                    "repack_ms_per_keyframe": t_repack / nkf * 1e3,
+                                    "note": "wall time inside the C-ABI calls: resident = window_solve + window_drop_victim + "
+                                            "append_frame (prior stays on the device); repack = ba_solve + ba_marginalize with "
+                                            "the whole window and the prior (S, e) through host buffers"}
+        br.close(); bp.close()
+    except Exception as e:
+        extras["keyframe_cycle"] = {"error": str(e)}
+
     # ---- literal BASELINE config 5: 8 independent cfg3 windows (seeds 648..655), window i -> GPU i mod G, full solves
     cfg5 = run_cfg5(local_rank, rank, world, use_dist, allmax)
 

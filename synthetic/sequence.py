@@ -122,3 +122,55 @@ class Chain:
         N = self.run.N
         x0 = np.concatenate([st.q[1:], st.p[1:], st.v[1:], st.bg[1:], st.ba[1:]], axis=1)
         self.prior = dict(frames=list(range(k + 1, k + N)), S=S, e=e, x0=x0)
+
+
+class ResidentPlayer:
+    """Feeds a run into the RESIDENT window of a handle (pvio_b200.resident.ResidentWindow): what the shim does with the
+    resident API -- per keyframe: solve, drop the victim, append the next frame with its observations."""
+
+    def __init__(self, ba, run):
+        from pvio_b200 import _lib
+        from pvio_b200.resident import ResidentWindow
+        self.run, self.rw, self.ids = run, ResidentWindow(ba, run.w), {}
+        g = run.guess
+        self.rec = _lib.PackedArgs(run.w, g).keep["imu"].reshape(-1, 288)     # factor f couples absolute frames (f, f + 1)
+        for f in range(run.N):
+            self.rw.append_frame(self.state16(f), False, self.rec[f - 1] if f > 0 else None)
+            self.feed(f, f)
+        w0, _, _ = Chain(run).window(0)                                       # first window: the 1e15 gauge prior
+        x0 = np.concatenate([w0.prior_q0, w0.prior_p0, w0.prior_v0, w0.prior_bg0, w0.prior_ba0], axis=1)
+        self.rw.set_prior(w0.prior_S, w0.prior_e, x0)
+        self.seconds = 0.0                                                    # wall time spent inside the C-ABI calls
+
+    def state16(self, f):
+        g = self.run.guess
+        return np.concatenate([g.q[f], g.p[f], g.v[f], g.bg[f], g.ba[f]])
+
+    def feed(self, f_abs, f_win):
+        new, seen = [], []
+        for l, (fr, zs) in enumerate(self.run.tracks):
+            if f_abs in fr:
+                (seen if l in self.ids else new).append((l, zs[fr.index(f_abs)]))
+        if seen:
+            self.rw.add_observations([self.ids[l] for l, _ in seen], [f_win] * len(seen), [z for _, z in seen])
+        if new:
+            got = self.rw.add_tracks([f_win] * len(new), [z for _, z in new], [self.run.guess.rho[l] for l, _ in new])
+            for (l, _), i in zip(new, got):
+                self.ids[l] = int(i)
+
+    def solve(self, max_iterations):
+        import time
+        t = time.perf_counter()
+        s = self.rw.solve(max_iterations=max_iterations)
+        self.seconds += time.perf_counter() - t
+        return s
+
+    def shift(self, k):
+        """drop frame k (the oldest), append absolute frame k + N"""
+        import time
+        f_abs = k + self.run.N
+        t = time.perf_counter()
+        self.rw.drop_victim()
+        self.rw.append_frame(self.state16(f_abs), False, self.rec[f_abs - 1])
+        self.seconds += time.perf_counter() - t
+        self.feed(f_abs, self.run.N - 1)

@@ -534,52 +534,24 @@ def test_resident_window_follows_the_repacked_sequence(ba):
     """the window kept in the handle across keyframes (append frame / new observations / drop victim,
     prior left on the device by the marginaliser) against the path that re-packs the whole window and carries the prior
     through the host at every keyframe (test_sequence_of_20_keyframes... pins THAT path to the oracle)."""
-    from synthetic.sequence import Run, Chain
-    from pvio_b200 import _lib
-    from pvio_b200.resident import ResidentWindow
+    from synthetic.sequence import Run, Chain, ResidentPlayer
     run = Run(F=26, N=6, M=260, seed=700)
-    N, g = run.N, run.guess
-    rec = _lib.PackedArgs(run.w, g).keep["imu"].reshape(-1, 288)            # factor f couples absolute frames (f, f + 1)
-    state16 = lambda f: np.concatenate([g.q[f], g.p[f], g.v[f], g.bg[f], g.ba[f]])
     chain = Chain(run)
     res = BundleAdjustor(max_windows=1, max_frames=8, max_landmarks=320, max_obs=2000)   # its own handle: the resident prior
-    rw = ResidentWindow(res, run.w)                                                      # lives in slot 0's device arrays
-    ids = {}                                                                 # run track -> resident track id
-
-    def feed_frame(f_abs, f_win):
-        new, seen = [], []
-        for l, (fr, zs) in enumerate(run.tracks):
-            if f_abs in fr:
-                (seen if l in ids else new).append((l, zs[fr.index(f_abs)]))
-        if seen:
-            rw.add_observations([ids[l] for l, _ in seen], [f_win] * len(seen), [z for _, z in seen])
-        if new:
-            got = rw.add_tracks([f_win] * len(new), [z for _, z in new], [g.rho[l] for l, _ in new])
-            for (l, _), i in zip(new, got):
-                ids[l] = int(i)
-
-    for f in range(N):
-        rw.append_frame(state16(f), False, rec[f - 1] if f > 0 else None)
-        feed_frame(f, f)
-    w0, s0, _ = chain.window(0)
-    x0 = np.concatenate([w0.prior_q0, w0.prior_p0, w0.prior_v0, w0.prior_bg0, w0.prior_ba0], axis=1)
-    rw.set_prior(w0.prior_S, w0.prior_e, x0)
+    player = ResidentPlayer(res, run)                                                    # lives in slot 0's device arrays
     worst = 0.0
     for k in range(20):
         w, st, lm = chain.window(k)
         out, summ = ba.solve(w, st, max_iterations=6, postpass=False)
         S, e = ba.marginalize_frame(w, out, index=0)
         chain.store(k, out, lm); chain.set_prior(k, S, e, out)
-        rs = rw.solve(max_iterations=6)
-        fr, rho, anchors, cnt = rw.get([ids[l] for l in lm])
+        rs = player.solve(6)
+        fr, rho, anchors, cnt = player.rw.get([player.ids[l] for l in lm])
         ref = np.concatenate([out.q, out.p, out.v, out.bg, out.ba], axis=1)
         assert rs['iterations'] == summ['iterations'] and rs['accepted_steps'] == summ['accepted_steps'], k
         worst = max(worst, np.abs(fr - ref).max(), np.max(np.abs(rho - out.rho) / np.abs(out.rho)))
         assert np.array_equal(anchors, w.lm_anchor), k
-        rw.drop_victim()
-        f_abs = k + N
-        rw.append_frame(state16(f_abs), False, rec[f_abs - 1])
-        feed_frame(f_abs, N - 1)
+        player.shift(k)
     res.close()
     print("resident window vs re-packed sequence: worst state / inverse-depth difference", worst)
     assert worst < 1e-7       # measured 3e-9 after 20 keyframes: the landmarks enter the two packings in different orders
