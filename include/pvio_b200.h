@@ -281,6 +281,19 @@ int pvio_b200_klt_track_cached(pvio_b200_handle h, uint64_t prev_id, const uint8
                                float *err, int n_points, int max_level, int max_iter, double eps, double clahe_clip,
                                int tiles_x, int tiles_y, int border);
 
+/* OpenCvImage::detect_keypoints (pvio-extra/src/pvio/extra/opencv_image.cpp:54-86): GFTT with the Harris response
+ * (GFTTDetector::create(1000, 1e-3, 20, 3, true), :183) on the preprocessed frame, PVIO's Poisson-disk filter
+ * (utility/poisson_disk_filter.h) against the `existing` keypoints [n_existing][2] with radius keypoint_distance, 20-pixel
+ * border.  The frame is taken from the pyramid cache of pvio_b200_klt_track_cached when frame_id is cached there
+ * (image may then be NULL); otherwise `image` is uploaded (clahe_clip > 0: raw frame, equalised on the device first).
+ * keypoints_out [max_out][2] pixel coordinates in the reference's order (decreasing response), *n_out their number.
+ * gftt_out [1000][2] / n_gftt (may be NULL): the corners before the Poisson filter, for parity checks against
+ * cv::goodFeaturesToTrack. */
+int pvio_b200_detect_keypoints(pvio_b200_handle h, uint64_t frame_id, const uint8_t *image, int width, int height, int stride,
+                               double clahe_clip, int tiles_x, int tiles_y, const double *existing, int n_existing,
+                               double keypoint_distance, int max_out, double *keypoints_out, int *n_out,
+                               float *gftt_out, int *n_gftt);
+
 /* CLAHE of one frame (same kernels); dst is [height][width]. */
 int pvio_b200_clahe(pvio_b200_handle h, const uint8_t *src, int width, int height, int stride, double clip_limit,
                     int tiles_x, int tiles_y, uint8_t *dst);

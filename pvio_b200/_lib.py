@@ -74,7 +74,7 @@ EXPORTS = [
     "pvio_b200_batch_download_state", "pvio_b200_batch_solve_host", "pvio_b200_selftest_lie", "pvio_b200_klt_track_cached",
     "pvio_b200_window_reset", "pvio_b200_window_append_frame", "pvio_b200_window_add_tracks",
     "pvio_b200_window_add_observations", "pvio_b200_window_remove_track", "pvio_b200_window_set_prior",
-    "pvio_b200_window_solve", "pvio_b200_window_drop_victim", "pvio_b200_window_get",
+    "pvio_b200_window_solve", "pvio_b200_window_drop_victim", "pvio_b200_window_get", "pvio_b200_detect_keypoints",
 ]
 
 _lib = None

@@ -36,6 +36,7 @@ struct Handle {
     bool prior_resident = false;                  // slot 0's prior (S, e, x0) was written on the device by the marginaliser
     int prior_resident_n = 0;                     // its frame count
     struct ResidentWindow *resident = nullptr;    // resident.cu
+    struct DetectState *detect = nullptr;         // detect.cu
     size_t sys_set = 0;                           // elements between the two buffer sets of the reduced-system arrays (LinBufs)
     int sm_count = 148;
 
@@ -117,6 +118,10 @@ int pnp_solve_impl(Handle *h, const pvio_b200_pnp_problem *pb, double *frame, co
                    pvio_b200_summary *summary);
 // ba_marg.cu
 void resident_free(Handle *h);     // resident.cu
+// klt.cu / detect.cu
+const uint8_t *klt_cached_level0(Handle *h, uint64_t frame_id, int width, int height, double clahe_clip);
+int klt_clahe_device(Handle *h, const uint8_t *d_src, uint8_t *d_dst, uint8_t *d_lut, int width, int height, double clip, int tiles_x, int tiles_y);
+void detect_free(Handle *h);
 int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s, int index, bool keep_on_device,
                      double *S_out, double *e_out, double *H_out, double *b_out);
 void marg_free(Handle *h);

@@ -454,6 +454,20 @@ int klt_track_impl(Handle *h, const uint8_t *prev, const uint8_t *next, int widt
     return 0;
 }
 
+// Level 0 (the equalised image) of a frame in the pyramid cache, or nullptr: the detector reads the frame the tracker
+// has just uploaded (frame.cpp:108-130 detects on the image it tracked into)
+const uint8_t *klt_cached_level0(Handle *h, uint64_t frame_id, int width, int height, double clahe_clip) {
+    KltState *k = h->klt;
+    if (!k || !frame_id || k->w != width || k->h != height) return nullptr;
+    for (int i = 0; i < 2; ++i) if (k->pyr_id[i] == frame_id && k->pyr_clahe[i] == clahe_clip) return k->pyr[i];
+    return nullptr;
+}
+// CLAHE of a device image into a device image (the detector's own upload path)
+int klt_clahe_device(Handle *h, const uint8_t *d_src, uint8_t *d_dst, uint8_t *d_lut, int width, int height, double clip, int tiles_x, int tiles_y) {
+    clahe_device(h, d_src, d_dst, d_lut, width, height, clip, tiles_x, tiles_y);
+    return 0;
+}
+
 // stand-alone CLAHE of one host image (dst row stride = width)
 int clahe_impl(Handle *h, const uint8_t *src, int width, int height, int stride, double clip, int tiles_x, int tiles_y, uint8_t *dst) {
     if (width < 1 || height < 1 || stride < width || clip <= 0.0 || tiles_x < 1 || tiles_y < 1 || width % tiles_x || height % tiles_y)
