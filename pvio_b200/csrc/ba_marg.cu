@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) marg_eig_kernel(const double *Ain, const 
             __syncthreads();
             const int tri = (l + 1) * (l + 2) / 2;          // rank-2 update of the lower triangle
             for (int idx = tid; idx < tri; idx += nt) {
-                int j = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+                int j = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
                 while ((j + 1) * (j + 2) / 2 <= idx) ++j;
                 while (j * (j + 1) / 2 > idx) --j;
                 const int k = idx - j * (j + 1) / 2;
@@ -338,17 +338,27 @@ __global__ void __launch_bounds__(256) marg_eig_kernel(const double *Ain, const 
                 for (; m < n - 1; ++m) { const double dd = fabs(d[m]) + fabs(d[m + 1]); if (fabs(e[m]) <= 2.3e-16 * dd) break; }
                 ctl[0] = m; ctl[1] = 0; ctl[2] = -1;
                 if (m != l) {
-                    double g = (d[l + 1] - d[l]) / (2.0 * e[l]), r = hypot(g, 1.0);
+                    // (sqrt(f^2 + g^2) instead of hypot, one reciprocal instead of two divisions: this scalar chain is the
+                    // critical path of the kernel -- ~60 dependent rotations per sweep, ~200 sweeps; the magnitudes here
+                    // (<= 1e15 from the gauge prior) are far from the range where hypot's rescaling matters)
+                    double g = (d[l + 1] - d[l]) / (2.0 * e[l]), r = sqrt(g * g + 1.0);
                     g = d[m] - d[l] + e[l] / (g + (g >= 0 ? fabs(r) : -fabs(r)));
                     double s = 1.0, c = 1.0, p = 0.0;
                     int i = m - 1;
                     bool broke = false;
+                    // e[i] and d[i] of the NEXT rotation are loaded ahead (they are untouched originals: off the dependent
+                    // chain s, c, g, p), and d[i + 1] is the d[i] of the rotation before
+                    double e_i = e[i], d_i = d[i], d_i1 = d[m];
                     for (; i >= l; --i) {
-                        const double f = s * e[i], b = c * e[i];
-                        e[i + 1] = r = hypot(f, g);
-                        if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; broke = true; break; }
-                        s = f / r; c = g / r; g = d[i + 1] - p; r = (d[i] - g) * s + 2.0 * c * b; p = s * r; d[i + 1] = g + p; g = c * r - b;
+                        const double e_nx = i > l ? e[i - 1] : 0.0, d_nx = i > l ? d[i - 1] : 0.0;
+                        const double f = s * e_i, b = c * e_i;
+                        const double q2 = f * f + g * g;
+                        if (q2 == 0.0) { e[i + 1] = 0.0; d[i + 1] -= p; e[m] = 0.0; broke = true; break; }
+                        const double ir = rsqrt(q2);            // one reciprocal square root gives both r and 1 / r
+                        e[i + 1] = r = q2 * ir;
+                        s = f * ir; c = g * ir; g = d_i1 - p; r = (d_i - g) * s + 2.0 * c * b; p = s * r; d[i + 1] = g + p; g = c * r - b;
                         rc[i] = c; rs[i] = s;
+                        d_i1 = d_i; e_i = e_nx; d_i = d_nx;
                     }
                     ctl[1] = m - 1; ctl[2] = broke ? i + 1 : l;      // rotations i = m-1 .. ctl[2], in this order
                     if (!broke) { d[l] -= p; e[l] = g; e[m] = 0.0; }
