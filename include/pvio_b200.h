@@ -294,6 +294,28 @@ int pvio_b200_detect_keypoints(pvio_b200_handle h, uint64_t frame_id, const uint
                                double keypoint_distance, int max_out, double *keypoints_out, int *n_out,
                                float *gftt_out, int *n_gftt);
 
+/* The F-matrix outlier rejection of OpenCvImage::track_keypoints (pvio-extra/src/pvio/extra/opencv_image.cpp:121-129):
+ * cv::findFundamentalMat(p, q, cv::FM_RANSAC, threshold, confidence, mask) with OpenCV's semantics -- n >= 15: RANSAC on
+ * 7-point models, at most max_iters (OpenCV: 1000) iterations with the adaptive iteration count; 8 <= n < 15: OpenCV's
+ * LMedS branch; n == 7: mask all ones; n < 7: mask zero.  p, q: [n][2] pixel coordinates (the cv::Point2f values).
+ * schedule == NULL: the samples are the ones OpenCV itself draws (cv::RNG((uint64)-1) and getSubset restated), so the
+ * mask is cv2's; otherwise int32 [n_schedule][7] injected sample indices (a row starting with -1 ends the run).
+ * Every iteration of the schedule is evaluated on the device at once; the host replays OpenCV's acceptance rule over
+ * the inlier counts (see csrc/fmat.cu).  mask: [n] 0/1.  F (may be NULL): the winning model, row-major 3x3.
+ * info (may be NULL): int32[4] = iterations the serial loop runs, winning iteration, winning model, method (1 RANSAC,
+ * 2 LMedS, 3 seven points). */
+int pvio_b200_find_fundamental_mask(pvio_b200_handle h, int n, const float *p, const float *q, double threshold, double confidence,
+                                    int max_iters, const int32_t *schedule, int n_schedule, uint8_t *mask, double *F, int32_t *info);
+
+/* OpenCvImage::track_keypoints as a whole (opencv_image.cpp:88-136): pvio_b200_klt_track_cached (LK on the cached pyramids,
+ * 20-pixel border on the device) followed by the F-matrix rejection above over the surviving matches when there are at
+ * least 8 (:121).  next_pts holds the initial guess on entry (:91-96: the caller's next_keypoints, or a copy of prev_pts);
+ * on return status[i] != 0 marks the matches the reference keeps and next_pts[i] their positions. */
+int pvio_b200_track_keypoints(pvio_b200_handle h, uint64_t prev_id, const uint8_t *prev, uint64_t next_id, const uint8_t *next,
+                              int width, int height, int stride, const float *prev_pts, float *next_pts, uint8_t *status,
+                              int n_points, int max_level, int max_iter, double eps, double clahe_clip, int tiles_x, int tiles_y,
+                              int border, double ransac_threshold, double ransac_confidence);
+
 /* CLAHE of one frame (same kernels); dst is [height][width]. */
 int pvio_b200_clahe(pvio_b200_handle h, const uint8_t *src, int width, int height, int stride, double clip_limit,
                     int tiles_x, int tiles_y, uint8_t *dst);

@@ -37,7 +37,7 @@ def build(force=False, verbose=False, defines=(), out=None):
 
     def cc(job):
         src, obj = job
-        extra = ["-fmad=false"] if src.endswith(("klt.cu", "detect.cu")) else []   # OpenCV's float rounding: no contraction
+        extra = ["-fmad=false"] if src.endswith(("klt.cu", "detect.cu", "fmat.cu")) else []   # OpenCV's float rounding: no contraction
         r = subprocess.run([NVCC] + FLAGS + extra + ["-c", src, "-o", obj], capture_output=True, text=True)
         return src, r
 
@@ -65,7 +65,7 @@ def _build_variant(defines, out):
     objs = []
     for s in sorted(f for f in os.listdir(CSRC) if f.endswith(".cu")):
         obj = os.path.join(odir, s[:-3] + ".o")
-        extra = ["-fmad=false"] if s in ("klt.cu", "detect.cu") else []
+        extra = ["-fmad=false"] if s in ("klt.cu", "detect.cu", "fmat.cu") else []
         ref = os.path.join(CSRC, s[:-3] + ".o")
         if s != "api.cu" and os.path.exists(ref):      # only api.cu depends on the tuning defines
             objs.append(ref)

@@ -896,6 +896,7 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     marg_free(h);
     resident_free(h);
     detect_free(h);
+    fm_free(h);
     release(h->hdr); release(h->cst); release(h->obs); release(h->lms); release(h->rho); release(h->frames);
     release(h->fobs); release(h->seg); release(h->jr); release(h->lm_w); release(h->lm_msk); release(h->frames_out); release(h->rho_out); release(h->lm_v); release(h->valid); release(h->quality);
     release(h->ctrl); release(h->rho_cand); release(h->frames_cand); release(h->lm_scale); release(h->lm_aux); release(h->hs);
@@ -1341,6 +1342,43 @@ int pvio_b200_klt_track_cached(pvio_b200_handle hh, uint64_t prev_id, const uint
     if (clahe_clip < 0.0) return fail(h, PVIO_B200_EINVAL, "klt_track_cached: clahe_clip must be >= 0 (0: frames are already equalised)");
     return klt_track_impl(h, prev, next, width, height, stride, prev_pts, next_pts, status, err, n_points, max_level,
                           max_iter, eps, clahe_clip, tiles_x, tiles_y, nullptr, nullptr, prev_id, next_id, border);
+}
+
+int pvio_b200_find_fundamental_mask(pvio_b200_handle hh, int n, const float *p, const float *q, double threshold, double confidence,
+                                    int max_iters, const int32_t *schedule, int n_schedule, uint8_t *mask, double *F, int32_t *info) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || n < 0 || (n > 0 && (!p || !q || !mask))) return PVIO_B200_EINVAL;
+    return fm_ransac_impl(h, n, p, q, threshold, confidence, max_iters, schedule, n_schedule, mask, F, info);
+}
+
+int pvio_b200_track_keypoints(pvio_b200_handle hh, uint64_t prev_id, const uint8_t *prev, uint64_t next_id, const uint8_t *next,
+                              int width, int height, int stride, const float *prev_pts, float *next_pts, uint8_t *status,
+                              int n_points, int max_level, int max_iter, double eps, double clahe_clip, int tiles_x, int tiles_y,
+                              int border, double ransac_threshold, double ransac_confidence) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !prev_pts || !next_pts || !status) return PVIO_B200_EINVAL;
+    if (clahe_clip < 0.0) return fail(h, PVIO_B200_EINVAL, "track_keypoints: clahe_clip must be >= 0 (0: frames are already equalised)");
+    if (n_points <= 0) return 0;
+    TRY(klt_track_impl(h, prev, next, width, height, stride, prev_pts, next_pts, status, nullptr, n_points, max_level,
+                       max_iter, eps, clahe_clip, tiles_x, tiles_y, nullptr, nullptr, prev_id, next_id, border));
+    // opencv_image.cpp:112-129: the survivors, in order, through findFundamentalMat(FM_RANSAC, 1.0, 0.99) when there are >= 8
+    std::vector<int> l;
+    std::vector<float> p, q;
+    l.reserve(n_points); p.reserve(2 * n_points); q.reserve(2 * n_points);
+    for (int i = 0; i < n_points; ++i)
+        if (status[i]) {
+            l.push_back(i);
+            p.push_back(prev_pts[2 * i]); p.push_back(prev_pts[2 * i + 1]);
+            q.push_back(next_pts[2 * i]); q.push_back(next_pts[2 * i + 1]);
+        }
+    if (l.size() >= 8) {
+        std::vector<uint8_t> mask(l.size());
+        TRY(fm_ransac_impl(h, (int)l.size(), p.data(), q.data(), ransac_threshold, ransac_confidence, 1000, nullptr, 0, mask.data(),
+                           nullptr, nullptr));
+        for (size_t i = 0; i < l.size(); ++i)
+            if (!mask[i]) status[l[i]] = 0;
+    }
+    return 0;
 }
 
 int pvio_b200_clahe(pvio_b200_handle hh, const uint8_t *src, int width, int height, int stride, double clip_limit,

@@ -20,6 +20,7 @@ struct DevBuf {
 
 struct KltState;         // klt.cu
 struct MargScratch;      // ba_marg.cu
+struct FmState;          // fmat.cu
 
 struct Handle {
     int device = 0;
@@ -87,6 +88,7 @@ struct Handle {
     bool capturing = false;
     KltState *klt = nullptr;
     MargScratch *marg = nullptr;
+    FmState *fm = nullptr;
     double *pnp_dev = nullptr, *pnp_host = nullptr;   // pnp.cu: device buffer + pinned staging, grown on demand
     size_t pnp_words = 0;
 };
@@ -125,6 +127,10 @@ void detect_free(Handle *h);
 int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state *s, int index, bool keep_on_device,
                      double *S_out, double *e_out, double *H_out, double *b_out);
 void marg_free(Handle *h);
+// fmat.cu
+int fm_ransac_impl(Handle *h, int n, const float *p, const float *q, double threshold, double confidence, int max_iters,
+                   const int32_t *schedule, int n_schedule, uint8_t *mask, double *F_out, int32_t *info);
+void fm_free(Handle *h);
 // selftest.cu
 int selftest_lie_impl(Handle *h, int n, const double *w_in, double *out);
 

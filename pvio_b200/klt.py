@@ -1,7 +1,7 @@
 """Host mirror of OpenCvImage::track_keypoints (pvio-extra/src/pvio/extra/opencv_image.cpp:88-136)
 over the C-ABI: pyramidal LK on the GPU (pvio_b200_klt_track) followed by the reference's 20-px
-border rejection (:106).  The F-matrix RANSAC of :121-129 is a SURVEY 8(f) "next" row and is not
-part of this call."""
+border rejection (:106) and the F-matrix RANSAC of :121-129 (pvio_b200_find_fundamental_mask;
+track_keypoints(..., ransac=True) is the whole OpenCvImage::track_keypoints)."""
 import ctypes as C
 
 import numpy as np
@@ -79,3 +79,51 @@ def _track_cached(ba, prev_img, next_img, curr_keypoints, next_keypoints, max_le
               _lib._ptr(status, C.c_uint8), _lib._ptr(err, C.c_float), n, max_level, max_iter, eps, float(clahe_clip),
               clahe_tiles[0], clahe_tiles[1], int(border)))
     return nxt, status[:n], err[:n]
+
+
+def find_fundamental_mask(ba, p, q, threshold=1.0, confidence=0.99, max_iters=1000, schedule=None, return_info=False):
+    """cv::findFundamentalMat(p, q, FM_RANSAC, threshold, confidence, mask) on the device (opencv_image.cpp:123);
+    schedule: int32 [S][7] injected sample indices, None = the samples OpenCV itself draws.
+    Returns (mask uint8 [n], F [3,3]) (+ info dict: iterations, best_iteration, best_model, method)."""
+    p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 2)
+    q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, 2)
+    n = len(p)
+    mask = np.zeros(max(n, 1), dtype=np.uint8)
+    F = np.zeros(9)
+    info = np.zeros(4, dtype=np.int32)
+    sch = None if schedule is None else np.ascontiguousarray(schedule, dtype=np.int32).reshape(-1, 7)
+    fn = ba.lib.pvio_b200_find_fundamental_mask
+    fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_double, C.c_double, C.c_int,
+                   C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    ba._ck(fn(ba.h, n, _lib._ptr(p, C.c_float), _lib._ptr(q, C.c_float), float(threshold), float(confidence), int(max_iters),
+              None if sch is None else _lib._ptr(sch, C.c_int32), 0 if sch is None else len(sch),
+              _lib._ptr(mask, C.c_uint8), _lib._ptr(F, C.c_double), _lib._ptr(info, C.c_int32)))
+    out = (mask[:n], F.reshape(3, 3))
+    if return_info:
+        out += ({"iterations": int(info[0]), "best_iteration": int(info[1]), "best_model": int(info[2]),
+                 "method": {0: None, 1: "ransac", 2: "lmeds", 3: "7point"}[int(info[3])]},)
+    return out
+
+
+def track_keypoints_ransac(ba, prev_img, next_img, curr_keypoints, next_keypoints=None, prev_id=1, next_id=2, max_level=3,
+                           max_iter=30, eps=0.01, border=20, clahe_clip=0.0, clahe_tiles=(8, 8), shape=None,
+                           ransac_threshold=1.0, ransac_confidence=0.99):
+    """The whole OpenCvImage::track_keypoints (opencv_image.cpp:88-136) in one C-ABI call: LK on the cached pyramids,
+    20-px border, F-matrix RANSAC over the survivors (>= 8).  Returns (next_keypoints float32 [n,2], status uint8 [n])."""
+    imgs = [None if im is None else np.ascontiguousarray(im, dtype=np.uint8) for im in (prev_img, next_img)]
+    ref = imgs[1] if imgs[1] is not None else imgs[0]
+    h, w = ref.shape if ref is not None else shape
+    cur = np.ascontiguousarray(curr_keypoints, dtype=np.float32).reshape(-1, 2)
+    nxt = cur.copy() if next_keypoints is None or len(next_keypoints) == 0 else \
+        np.array(next_keypoints, dtype=np.float32, copy=True).reshape(-1, 2)
+    n = len(cur)
+    status = np.zeros(max(n, 1), dtype=np.uint8)
+    fn = ba.lib.pvio_b200_track_keypoints
+    fn.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int,
+                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_double,
+                   C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+    ptr = lambda a: None if a is None else _lib._ptr(a, C.c_uint8)
+    ba._ck(fn(ba.h, prev_id, ptr(imgs[0]), next_id, ptr(imgs[1]), w, h, w, _lib._ptr(cur, C.c_float), _lib._ptr(nxt, C.c_float),
+              _lib._ptr(status, C.c_uint8), n, max_level, max_iter, eps, float(clahe_clip), clahe_tiles[0], clahe_tiles[1],
+              int(border), float(ransac_threshold), float(ransac_confidence)))
+    return nxt, status[:n]

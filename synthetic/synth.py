@@ -418,3 +418,29 @@ def make_pnp(seed=651, n_points=150, cal=EUROC, use_inertial=True, kf_dt=0.05, i
     return dict(frame=guess, last=last, truth=truth, imu=imu, pts=np.array(pts), zs=np.array(zs),
                 cam_q=w.cam_q_cs, cam_p=w.cam_p_cs, imu_q=w.imu_q_cs, imu_p=w.imu_p_cs, W=w.sqrt_inv_cov,
                 use_inertial=use_inertial)
+
+
+def make_fm_matches(seed=652, n=300, outlier_frac=0.2, noise=0.3, planar=False, cal=EUROC):
+    """Matched keypoints (float32 pixels) of n world points seen from two nearby camera poses, Gaussian pixel noise,
+    the first int(outlier_frac n) matches displaced by up to 40 px: the input of the F-matrix RANSAC of
+    OpenCvImage::track_keypoints (opencv_image.cpp:121-129).  Returns (p, q)."""
+    r = np.random.default_rng(seed)
+    fx, fy, cx, cy = 458.0, 457.0, 367.0, 248.0
+    X = np.stack([r.uniform(-4, 4, n), r.uniform(-3, 3, n), r.uniform(3, 12, n)], 1)
+    if planar:
+        X[:, 2] = 6.0 + 0.01 * r.standard_normal(n)
+    w = r.normal(0, 0.05, 3)
+    t = r.normal(0, 0.3, 3)
+    th = np.linalg.norm(w)
+    k = w / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    x1 = np.stack([fx * X[:, 0] / X[:, 2] + cx, fy * X[:, 1] / X[:, 2] + cy], 1)
+    X2 = X @ R.T + t
+    x2 = np.stack([fx * X2[:, 0] / X2[:, 2] + cx, fy * X2[:, 1] / X2[:, 2] + cy], 1)
+    x1 = x1 + r.normal(0, noise, x1.shape)
+    x2 = x2 + r.normal(0, noise, x2.shape)
+    no = int(outlier_frac * n)
+    if no:
+        x2[:no] += r.uniform(-40, 40, (no, 2))
+    return x1.astype(np.float32), x2.astype(np.float32)
