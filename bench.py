@@ -461,6 +461,22 @@ def run_gpu(args):
             klt_info["detect_keypoints"]["cv2_error"] = str(e)
     except Exception as e:
         klt_info["cached_error"] = str(e)
+    try:
+        # the F-matrix outlier rejection of track_keypoints (opencv_image.cpp:121-129) and the whole call with it
+        fp, fq = synth.make_fm_matches(seed=652, n=400, outlier_frac=0.2)
+        f_s, (fmask, _, finfo) = time_call(lambda: klt.find_fundamental_mask(kb, fp, fq, return_info=True), 50, warm=3)
+        klt_info["f_ransac"] = {"ms_per_call_e2e": f_s * 1e3, "matches": int(len(fp)), "inliers": int(fmask.sum()),
+                                "serial_iterations": finfo["iterations"], "iterations_evaluated_on_device": 1000}
+        w_s, _ = time_call(lambda: klt.track_keypoints_ransac(kb, prev, nxt, pts, prev_id=901, next_id=902), 20, warm=2)
+        klt_info["track_keypoints_whole_call_ms"] = w_s * 1e3
+        try:
+            import cv2
+            cf_s, _ = time_call(lambda: cv2.findFundamentalMat(fp, fq, cv2.FM_RANSAC, 1.0, 0.99), 50, warm=3)
+            klt_info["f_ransac"]["cv2_ms"] = cf_s * 1e3
+        except Exception as e:
+            klt_info["f_ransac"]["cv2_error"] = str(e)
+    except Exception as e:
+        klt_info["f_ransac_error"] = str(e)
 
     # ---- visual_inertial_pnp (150 points + IMU prior): one kernel launch per solve, host buffers in/out
     d = synth.make_pnp()

@@ -966,9 +966,9 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     }
 }
 
-static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) { solve_body<true>(a); }
+static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) { pdl_prologue(); solve_body<true>(a); }
 // visual-only windows (no IMU / prior / plane factors): small register footprint, many CTAs per SM
-static __global__ void __launch_bounds__(64, 10) solve_kernel_visual(SolveArgs a) { solve_body<false>(a); }
+static __global__ void __launch_bounds__(64, 10) solve_kernel_visual(SolveArgs a) { pdl_prologue(); solve_body<false>(a); }
 
 // Non-vision part of the cost at the candidate state (IMU + prior + plane), one CTA per window.
 struct CostArgs {
@@ -1003,6 +1003,7 @@ struct CostArgs {
 };
 
 static __global__ void aux_cost_kernel(CostArgs a) {
+    pdl_prologue();
     const int w = blockIdx.x + a.w0;
     const WinHdr &H = a.hdr[w];
     const WinConst &wc = a.cst[w];
@@ -1114,6 +1115,7 @@ struct JvAuxArgs {
 };  // c.loop != 0: runs only for windows whose GN step left the trust region, then picks the dogleg step (tr_after_jv)
 
 static __global__ void jv_aux_kernel(JvAuxArgs ja) {
+    pdl_prologue();
     const CostArgs &a = ja.c;
     const int w = blockIdx.x + a.w0;
     const WinHdr &H = a.hdr[w];
