@@ -397,7 +397,6 @@ struct StepCfg {
     int dump = 0;
     int loop = 0;                  // kernels obey the per-window trust-region flags
     int w0 = 0;                    // first window (sub-batch pipelining)
-    int pdl = 0;                   // programmatic dependent launch of the body's kernels (latency path, ba_types.h)
     cudaStream_t stream = nullptr; // nullptr: the handle's stream
 };
 
@@ -417,8 +416,8 @@ static size_t solve_smem_one(const WinHdr &H, bool lean) {
     const size_t nb = (D + 3) / 4, Dp = nb * 4;
     const size_t np_ = (size_t)H.N * (H.N + 1) / 2;
     size_t scr = lean ? Dp + 10 * 36 + 36 : std::max<size_t>(Dp, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);
-    if (H.use_inertial) scr = std::max<size_t>(scr, 2 * (8 * 450 + 8 * 16));      // kImuRound factors: raw + whitened J, r
-    if (H.n_prior > 0) scr = std::max<size_t>(scr, 3 * 15 * (size_t)H.n_prior + 9 * (size_t)H.n_prior);
+    if (H.use_inertial) scr = std::max<size_t>(scr, 2 * (8 * 450 + 8 * 16) + 8 * 225);      // kImuRound factors: raw + whitened J, r; their W
+    if (H.n_prior > 0) scr = std::max<size_t>(scr, 3 * 15 * (size_t)H.n_prior + 9 * (size_t)H.n_prior + 8 * 225);   // + one 15 x 15 block per warp
     return sizeof(double) * ((nb + 1) * (nb + 2) / 2 * 18 + 4 * Dp + (size_t)H.N * 36 + scr);   // tiles of kTP = 18 doubles (ba_solve.cuh)
 }
 
@@ -493,27 +492,10 @@ static size_t schur_launch_smem(int N, int nfree) { return schur_smem_bytes<real
         if (e__ != cudaSuccess) return fail((h), PVIO_B200_ECUDA, "launch of " what, e__);        \
     } while (0)
 
-// Kernel launch of the solve pipeline.  pdl: the launch carries cudaLaunchAttributeProgrammaticStreamSerialization, i.e. the
-// kernel may be scheduled before its predecessor in the stream has finished (it parks in pdl_prologue()); used for every
-// kernel of a captured single-window solve except the first node of the graph.
-template <typename... KArgs, typename... Args>
-static void launch_k(Handle *h, const StepCfg &c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = (c.pdl && h->pdl_seq++ > 0) ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
-}
-
 // linearise + Schur stage of windows [w0, w0 + n)
 // zeroes the direct / reduced system of the buffer set a sweep is about to accumulate into with atomics (several CTAs
 // per window: the latency path)
 static __global__ void zero_system_kernel(PipeArgs a_in, int npairs_cap) {
-    pdl_prologue();
     PipeArgs a = a_in;
     const int w = blockIdx.x + a.w0;
     const int bsel = pipe_buffer(a, w);
@@ -536,21 +518,21 @@ static int launch_lin(Handle *h, int n, const StepCfg &c, const BatchShape &b, b
     a.victim_only = victim_only ? 1 : 0;
     a.spec = spec ? 1 : 0;
     if (gx > 1) {
-        launch_k(h, c, zero_system_kernel, dim3(n), dim3(256), 0, st, a, h->Ncap * (h->Ncap + 1) / 2);
+        zero_system_kernel<<<n, 256, 0, st>>>(a, h->Ncap * (h->Ncap + 1) / 2);
         ++h->launches;
         LAUNCH_CK(h, "zero_system_kernel");
     }
     const int Mp = (b.M + 31) & ~31;
     if (!h->hs_double) {
         if (!loss) return fail(h, PVIO_B200_EINVAL, "the loss-free sweep runs in fp64");
-        launch_k(h, c, lin_obs_kernel<true, float, kLinWarps, kLinBlocks>, dim3(gx, n), dim3(kLinWarps * 32), lin_smem_bytes<float>(b.N, Mp, kLinWarps), st, a);
+        lin_obs_kernel<true, float, kLinWarps, kLinBlocks><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<float>(b.N, Mp, kLinWarps), st>>>(a);
         LAUNCH_CK(h, "lin_obs_kernel<float>");
-        if (gx > 1) { launch_k(h, c, lm_finish_kernel<float>, dim3((b.M + 127) / 128, n), dim3(128), 0, st, a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<float>"); }
+        if (gx > 1) { lm_finish_kernel<float><<<dim3((b.M + 127) / 128, n), 128, 0, st>>>(a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<float>"); }
     } else {
-        if (loss) launch_k(h, c, lin_obs_kernel<true, double, kLinWarps, 2>, dim3(gx, n), dim3(kLinWarps * 32), lin_smem_bytes<double>(b.N, Mp, kLinWarps), st, a);
-        else launch_k(h, c, lin_obs_kernel<false, double, kLinWarps, 2>, dim3(gx, n), dim3(kLinWarps * 32), lin_smem_bytes<double>(b.N, Mp, kLinWarps), st, a);
+        if (loss) lin_obs_kernel<true, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp, kLinWarps), st>>>(a);
+        else lin_obs_kernel<false, double, kLinWarps, 2><<<dim3(gx, n), kLinWarps * 32, lin_smem_bytes<double>(b.N, Mp, kLinWarps), st>>>(a);
         LAUNCH_CK(h, "lin_obs_kernel<double>");
-        if (gx > 1) { launch_k(h, c, lm_finish_kernel<double>, dim3((b.M + 127) / 128, n), dim3(128), 0, st, a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<double>"); }
+        if (gx > 1) { lm_finish_kernel<double><<<dim3((b.M + 127) / 128, n), 128, 0, st>>>(a); ++h->launches; LAUNCH_CK(h, "lm_finish_kernel<double>"); }
     }
     ++h->launches;
     return 0;
@@ -563,10 +545,10 @@ static int launch_schur(Handle *h, int n, const StepCfg &c, const BatchShape &b,
     a.victim_only = victim_only ? 1 : 0;
     const int sgx = std::min(gx, std::max(1, (b.M + kSlab - 1) / kSlab));
     if (!h->hs_double) {
-        launch_k(h, c, schur_kernel<float, kSchurThreads, kSchurBlocks>, dim3(sgx, n), dim3(kSchurThreads), schur_launch_smem<float>(b.N, b.nfree), st, a);
+        schur_kernel<float, kSchurThreads, kSchurBlocks><<<dim3(sgx, n), kSchurThreads, schur_launch_smem<float>(b.N, b.nfree), st>>>(a);
         LAUNCH_CK(h, "schur_kernel<float>");
     } else {
-        launch_k(h, c, schur_kernel<double, kSchurThreads, 1>, dim3(sgx, n), dim3(kSchurThreads), schur_launch_smem<double>(b.N, b.nfree), st, a);
+        schur_kernel<double, kSchurThreads, 1><<<dim3(sgx, n), kSchurThreads, schur_launch_smem<double>(b.N, b.nfree), st>>>(a);
         LAUNCH_CK(h, "schur_kernel<double>");
     }
     ++h->launches;
@@ -617,8 +599,8 @@ static int run_solve(Handle *h, int n, const StepCfg &c, const BatchShape &b) {
     const bool visual = n >= 64 && !b.inertial && !b.planes && b.solve_smem_lean <= 48 * 1024;
     const size_t smem = visual ? b.solve_smem_lean : b.solve_smem_full;
     if (smem > 220 * 1024) return fail(h, PVIO_B200_EINVAL, "reduced system too large for shared memory");
-    if (visual) launch_k(h, c, solve_kernel_visual, dim3(n), dim3(64), smem, st, a);
-    else launch_k(h, c, solve_kernel, dim3(n), dim3(256), smem, st, a);
+    if (visual) solve_kernel_visual<<<n, 64, smem, st>>>(a);
+    else solve_kernel<<<n, 256, smem, st>>>(a);
     ++h->launches;
     LAUNCH_CK(h, "solve_kernel");
     return 0;
@@ -660,11 +642,11 @@ static int launch_update(Handle *h, int n, const StepCfg &c, const BatchShape &b
     constexpr int kW = kUpdWarps;
     constexpr int kB = 4, kBf = kUpdBlocks;
     if (kMode == 1 && n * 2 < h->sm_count) {        // latency path: one wide CTA per window for the back-substitution
-        if (!h->hs_double) launch_k(h, c, update_obs_kernel<true, float, 8, 2, 1>, dim3(gx, n), dim3(256), upd_smem_bytes<float>(b.N, Mp, 8), st, u);
-        else launch_k(h, c, update_obs_kernel<true, double, 8, 2, 1>, dim3(gx, n), dim3(256), upd_smem_bytes<double>(b.N, Mp, 8), st, u);
+        if (!h->hs_double) update_obs_kernel<true, float, 8, 2, 1><<<dim3(gx, n), 256, upd_smem_bytes<float>(b.N, Mp, 8), st>>>(u);
+        else update_obs_kernel<true, double, 8, 2, 1><<<dim3(gx, n), 256, upd_smem_bytes<double>(b.N, Mp, 8), st>>>(u);
     }
-    else if (!h->hs_double) launch_k(h, c, update_obs_kernel<true, float, kW, kBf, kMode>, dim3(gx, n), dim3(kW * 32), upd_smem_bytes<float>(b.N, Mp, kW), st, u);
-    else launch_k(h, c, update_obs_kernel<true, double, kW, kB, kMode>, dim3(gx, n), dim3(kW * 32), upd_smem_bytes<double>(b.N, Mp, kW), st, u);
+    else if (!h->hs_double) update_obs_kernel<true, float, kW, kBf, kMode><<<dim3(gx, n), kW * 32, upd_smem_bytes<float>(b.N, Mp, kW), st>>>(u);
+    else update_obs_kernel<true, double, kW, kB, kMode><<<dim3(gx, n), kW * 32, upd_smem_bytes<double>(b.N, Mp, kW), st>>>(u);
     ++h->launches;
     LAUNCH_CK(h, "update_obs_kernel");
     return 0;
@@ -673,7 +655,7 @@ static int launch_update(Handle *h, int n, const StepCfg &c, const BatchShape &b
 static int launch_aux_cost(Handle *h, int n, const StepCfg &c) {
     cudaStream_t st = c.stream ? c.stream : h->stream;
     const CostArgs k = make_cost_args(h, c);
-    launch_k(h, c, aux_cost_kernel, dim3(n), dim3(64), sizeof(double) * 15 * kMaxFrames, st, k);
+    aux_cost_kernel<<<n, 64, sizeof(double) * 15 * kMaxFrames, st>>>(k);
     ++h->launches;
     LAUNCH_CK(h, "aux_cost_kernel");
     return 0;
@@ -699,12 +681,12 @@ static int iteration_body(Handle *h, int n, const StepCfg &c, const BatchShape &
     TRY(launch_update<1>(h, n, c, b, 1));
     {
         const UpdArgs u = make_upd_args(h, c);
-        launch_k(h, c, jv_vision_kernel<true>, dim3(sweep_grid_x(h, n), n), dim3(kLinThreads), 0, st, u);
+        jv_vision_kernel<true><<<dim3(sweep_grid_x(h, n), n), kLinThreads, 0, st>>>(u);
         LAUNCH_CK(h, "jv_vision_kernel");
         JvAuxArgs ja;
         ja.c = make_cost_args(h, c);
         ja.v_pose = h->v_pose.d; ja.acc = h->acc.d;
-        launch_k(h, c, jv_aux_kernel, dim3(n), dim3(64), sizeof(double) * 15 * kMaxFrames, st, ja);
+        jv_aux_kernel<<<n, 64, sizeof(double) * 15 * kMaxFrames, st>>>(ja);
         LAUNCH_CK(h, "jv_aux_kernel");
         h->launches += 2;
     }
@@ -739,10 +721,6 @@ static int run_solve_loop(Handle *h, int n, int max_iter, double max_time, doubl
         cudaGraphExec_t ge = nullptr;
         CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         h->capturing = true;
-        h->pdl_seq = 0;
-#ifndef PVIO_NO_PDL                // tuning builds of tools/ only (A/B of the programmatic launch)
-        c.pdl = 1;                 // captured as programmatic dependency edges between the kernel nodes
-#endif
         int rc = 0;
         for (int i = 0; i < bodies && rc == 0; ++i) rc = iteration_body(h, n, c, b);
         h->capturing = false;
@@ -1415,5 +1393,11 @@ int pvio_b200_selftest_lie(pvio_b200_handle hh, int n, const double *w, double *
     if (!h || !w || !out || n < 1) return PVIO_B200_EINVAL;
     return selftest_lie_impl(h, n, w, out);
 }
+
+#ifdef PVIO_SOLVE_STAMPS
+int pvio_b200_debug_solve_stamps(long long *out) {      // tuning builds only (tools/solve_stamps.py); not declared in include/pvio_b200.h
+    return cudaMemcpyFromSymbol(out, pvio::g_solve_stamps, sizeof(long long) * 16) == cudaSuccess ? 0 : PVIO_B200_ECUDA;
+}
+#endif
 
 }  // extern "C"

@@ -86,7 +86,6 @@ struct Handle {
     typedef std::tuple<int, int, int, int> GraphKey;
     std::map<GraphKey, std::pair<cudaGraphExec_t, int>> graphs;
     bool capturing = false;
-    int pdl_seq = 0;                              // kernels launched so far in the sequence being captured (api.cu: launch_k)
     KltState *klt = nullptr;
     MargScratch *marg = nullptr;
     FmState *fm = nullptr;

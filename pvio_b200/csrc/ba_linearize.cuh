@@ -382,7 +382,6 @@ __device__ __forceinline__ void lm_finish(const PipeArgs &a, int w, int l, int N
 
 template <typename real>
 __global__ void __launch_bounds__(128) lm_finish_kernel(PipeArgs a_in) {
-    pdl_prologue();
     PipeArgs a = a_in;
     const int w = blockIdx.y + a.w0;
     const int bsel = pipe_buffer(a, w);
@@ -420,7 +419,6 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 lin_obs_kernel(PipeArgs a_in) {
     typedef typename Vec2<real>::type real2;
     constexpr int kThreads = kWarps * 32;
-    pdl_prologue();
     PipeArgs a = a_in;
     const int w = blockIdx.y + a.w0;
     const int bsel = pipe_buffer(a, w);

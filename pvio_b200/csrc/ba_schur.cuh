@@ -63,7 +63,6 @@ template <typename real, int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 schur_kernel(PipeArgs a_in) {
     typedef typename Vec2<real>::type real2;
-    pdl_prologue();
     PipeArgs a = a_in;
     const int w = blockIdx.y + a.w0;
     if (a.loop) {

@@ -475,6 +475,13 @@ __device__ inline bool chol_solve_tiled(double *A, double *x, int nb, int *flag_
 constexpr int kSolveImuSlab = 15 * 30 + 16;     // raw J + r per factor
 constexpr int kImuRound = 8;                    // IMU factors linearised concurrently by solve_kernel
 
+#ifdef PVIO_SOLVE_STAMPS          // tuning builds of tools/ only: clock64() at the phase boundaries of solve_kernel
+__device__ long long g_solve_stamps[16];
+#define SOLVE_STAMP(k) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) g_solve_stamps[k] = clock64(); } while (0)
+#else
+#define SOLVE_STAMP(k) do { } while (0)
+#endif
+
 template <bool kFull>
 static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     const int w = blockIdx.x + a.w0;
@@ -513,6 +520,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     __shared__ double cost_sm[4];
     __shared__ int flag_sm;
 
+    SOLVE_STAMP(0);
     for (int i = tid; i < nA; i += nt) A[i] = 0.0;
     for (int i = tid; i < 4 * Dp; i += nt) g[i] = 0.0;      // g, gu, hcorr, xs contiguous
     if (tid < 4) cost_sm[tid] = 0.0;
@@ -672,6 +680,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         }
     }
     __syncthreads();
+    SOLVE_STAMP(1);
     // ---- IMU factors (bundle_adjustor.cpp:220-242): no loss
     if (kFull && inertial && H.n_imu > 0) {
         const int32_t *idx = a.imu_idx + (size_t)w * a.Ncap * 2;
@@ -682,16 +691,27 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             double *rraw = scr + kImuRound * 450;
             double *Jw = rraw + kImuRound * 16;              // [R][450]
             double *rw = Jw + kImuRound * 450;               // [R][16]
+            double *Wsm = rw + kImuRound * 16;               // [R][225] sqrt information matrices of the round
+            __shared__ int imu_fr[2 * kImuRound];            // frame pair of each factor of the round (read in every inner loop)
+            __shared__ int imu_chain;
+            if (tid >= 32 && tid < 32 + 2 * nb) imu_fr[tid - 32] = idx[2 * n0 + tid - 32];
             if (tid < nb) {
                 const int n = n0 + tid;
                 imu_factor_raw(frames + idx[2 * n] * kFrameStride, frames + idx[2 * n + 1] * kFrameStride,
                                recs + (size_t)n * kImuStride, wc, a.alias_bias, rraw + tid * 16, Jraw + tid * 450);
+            } else if (tid >= 32) {
+                // the other warps meanwhile stage W (one coalesced pass instead of 15 L2 loads per whitened entry)
+                for (int e = tid - 32; e < nb * 225; e += nt - 32) {      // (lanes nb..31 of warp 0 idle with the factor threads)
+                    const int n = e / 225;
+                    Wsm[e] = __ldg(recs + (size_t)(n0 + n) * kImuStride + 11 + (e - n * 225));
+                }
             }
             __syncthreads();
+            SOLVE_STAMP(2);
             // whiten: Jw = W J, rw = W r                      :157 and the "sqrt_inv_cov *" lines
             for (int e = tid; e < nb * 15 * 31; e += nt) {
                 const int n = e / (15 * 31), rem = e - n * 15 * 31, row = rem / 31, col = rem - row * 31;
-                const double *Wm = recs + (size_t)(n0 + n) * kImuStride + 11 + row * 15;
+                const double *Wm = Wsm + n * 225 + row * 15;
                 double s = 0.0;
                 if (col < 30) { for (int k = 0; k < 15; ++k) s += Wm[k] * Jraw[n * 450 + k * 30 + col]; Jw[n * 450 + row * 30 + col] = s; }
                 else { for (int k = 0; k < 15; ++k) s += Wm[k] * rraw[n * 16 + k]; rw[n * 16 + row] = s; }
@@ -700,19 +720,24 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             // accumulate.  Two factors touch the same entries of the system only if they share a frame; the reference's
             // factors form a chain (frame n, n + 1), so the factors at even positions of the round go first, all at once,
             // then the odd ones.  A round whose factors are not such a chain falls back to one factor at a time.
-            bool chain = true;                               // no two factors of equal parity share a frame
-            for (int n = 0; n < nb && chain; ++n)
-                for (int m = n + 2; m < nb; m += 2) {
-                    const int a0 = idx[2 * (n0 + n)], a1 = idx[2 * (n0 + n) + 1], b0 = idx[2 * (n0 + m)], b1 = idx[2 * (n0 + m) + 1];
-                    chain &= (a0 != b0 && a0 != b1 && a1 != b0 && a1 != b1);
-                }
+            if (tid == 0) {
+                bool ch = true;                              // no two factors of equal parity share a frame
+                for (int n = 0; n < nb && ch; ++n)
+                    for (int m = n + 2; m < nb; m += 2) {
+                        const int a0 = imu_fr[2 * n], a1 = imu_fr[2 * n + 1], b0 = imu_fr[2 * m], b1 = imu_fr[2 * m + 1];
+                        ch &= (a0 != b0 && a0 != b1 && a1 != b0 && a1 != b1);
+                    }
+                imu_chain = ch ? 1 : 0;
+            }
+            __syncthreads();
+            const bool chain = imu_chain != 0;
             const int phases = chain ? 2 : nb;
             for (int ph = 0; ph < phases; ++ph) {
                 const int first = ph, step = chain ? 2 : nb, cnt = chain ? (nb - ph + 1) / 2 : 1;
                 for (int e = tid; e < cnt * 30 * 31; e += nt) {
                     const int q = e / (30 * 31), rem = e - q * 30 * 31;
                     const int n = first + q * step;
-                    const int fi = idx[2 * (n0 + n)], fj = idx[2 * (n0 + n) + 1];
+                    const int fi = imu_fr[2 * n], fj = imu_fr[2 * n + 1];
                     const int ra = rem / 31, cb_ = rem - ra * 31;
                     const int ga = (ra < 15 ? fi * 15 + ra : fj * 15 + ra - 15);
                     double s = 0.0;
@@ -737,6 +762,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         }
     }
 
+    SOLVE_STAMP(3);
     // ---- marginalisation prior (bundle_adjustor.cpp:126-139): no loss
     if (kFull && inertial && H.n_prior > 0) {
         const int n = H.n_prior, d = 15 * n, dcap = 15 * a.Ncap;
@@ -749,54 +775,115 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         double *rr = r0 + d;              // [d] r = S r0 + e
         double *vv = rr + d;              // [d] S^T r
         double *Ji = vv + d;              // [n][9] Jr^-1
+        double *Bs = Ji + 9 * n;          // [warps][225] block staging of the Hessian pass
+        __shared__ int pf_s[kMaxFrames];
+        if (tid >= 32 && tid < 32 + n) pf_s[tid - 32] = pf[tid - 32];
         if (tid < n) prior_frame_raw(frames + pf[tid] * kFrameStride, x0 + tid * kFrameStride, r0 + 15 * tid, Ji + 9 * tid);
         __syncthreads();
-        for (int i = tid >> 5; i < d; i += nt >> 5) {          // warp per row: coalesced reads of S
-            double s = 0.0;
-            for (int k = tid & 31; k < d; k += 32) s += S[(size_t)i * d + k] * r0[k];
+        // warp per row, kPriorRows rows per pass: the loads of a pass (rows x d / 32 per lane) are all in flight
+        // together -- S sits in L2 and a row at a time was one exposed L2 round trip per row
+        constexpr int kPriorRows = 5;
+        for (int i0 = (tid >> 5) * kPriorRows; i0 < d; i0 += (nt >> 5) * kPriorRows) {
+            double sr[kPriorRows];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if ((tid & 31) == 0) rr[i] = ev[i] + s;            // marginalization_error_cost.h:91
+            for (int r = 0; r < kPriorRows; ++r) sr[r] = 0.0;
+#pragma unroll 2
+            for (int k = tid & 31; k < d; k += 32) {
+                double sv[kPriorRows];
+#pragma unroll
+                for (int r = 0; r < kPriorRows; ++r) sv[r] = i0 + r < d ? __ldg(S + (size_t)(i0 + r) * d + k) : 0.0;
+                const double rk = r0[k];
+#pragma unroll
+                for (int r = 0; r < kPriorRows; ++r) sr[r] += sv[r] * rk;
+            }
+#pragma unroll
+            for (int r = 0; r < kPriorRows; ++r) {
+                double s = sr[r];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if ((tid & 31) == 0 && i0 + r < d) rr[i0 + r] = ev[i0 + r] + s;     // marginalization_error_cost.h:91
+            }
         }
         __syncthreads();
-        for (int i = tid; i < d; i += nt) {
+        for (int i = tid; i < d; i += nt) {                    // S^T r: column i, the loads of 8 rows ahead of the sum
             double s = 0.0;
-            for (int k = 0; k < d; ++k) s += S[(size_t)k * d + i] * rr[k];
+            int k = 0;
+            for (; k + 8 <= d; k += 8) {
+                double sv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sv[u] = __ldg(S + (size_t)(k + u) * d + i);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += sv[u] * rr[k + u];
+            }
+            for (; k < d; ++k) s += __ldg(S + (size_t)k * d + i) * rr[k];
             vv[i] = s;
         }
         if (tid == 0) { double c = 0.0; for (int k = 0; k < d; ++k) c += rr[k] * rr[k]; cost_sm[2] = 0.5 * c; }
         __syncthreads();
+        SOLVE_STAMP(4);
         // g += E^T vv ; H += E^T Lambda E  with E = blockdiag(Jr^-1, I, I, I, I) per frame  (:72-88)
         for (int i = tid; i < d; i += nt) {
             const int fi = i / 15, ci = i - fi * 15;
             double s;
             if (ci < 3) { s = 0.0; for (int k = 0; k < 3; ++k) s += Ji[9 * fi + 3 * k + ci] * vv[15 * fi + k]; }
             else s = vv[i];
-            const int gi = pf[fi] * 15 + ci;
+            const int gi = pf_s[fi] * 15 + ci;
             g[gi] += s; gu[gi] += s;
         }
-        for (int e = tid; e < d * d; e += nt) {
-            const int i = e / d, j = e - i * d;
-            const int fi = i / 15, ci = i - fi * 15, fj = j / 15, cj = j - fj * 15;
-            const int gi = pf[fi] * 15 + ci, gj = pf[fj] * 15 + cj;
-            if (gj > gi) continue;
-            double s = 0.0;
-            if (ci < 3 && cj < 3) {
-                for (int k = 0; k < 3; ++k)
-                    for (int m = 0; m < 3; ++m)
-                        s += Ji[9 * fi + 3 * k + ci] * L[(size_t)(15 * fi + k) * d + 15 * fj + m] * Ji[9 * fj + 3 * m + cj];
-            } else if (ci < 3) {
-                for (int k = 0; k < 3; ++k) s += Ji[9 * fi + 3 * k + ci] * L[(size_t)(15 * fi + k) * d + j];
-            } else if (cj < 3) {
-                for (int m = 0; m < 3; ++m) s += L[(size_t)i * d + 15 * fj + m] * Ji[9 * fj + 3 * m + cj];
-            } else {
-                s = L[(size_t)i * d + j];
+        // H += E^T Lambda E by 15 x 15 frame blocks, one warp per block (fi, fj) of the lower triangle: the block of
+        // Lambda comes in with 8 loads per lane in flight at once (the per-entry loop it replaces was a chain of exposed
+        // L2 round trips), the Jr^-1 factors are applied to its first three columns, then rows, in shared memory
+        {
+            const int lane = tid & 31, wp = tid >> 5, nw = nt >> 5;
+            double *B = Bs + wp * 225;
+            for (int blk = wp; blk < n * n; blk += nw) {
+                const int fi = blk / n, fj = blk - fi * n;
+                const int gfi = pf_s[fi], gfj = pf_s[fj];
+                if (gfj > gfi) continue;                              // (warp-uniform) the transposed block covers it
+                double lv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = lane + 32 * u;
+                    const int r = e / 15, c = e - r * 15;
+                    lv[u] = e < 225 ? __ldg(L + (size_t)(15 * fi + r) * d + 15 * fj + c) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (lane + 32 * u < 225) B[lane + 32 * u] = lv[u];
+                __syncwarp();
+                double t0 = 0.0, t1 = 0.0;                            // columns 0..2 <- B[:, 0..2] Jr_j^-1
+                {
+                    const double *Jj = Ji + 9 * fj;
+                    const int e0 = lane, e1 = lane + 32;              // 45 outputs (r, cj)
+                    if (e0 < 45) { const int r = e0 / 3, cj = e0 - r * 3; for (int m = 0; m < 3; ++m) t0 += B[r * 15 + m] * Jj[3 * m + cj]; }
+                    if (e1 < 45) { const int r = e1 / 3, cj = e1 - r * 3; for (int m = 0; m < 3; ++m) t1 += B[r * 15 + m] * Jj[3 * m + cj]; }
+                    __syncwarp();
+                    if (e0 < 45) B[(e0 / 3) * 15 + e0 % 3] = t0;
+                    if (e1 < 45) B[(e1 / 3) * 15 + e1 % 3] = t1;
+                    __syncwarp();
+                }
+                {
+                    const double *Jf = Ji + 9 * fi;                   // rows 0..2 <- Jr_i^-T B[0..2, :]
+                    const int e0 = lane, e1 = lane + 32;              // 45 outputs (ci, c)
+                    t0 = 0.0; t1 = 0.0;
+                    if (e0 < 45) { const int ci = e0 / 15, c = e0 - ci * 15; for (int k = 0; k < 3; ++k) t0 += Jf[3 * k + ci] * B[k * 15 + c]; }
+                    if (e1 < 45) { const int ci = e1 / 15, c = e1 - ci * 15; for (int k = 0; k < 3; ++k) t1 += Jf[3 * k + ci] * B[k * 15 + c]; }
+                    __syncwarp();
+                    if (e0 < 45) B[e0] = t0;
+                    if (e1 < 45) B[e1] = t1;
+                    __syncwarp();
+                }
+                for (int e = lane; e < 225; e += 32) {                // each (gi, gj) has a unique owner: prior frames are distinct
+                    const int r = e / 15, c = e - r * 15;
+                    if (fi == fj && c > r) continue;
+                    A[tri(gfi * 15 + r, gfj * 15 + c)] += B[e];
+                }
+                __syncwarp();
             }
-            A[tri(gi, gj)] += s;       // each (gi,gj) has a unique (i,j) owner: prior frames are distinct
         }
         __syncthreads();
     }
 
+    SOLVE_STAMP(5);
     // ---- plane factors (bundle_adjustor.cpp:162-196): CauchyLoss
     if (kFull && H.n_ptracks > 0) {
         const double *pl = a.plane_param + (size_t)w * a.Pcap * 4;
@@ -809,8 +896,13 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         // no observation), and the corrected residual go to a scratch row; then thread per ENTRY of the pose block of the
         // system sums over the tracks -- no atomics (fp64 atomicAdd on shared memory is a compare-and-swap loop, and all
         // tracks of a plane hit the same frames: the atomic version took 600 us of the kernel's 820 on cfg4)
-        const int PW = 6 * a.Ncap + 2;                              // row: [6 N] Jacobian, residual
-        double *PJ = a.pt_J + (size_t)w * a.Tcap * PW;
+        const int PW = 6 * N + 2;                                   // row: [6 N] Jacobian, residual
+        // the rows live in the kernel's shared scratch when they fit (inertial windows: the IMU slabs are free again),
+        // otherwise in the per-window global scratch
+        unsigned dyn_bytes;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+        const size_t scr_words = dyn_bytes / sizeof(double) - (size_t)(scr - reinterpret_cast<double *>(smem_raw));
+        double *PJ = (size_t)H.n_ptracks * PW <= scr_words ? scr : a.pt_J + (size_t)w * a.Tcap * (6 * a.Ncap + 2);
         for (int t = tid; t < H.n_ptracks; t += nt) {
             const int b0 = ptb[t], K = ptb[t + 1] - b0;
             double r, J[6 * kMaxFrames];
@@ -829,7 +921,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             if (e >= P6 * (P6 + 1) / 2) {                            // gradient entries
                 const int i = e - P6 * (P6 + 1) / 2;
                 double sg = 0.0;
-                for (int t = 0; t < T; ++t) sg += __ldcg(PJ + (size_t)t * PW + i) * __ldcg(PJ + (size_t)t * PW + P6);
+                for (int t = 0; t < T; ++t) sg += PJ[(size_t)t * PW + i] * PJ[(size_t)t * PW + P6];
                 const int gi = (i / 6) * stride + (i % 6);
                 g[gi] += sg; gu[gi] += sg;
                 continue;
@@ -839,7 +931,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             while (i * (i + 1) / 2 > e) --i;
             const int j = e - i * (i + 1) / 2;                       // j <= i
             double sh = 0.0;
-            for (int t = 0; t < T; ++t) sh += __ldcg(PJ + (size_t)t * PW + i) * __ldcg(PJ + (size_t)t * PW + j);
+            for (int t = 0; t < T; ++t) sh += PJ[(size_t)t * PW + i] * PJ[(size_t)t * PW + j];
             const int gi = (i / 6) * stride + (i % 6), gj = (j / 6) * stride + (j % 6);
             A[tri(gi, gj)] += sh;                                    // gi >= gj since i >= j
         }
@@ -862,6 +954,7 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             go[(compact ? __fns(freem, 0, fi + 1) : fi) * 15 + (i % stride)] = g[i];
         }
     }
+    SOLVE_STAMP(6);
     // ---- Jacobi scale, LM diagonal, constant blocks
     double *scale = a.pose_scale + (size_t)w * 15 * a.Ncap;
     double my_gdx = 0.0;
@@ -878,13 +971,21 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     }
     __syncthreads();
     const int fixed_mask = mask_c;
-    for (int e = tid; e < Dp * Dp; e += nt) {
-        const int i = e / Dp, j = e - i * Dp;
-        if (j > i) continue;
-        if (i >= D) { A[tri(i, j)] = (i == j) ? 1.0 : 0.0; continue; }     // padding rows
-        const int fi = i / stride, ci = i - fi * stride, fj = j / stride, cj = j - fj * stride;
-        const bool mi = ((fixed_mask >> fi) & 1) && ci < 6, mj = ((fixed_mask >> fj) & 1) && cj < 6;
-        if (mi || mj) A[tri(i, j)] = (i == j) ? 1.0 : 0.0;
+    {
+        // identity rows / columns for the pinned unknowns: the pose rows of constant frames and the padding rows >= D.
+        // Work item (q, j): the q-th pinned index m against column j; a pair of pinned indices is written by the larger one.
+        const unsigned fm = (unsigned)fixed_mask & ((1u << nfr) - 1u);
+        const int nfix6 = 6 * __popc(fm), npin = nfix6 + (Dp - D);
+        for (int e = tid; e < npin * Dp; e += nt) {
+            const int q = e / Dp, j = e - q * Dp;
+            int m;
+            if (q < nfix6) { const int fq = q / 6; m = __fns(fm, 0, fq + 1) * stride + (q - fq * 6); }
+            else m = D + (q - nfix6);
+            const int fj = j / stride;
+            const bool pj = j >= D || (((fm >> fj) & 1u) && (j - fj * stride) < 6);
+            if (pj && j > m) continue;
+            A[j > m ? tri(j, m) : tri(m, j)] = (j == m) ? 1.0 : 0.0;
+        }
     }
     double *reg_keep = scr;       // [D]
     for (int i = tid; i < D; i += nt) {
@@ -895,7 +996,9 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         xs[i] = -g[i];
     }
     __syncthreads();
+    SOLVE_STAMP(7);
     const bool ok = chol_solve_tiled<kFull>(A, xs, nb, &flag_sm);
+    SOLVE_STAMP(8);
 
     // ---- outputs
     double *dxo = a.dx_pose + (size_t)w * a.Ncap * 15;
@@ -964,11 +1067,12 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             ctrl.fresh = 1;
         }
     }
+    SOLVE_STAMP(9);
 }
 
-static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) { pdl_prologue(); solve_body<true>(a); }
+static __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) { solve_body<true>(a); }
 // visual-only windows (no IMU / prior / plane factors): small register footprint, many CTAs per SM
-static __global__ void __launch_bounds__(64, 10) solve_kernel_visual(SolveArgs a) { pdl_prologue(); solve_body<false>(a); }
+static __global__ void __launch_bounds__(64, 10) solve_kernel_visual(SolveArgs a) { solve_body<false>(a); }
 
 // Non-vision part of the cost at the candidate state (IMU + prior + plane), one CTA per window.
 struct CostArgs {
@@ -1003,7 +1107,6 @@ struct CostArgs {
 };
 
 static __global__ void aux_cost_kernel(CostArgs a) {
-    pdl_prologue();
     const int w = blockIdx.x + a.w0;
     const WinHdr &H = a.hdr[w];
     const WinConst &wc = a.cst[w];
@@ -1115,7 +1218,6 @@ struct JvAuxArgs {
 };  // c.loop != 0: runs only for windows whose GN step left the trust region, then picks the dogleg step (tr_after_jv)
 
 static __global__ void jv_aux_kernel(JvAuxArgs ja) {
-    pdl_prologue();
     const CostArgs &a = ja.c;
     const int w = blockIdx.x + a.w0;
     const WinHdr &H = a.hdr[w];

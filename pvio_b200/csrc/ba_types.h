@@ -105,15 +105,4 @@ struct __align__(16) LmAux {
     double pad;
 };
 
-#ifdef __CUDACC__
-// Programmatic dependent launch (latency path, api.cu: launch_k): the kernels of a single-window solve are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, so the NEXT kernel's CTAs are scheduled while this one still runs
-// (launch_dependents) and park here until this grid has completed and flushed (wait).  Every kernel of the chain waits
-// before its first global read, so the order of the data flow is the stream order.  Without the attribute both are no-ops.
-__device__ __forceinline__ void pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-#endif
-
 }  // namespace pvio

@@ -93,7 +93,6 @@ template <bool kLoss, typename real, int kWarps, int kMinBlocks, int kMode>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 update_obs_kernel(UpdArgs a) {
     constexpr int kThreads = kWarps * 32;
-    pdl_prologue();
     const int w = blockIdx.y + a.w0;
     WinCtrl &ctrl = a.ctrl[w];
     if (kMode == 1 && ctrl.done) return;
@@ -330,7 +329,6 @@ update_obs_kernel(UpdArgs a) {
 template <bool kLoss>
 __global__ void __launch_bounds__(kLinThreads, 2)
 jv_vision_kernel(UpdArgs a) {
-    pdl_prologue();
     const int w = blockIdx.y + a.w0;
     if (a.loop && (a.ctrl[w].done || a.ctrl[w].skip || !a.ctrl[w].need_jv)) return;
     const WinHdr &H = a.hdr[w];

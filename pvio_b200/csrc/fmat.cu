@@ -420,13 +420,14 @@ int fm_ransac_impl(Handle *h, int n, const float *p, const float *q, double thre
     } else if (schedule) {
         if (n_schedule < 1) return fail(h, PVIO_B200_EINVAL, "find_fundamental_mask: empty schedule");
         have = std::min(budget, n_schedule);
-        for (int i = 0; i < 7 * have; ++i) {
-            if (schedule[i] >= n || (schedule[i] < 0 && i % 7 != 0))
-                return fail(h, PVIO_B200_EINVAL, "find_fundamental_mask: schedule index out of range");
-            f->h_sched[i] = schedule[i];
+        for (int it = 0; it < have; ++it) {
+            if (schedule[7 * it] < 0) { have = it; break; }          // a row starting with -1: getSubset gave up there
+            for (int i = 0; i < 7; ++i) {
+                const int v = schedule[7 * it + i];
+                if (v < 0 || v >= n) return fail(h, PVIO_B200_EINVAL, "find_fundamental_mask: schedule index out of range");
+                f->h_sched[7 * it + i] = v;
+            }
         }
-        for (int it = 0; it < have; ++it)
-            if (f->h_sched[7 * it] < 0) { have = it; break; }       // a row of -1: getSubset gave up there
     } else {
         have = cv_schedule(p, q, n, budget, ransac ? 10000 : 1000, f->h_sched);
     }

@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || cd /root/repo
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/c3_tests.log 2>&1; echo "tests rc=$?"
+tail -12 gpurun_out/c3_tests.log
+PVIO_B200_TUNE_LIB=$PWD/tools/_variants/libpvio_stamps.so timeout 300 python tools/solve_stamps.py 2>&1 | grep -v "cfg2\|e+\|-5" | tee gpurun_out/c3_stamps.log
+timeout 300 python tools/marg_probe.py 2>&1 | tail -4
+timeout 300 python tools/cfg3_probe.py cfg4 2>&1 | tail -3
