@@ -416,7 +416,7 @@ static size_t solve_smem_one(const WinHdr &H, bool lean) {
     const size_t nb = (D + 3) / 4, Dp = nb * 4;
     const size_t np_ = (size_t)H.N * (H.N + 1) / 2;
     size_t scr = lean ? Dp + 10 * 36 + 36 : std::max<size_t>(Dp, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);
-    if (H.use_inertial) scr = std::max<size_t>(scr, 2 * (8 * 450 + 8 * 16) + 8 * 225);      // kImuRound factors: raw + whitened J, r; their W
+    if (H.use_inertial) scr = std::max<size_t>(scr, 8 * 450 + 8 * 16 + 8 * 480 + 8 * 225);      // kImuRound factors: raw J, r; whitened [J | r]; their W
     if (H.n_prior > 0) scr = std::max<size_t>(scr, 3 * 15 * (size_t)H.n_prior + 9 * (size_t)H.n_prior + 8 * 225);   // + one 15 x 15 block per warp
     return sizeof(double) * ((nb + 1) * (nb + 2) / 2 * 18 + 4 * Dp + (size_t)H.N * 36 + scr);   // tiles of kTP = 18 doubles (ba_solve.cuh)
 }
@@ -652,10 +652,11 @@ static int launch_update(Handle *h, int n, const StepCfg &c, const BatchShape &b
     return 0;
 }
 
-static int launch_aux_cost(Handle *h, int n, const StepCfg &c) {
+static int launch_aux_cost(Handle *h, int n, const StepCfg &c, const BatchShape &b) {
     cudaStream_t st = c.stream ? c.stream : h->stream;
     const CostArgs k = make_cost_args(h, c);
-    aux_cost_kernel<<<n, 64, sizeof(double) * 15 * kMaxFrames, st>>>(k);
+    // inertial windows: 8 warps share the prior's S r0 product; reprojection-only batches only need the acceptance copy
+    aux_cost_kernel<<<n, b.inertial ? 256 : 64, sizeof(double) * 2 * 15 * kMaxFrames, st>>>(k);
     ++h->launches;
     LAUNCH_CK(h, "aux_cost_kernel");
     return 0;
@@ -669,7 +670,7 @@ static int run_gn_step(Handle *h, int n, const StepCfg &c, const BatchShape &b) 
     TRY(run_solve(h, n, c, b));
     CK(h, cudaMemsetAsync(h->acc.d + (size_t)kAcc * c.w0, 0, sizeof(double) * kAcc * n, st));
     TRY(launch_update<0>(h, n, c, b, sweep_grid_x(h, n)));
-    TRY(launch_aux_cost(h, n, c));
+    TRY(launch_aux_cost(h, n, c, b));
     return 0;
 }
 
@@ -692,7 +693,7 @@ static int iteration_body(Handle *h, int n, const StepCfg &c, const BatchShape &
     }
     TRY(launch_update<2>(h, n, c, b, 1));
     TRY(launch_lin(h, n, c, b, true, false, true));      // the candidate's linearisation: its cost decides, its Jacobians stay
-    TRY(launch_aux_cost(h, n, c));
+    TRY(launch_aux_cost(h, n, c, b));
     return 0;
 }
 

@@ -75,8 +75,11 @@ __device__ __forceinline__ int tri(int i, int j) {   // element (i,j), j <= i
 
 // ---- IMU factor: raw residual and Jacobian (before whitening); J is [15][30] row-major.
 __device__ inline void imu_factor_raw(const double *fi, const double *fj, const double *rec,
-                                      const WinConst &wc, int alias_bias, double *r, double *J) {
+                                      const WinConst &wc, int alias_bias, double *r, double *J,
+                                      const double *bias0 = nullptr) {
     // J == nullptr: residual only (candidate-cost evaluations)
+    // bias0 (bg, ba: 6 doubles): the bias linearisation point to use instead of the record's (candidate cost under Q1:
+    // the CURRENT state's biases while fi is the candidate)
     const double g[3] = {0.0, 0.0, -9.80665};                 // preintegration_error_cost.h:41
     if (J) for (int i = 0; i < 450; ++i) J[i] = 0.0;
     const double *qic = fi, *pic = fi + 4, *vi = fi + 7, *bgi = fi + 10, *bai = fi + 13;
@@ -86,8 +89,8 @@ __device__ inline void imu_factor_raw(const double *fi, const double *fj, const 
     const double *dq_dbg = rec + 236, *dp_dbg = rec + 245, *dp_dba = rec + 254, *dv_dbg = rec + 263, *dv_dba = rec + 272;
     double dbg[3], dba[3];
     for (int k = 0; k < 3; ++k) {
-        dbg[k] = alias_bias ? 0.0 : bgi[k] - rec[281 + k];    // :69-70 (Q1: bg_i_0 aliases the parameter)
-        dba[k] = alias_bias ? 0.0 : bai[k] - rec[284 + k];
+        dbg[k] = alias_bias ? 0.0 : bgi[k] - (bias0 ? bias0[k] : rec[281 + k]);    // :69-70 (Q1: bg_i_0 aliases the parameter)
+        dba[k] = alias_bias ? 0.0 : bai[k] - (bias0 ? bias0[3 + k] : rec[284 + k]);
     }
     double qi[4], qj[4], Rci[9], Rcj[9], t3[3], pi[3], pj[3];
     quat_mul(qic, wc.imu_q, qi);                                // :60
@@ -474,6 +477,7 @@ __device__ inline bool chol_solve_tiled(double *A, double *x, int nb, int *flag_
 
 constexpr int kSolveImuSlab = 15 * 30 + 16;     // raw J + r per factor
 constexpr int kImuRound = 8;                    // IMU factors linearised concurrently by solve_kernel
+constexpr int kImuJx = 15 * 32;                 // whitened Jacobian + residual column of one factor, row pitch 32
 
 #ifdef PVIO_SOLVE_STAMPS          // tuning builds of tools/ only: clock64() at the phase boundaries of solve_kernel
 __device__ long long g_solve_stamps[16];
@@ -689,11 +693,11 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             const int nb = min(kImuRound, H.n_imu - n0);
             double *Jraw = scr;                              // [R][450], r at [R*450 + n*16]
             double *rraw = scr + kImuRound * 450;
-            double *Jw = rraw + kImuRound * 16;              // [R][450]
-            double *rw = Jw + kImuRound * 450;               // [R][16]
-            double *Wsm = rw + kImuRound * 16;               // [R][225] sqrt information matrices of the round
+            double *Jx = rraw + kImuRound * 16;              // [R][15][32] whitened [J | r | 0]
+            double *Wsm = Jx + kImuRound * kImuJx;           // [R][225] sqrt information matrices of the round
             __shared__ int imu_fr[2 * kImuRound];            // frame pair of each factor of the round (read in every inner loop)
             __shared__ int imu_chain;
+            __shared__ double imu_cost[kImuRound];           // r^T r of each factor of the round
             if (tid >= 32 && tid < 32 + 2 * nb) imu_fr[tid - 32] = idx[2 * n0 + tid - 32];
             if (tid < nb) {
                 const int n = n0 + tid;
@@ -708,18 +712,24 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             }
             __syncthreads();
             SOLVE_STAMP(2);
-            // whiten: Jw = W J, rw = W r                      :157 and the "sqrt_inv_cov *" lines
-            for (int e = tid; e < nb * 15 * 31; e += nt) {
-                const int n = e / (15 * 31), rem = e - n * 15 * 31, row = rem / 31, col = rem - row * 31;
-                const double *Wm = Wsm + n * 225 + row * 15;
-                double s = 0.0;
-                if (col < 30) { for (int k = 0; k < 15; ++k) s += Wm[k] * Jraw[n * 450 + k * 30 + col]; Jw[n * 450 + row * 30 + col] = s; }
-                else { for (int k = 0; k < 15; ++k) s += Wm[k] * rraw[n * 16 + k]; rw[n * 16 + row] = s; }
+            // whiten: Jx = [W J | W r | 0] (15 x 32 per factor)      :157 and the "sqrt_inv_cov *" lines
+            // One thread per COLUMN of a factor: the raw column sits in registers, the rows of W are broadcast loads --
+            // one shared-memory load per multiply-add instead of two (the entry-per-thread form was shared-memory bound).
+            for (int e = tid; e < nb * 32; e += nt) {
+                const int n = e >> 5, col = e & 31;
+                double *out = Jx + n * kImuJx + col;
+                if (col == 31) { for (int row = 0; row < 15; ++row) out[row * 32] = 0.0; continue; }
+                double cv[15];
+#pragma unroll
+                for (int k = 0; k < 15; ++k) cv[k] = col < 30 ? Jraw[n * 450 + k * 30 + col] : rraw[n * 16 + k];
+                const double *Wm = Wsm + n * 225;
+                for (int row = 0; row < 15; ++row) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 15; ++k) s += Wm[row * 15 + k] * cv[k];
+                    out[row * 32] = s;
+                }
             }
-            __syncthreads();
-            // accumulate.  Two factors touch the same entries of the system only if they share a frame; the reference's
-            // factors form a chain (frame n, n + 1), so the factors at even positions of the round go first, all at once,
-            // then the odd ones.  A round whose factors are not such a chain falls back to one factor at a time.
             if (tid == 0) {
                 bool ch = true;                              // no two factors of equal parity share a frame
                 for (int n = 0; n < nb && ch; ++n)
@@ -730,35 +740,67 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
                 imu_chain = ch ? 1 : 0;
             }
             __syncthreads();
+            // accumulate Jx^T Jx: rows / columns 0..29 are the 30 x 30 block of the system, row 30 the gradient, entry
+            // (30, 30) twice the cost.  One thread per 4 x 4 tile of the lower triangle (36 tiles per factor), 15 steps of
+            // 2 x 4 loaded values for 16 multiply-adds.  Two factors touch the same entries of the system only if they
+            // share a frame; the reference's factors form a chain (frame n, n + 1), so the factors at even positions of
+            // the round go first, all at once, then the odd ones.  Any other round: one factor at a time.
             const bool chain = imu_chain != 0;
             const int phases = chain ? 2 : nb;
             for (int ph = 0; ph < phases; ++ph) {
                 const int first = ph, step = chain ? 2 : nb, cnt = chain ? (nb - ph + 1) / 2 : 1;
-                for (int e = tid; e < cnt * 30 * 31; e += nt) {
-                    const int q = e / (30 * 31), rem = e - q * 30 * 31;
+                for (int e = tid; e < cnt * 36; e += nt) {
+                    const int q = e / 36, t = e - q * 36;
                     const int n = first + q * step;
+                    int tr = 0;
+                    while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
+                    const int tc = t - tr * (tr + 1) / 2;    // tile (tr, tc), tc <= tr < 8
+                    const double *Jn = Jx + n * kImuJx;
+                    double acc[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 5
+                    for (int k = 0; k < 15; ++k) {
+                        const double2 a0 = *reinterpret_cast<const double2 *>(Jn + k * 32 + 4 * tr);
+                        const double2 a1 = *reinterpret_cast<const double2 *>(Jn + k * 32 + 4 * tr + 2);
+                        const double2 b0 = *reinterpret_cast<const double2 *>(Jn + k * 32 + 4 * tc);
+                        const double2 b1 = *reinterpret_cast<const double2 *>(Jn + k * 32 + 4 * tc + 2);
+                        const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+                    }
                     const int fi = imu_fr[2 * n], fj = imu_fr[2 * n + 1];
-                    const int ra = rem / 31, cb_ = rem - ra * 31;
-                    const int ga = (ra < 15 ? fi * 15 + ra : fj * 15 + ra - 15);
-                    double s = 0.0;
-                    if (cb_ < 30) {
-                        const int gb = (cb_ < 15 ? fi * 15 + cb_ : fj * 15 + cb_ - 15);
-                        if (gb > ga) continue;
-                        for (int k = 0; k < 15; ++k) s += Jw[n * 450 + k * 30 + ra] * Jw[n * 450 + k * 30 + cb_];
-                        A[tri(ga, gb)] += s;
-                    } else {
-                        for (int k = 0; k < 15; ++k) s += Jw[n * 450 + k * 30 + ra] * rw[n * 16 + k];
-                        g[ga] += s; gu[ga] += s;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int ra = 4 * tr + i;
+                        if (ra > 30) continue;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int cb_ = 4 * tc + j;
+                            if (cb_ > ra || cb_ > 30) continue;          // the lower triangle of the 31 x 31 product, once
+                            const double v = acc[i][j];
+                            if (ra == 30) {
+                                if (cb_ == 30) imu_cost[n] = v;
+                                else { const int gb = (cb_ < 15 ? fi * 15 + cb_ : fj * 15 + cb_ - 15); g[gb] += v; gu[gb] += v; }
+                            } else {
+                                const int ga = (ra < 15 ? fi * 15 + ra : fj * 15 + ra - 15);
+                                const int gb = (cb_ < 15 ? fi * 15 + cb_ : fj * 15 + cb_ - 15);
+                                A[ga >= gb ? tri(ga, gb) : tri(gb, ga)] += v;
+                            }
+                        }
                     }
                 }
                 __syncthreads();
             }
-            if (tid == 0) {
+            if (tid == 0) {                                  // in factor order: the cost does not depend on the schedule
                 double c = 0.0;
-                for (int n = 0; n < nb; ++n) for (int k = 0; k < 15; ++k) c += rw[n * 16 + k] * rw[n * 16 + k];
+                for (int n = 0; n < nb; ++n) c += imu_cost[n];
                 cost_sm[1] += 0.5 * c;
             }
-            __syncthreads();
         }
     }
 
@@ -1124,44 +1166,69 @@ static __global__ void aux_cost_kernel(CostArgs a) {
     if (H.use_inertial) {
         const int32_t *idx = a.imu_idx + (size_t)w * a.Ncap * 2;
         const double *recs = a.imu_data + (size_t)w * a.Ncap * kImuStride;
+        __shared__ double imu_c[kMaxFrames];
+        const int n_pr = H.n_prior, d = 15 * n_pr, dcap = 15 * a.Ncap;
+        const int32_t *pf = a.prior_frames + (size_t)w * a.Ncap;
+        const double *x0 = a.prior_x0 + (size_t)w * a.Ncap * kFrameStride;
+        double *rc = r0 + 15 * kMaxFrames;                    // [d] squared whitened prior residuals
         for (int n = tid; n < H.n_imu; n += nt) {
-            // residual only: reuse the raw evaluator (Jacobian discarded)
+            // residual only: the raw evaluator without Jacobian.  Q1 (alias_bias): the bias linearisation point is the
+            // CURRENT (accepted) bias of frame i while the state is the candidate
             double r[15];
-            double rec_local[kImuStride];
             const double *rec = recs + (size_t)n * kImuStride;
-            for (int k = 0; k < kImuStride; ++k) rec_local[k] = rec[k];
-            if (a.alias_bias) {   // Q1: the linearisation point is the CURRENT (accepted) bias of frame i
-                for (int k = 0; k < 3; ++k) {
-                    rec_local[281 + k] = fcur[idx[2 * n] * kFrameStride + 10 + k];
-                    rec_local[284 + k] = fcur[idx[2 * n] * kFrameStride + 13 + k];
-                }
-            }
-            imu_factor_raw(fc + idx[2 * n] * kFrameStride, fc + idx[2 * n + 1] * kFrameStride, rec_local, wc, 0, r, nullptr);
+            imu_factor_raw(fc + idx[2 * n] * kFrameStride, fc + idx[2 * n + 1] * kFrameStride, rec, wc, 0, r, nullptr,
+                           a.alias_bias ? fcur + idx[2 * n] * kFrameStride + 10 : nullptr);
             double c = 0.0;
             for (int i = 0; i < 15; ++i) {
                 double s = 0.0;
-                for (int k = 0; k < 15; ++k) s += rec[11 + i * 15 + k] * r[k];
+#pragma unroll
+                for (int k = 0; k < 15; ++k) s += __ldg(rec + 11 + i * 15 + k) * r[k];
                 c += s * s;
             }
-            atomicAdd(&acc, 0.5 * c);
+            imu_c[n] = c;
         }
-        if (H.n_prior > 0) {
-            const int n = H.n_prior, d = 15 * n, dcap = 15 * a.Ncap;
-            const int32_t *pf = a.prior_frames + (size_t)w * a.Ncap;
+        {   // the prior's raw residuals meanwhile on the second warp (a CTA of one warp: after the IMU factors)
+            const int pt = nt > 32 ? tid - 32 : tid;
+            double Ji[9];
+            if (pt >= 0 && pt < n_pr) prior_frame_raw(fc + pf[pt] * kFrameStride, x0 + pt * kFrameStride, r0 + 15 * pt, Ji);
+        }
+        __syncthreads();
+        if (n_pr > 0) {
             const double *S = a.prior_S + (size_t)w * dcap * dcap;
             const double *ev = a.prior_e + (size_t)w * dcap;
-            const double *x0 = a.prior_x0 + (size_t)w * a.Ncap * kFrameStride;
-            double Ji[9];
-            if (tid < n) prior_frame_raw(fc + pf[tid] * kFrameStride, x0 + tid * kFrameStride, r0 + 15 * tid, Ji);
-            __syncthreads();
-            double c = 0.0;
-            for (int i = tid; i < d; i += nt) {
-                double s = ev[i];
-                for (int k = 0; k < d; ++k) s += S[(size_t)i * d + k] * r0[k];
-                c += s * s;
+            // r = S r0 + e, warp per row, kRows rows per pass with all their loads in flight (S sits in L2)
+            constexpr int kRows = 5;
+            for (int i0 = (tid >> 5) * kRows; i0 < d; i0 += (nt >> 5) * kRows) {
+                double sr[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) sr[r] = 0.0;
+#pragma unroll 2
+                for (int k = tid & 31; k < d; k += 32) {
+                    double sv[kRows];
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) sv[r] = i0 + r < d ? __ldg(S + (size_t)(i0 + r) * d + k) : 0.0;
+                    const double rk = r0[k];
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) sr[r] += sv[r] * rk;
+                }
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) {
+                    double sx = sr[r];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, off);
+                    if ((tid & 31) == 0 && i0 + r < d) { const double v = ev[i0 + r] + sx; rc[i0 + r] = v * v; }
+                }
             }
-            atomicAdd(&acc, 0.5 * c);
+            __syncthreads();
         }
+        if (tid == 0) {                                        // fixed summation order: the cost is reproducible
+            double c = 0.0;
+            for (int n = 0; n < H.n_imu; ++n) c += imu_c[n];
+            double cp = 0.0;
+            for (int i = 0; i < d; ++i) cp += rc[i];
+            acc += 0.5 * c + 0.5 * cp;
+        }
+        __syncthreads();
     }
     if (H.n_ptracks > 0) {
         const double *pl = a.plane_param + (size_t)w * a.Pcap * 4;

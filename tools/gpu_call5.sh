@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || cd /root/repo
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_ba.py -m gpu -q -x > gpurun_out/c5_tests.log 2>&1; echo "tests rc=$?"
+tail -12 gpurun_out/c5_tests.log
+PVIO_B200_TUNE_LIB=$PWD/tools/_variants/libpvio_stamps.so timeout 300 python tools/solve_stamps.py 2>&1 | grep -v "e+\|-5\|-6" | tee gpurun_out/c5_stamps.log
+timeout 300 python tools/cfg3_probe.py cfg4 2>&1 | tail -3
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/c5_cfg3_launches.csv python tools/cfg3_probe.py > /dev/null 2>&1
+echo "ncu rc=$?"
