@@ -320,6 +320,18 @@ __device__ inline void plane_factor(int K, const int32_t *fr, const float *z, co
     }
 }
 
+#ifdef PVIO_SOLVE_STAMPS          // tuning builds of tools/ only: clock64() at the phase boundaries of solve_kernel
+__device__ long long g_solve_stamps[16];
+#define SOLVE_STAMP(k) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) g_solve_stamps[k] = clock64(); } while (0)
+#define CHOL_T0() long long ct__ = clock64()
+#define CHOL_ACC(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long n__ = clock64(); g_solve_stamps[k] += n__ - ct__; ct__ = n__; } } while (0)
+#else
+#define SOLVE_STAMP(k) do { } while (0)
+#define CHOL_T0() do { } while (0)
+#define CHOL_ACC(k) do { } while (0)
+#endif
+
+
 // Tiled dense Cholesky A = L L^T + solve, all threads of the CTA, fp64, in shared memory.
 // nb block rows of 4 (padding rows carry an identity diagonal).  The right-hand side is block row
 // nb of the packed tile array (row 0 of its tiles), so the panel / trailing phases carry out the
@@ -381,75 +393,10 @@ __device__ __forceinline__ void tri_unrank(int e, int &ii, int &jj) {
     jj = e - ii * (ii + 1) / 2;
 }
 
-template <bool kPerTile>
-__device__ inline bool chol_solve_tiled(double *A, double *x, int nb, int *flag_sm) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    double *R = A + tile_off(nb, 0);                       // rhs block row: tiles (nb, J), row 0 used
-    for (int i = tid; i < nb * kTP; i += nt) { const int J = i / kTP, o = i - J * kTP; R[i] = (o < 4) ? x[J * 4 + o] : 0.0; }
-    if (tid == 0) *flag_sm = 1;
-    __syncthreads();
-    if (tid == 0) chol_factor4(A + tile_off(0, 0), flag_sm);
-    __syncthreads();
-    for (int kb = 0; kb < nb; ++kb) {
-        if (*flag_sm == 0) break;                      // uniform
-        // (b) panel tiles incl. the rhs block row (I = nb): X <- X * Linv^T, one thread per tile ROW
-        for (int e = tid; e < (nb - kb) * 4; e += nt) {
-            const int I = kb + 1 + (e >> 2), r = e & 3;
-            if (I == nb && r != 0) continue;           // only row 0 of the rhs tiles carries data
-            double *X = A + tile_off(I, kb) + r * 4;
-            const double *Li = A + tile_off(kb, kb);
-            const double x0 = X[0], x1 = X[1], x2 = X[2], x3 = X[3];
-            X[0] = x0 * Li[0];
-            X[1] = x0 * Li[4] + x1 * Li[5];
-            X[2] = x0 * Li[8] + x1 * Li[9] + x2 * Li[10];
-            X[3] = x0 * Li[12] + x1 * Li[13] + x2 * Li[14] + x3 * Li[15];
-        }
-        __syncthreads();
-        // (c) trailing tiles (I,J), kb < J <= I < nb, plus the rhs row (I = nb, kb < J < nb); tile 0 is the next diagonal tile
-        const int n = nb - kb - 1, ntile = n * (n + 1) / 2;
-        if (kPerTile) {
-            for (int e = tid; e < ntile + n; e += nt) {
-                int I, J;
-                if (e < ntile) { int ii, jj; tri_unrank(e, ii, jj); I = kb + 1 + ii; J = kb + 1 + jj; }
-                else { I = nb; J = kb + 1 + (e - ntile); }
-                const double *P = A + tile_off(I, kb), *Q = A + tile_off(J, kb);
-                double *C = A + tile_off(I, J);
-                double q[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) q[k] = Q[k];
-                const int rows = (I == nb) ? 1 : 4;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    if (r >= rows) break;
-                    const double p0 = P[r * 4], p1 = P[r * 4 + 1], p2 = P[r * 4 + 2], p3 = P[r * 4 + 3];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) C[r * 4 + c] -= p0 * q[c * 4] + p1 * q[c * 4 + 1] + p2 * q[c * 4 + 2] + p3 * q[c * 4 + 3];
-                }
-                if (e == 0) chol_factor4(C, flag_sm);     // look-ahead: tile (kb+1, kb+1) is complete
-            }
-        } else {
-            for (int e4 = tid; e4 < (ntile + n) * 4; e4 += nt) {
-                const int e = e4 >> 2, r = e4 & 3;
-                int I, J;
-                if (e < ntile) { int ii, jj; tri_unrank(e, ii, jj); I = kb + 1 + ii; J = kb + 1 + jj; }
-                else { I = nb; J = kb + 1 + (e - ntile); }
-                if (!(I == nb && r != 0)) {
-                    const double *P = A + tile_off(I, kb) + r * 4, *Q = A + tile_off(J, kb);
-                    double *C = A + tile_off(I, J) + r * 4;
-                    const double p0 = P[0], p1 = P[1], p2 = P[2], p3 = P[3];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) C[c] -= p0 * Q[c * 4] + p1 * Q[c * 4 + 1] + p2 * Q[c * 4 + 2] + p3 * Q[c * 4 + 3];
-                }
-                if (e4 < 4 && n > 0) {                 // threads 0..3 hold the four rows of tile (kb+1, kb+1): look-ahead
-                    __syncwarp(0xFu);
-                    if (e4 == 0) chol_factor4(A + tile_off(kb + 1, kb + 1), flag_sm);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (*flag_sm == 0) return false;
-    // y = L^-1 b now sits in row 0 of the rhs tiles; back substitution x = L^-T y on warp 0
+// back substitution x = L^-T y on warp 0 (y: row 0 of the rhs tiles; the diagonal tiles hold the inverse factors)
+__device__ __forceinline__ void chol_back_substitute(double *A, double *x, int nb) {
+    const int tid = threadIdx.x;
+    const double *R = A + tile_off(nb, 0);
     if (tid < 32) {
         for (int i = tid; i < nb * 4; i += 32) x[i] = R[(i >> 2) * kTP + (i & 3)];
         __syncwarp();
@@ -471,6 +418,238 @@ __device__ inline bool chol_solve_tiled(double *A, double *x, int nb, int *flag_
             __syncwarp();
         }
     }
+}
+
+template <bool kPerTile>
+__device__ inline bool chol_solve_tiled(double *A, double *x, int nb, int *flag_sm) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double *R = A + tile_off(nb, 0);                       // rhs block row: tiles (nb, J), row 0 used
+    for (int i = tid; i < nb * kTP; i += nt) { const int J = i / kTP, o = i - J * kTP; R[i] = (o < 4) ? x[J * 4 + o] : 0.0; }
+    if (tid == 0) *flag_sm = 1;
+    __syncthreads();
+    if (tid == 0) chol_factor4(A + tile_off(0, 0), flag_sm);
+    __syncthreads();
+#ifdef PVIO_SOLVE_STAMPS
+    if (tid == 0 && blockIdx.x == 0) for (int k = 10; k < 16; ++k) g_solve_stamps[k] = 0;
+#endif
+    CHOL_T0();
+    for (int kb = 0; kb < nb; ++kb) {
+        if (*flag_sm == 0) break;                      // uniform
+        // (b) panel tiles incl. the rhs block row (I = nb): X <- X * Linv^T, one thread per tile ROW
+        for (int e = tid; e < (nb - kb) * 4; e += nt) {
+            const int I = kb + 1 + (e >> 2), r = e & 3;
+            if (I == nb && r != 0) continue;           // only row 0 of the rhs tiles carries data
+            double *X = A + tile_off(I, kb) + r * 4;
+            const double *Li = A + tile_off(kb, kb);
+            const double x0 = X[0], x1 = X[1], x2 = X[2], x3 = X[3];
+            X[0] = x0 * Li[0];
+            X[1] = x0 * Li[4] + x1 * Li[5];
+            X[2] = x0 * Li[8] + x1 * Li[9] + x2 * Li[10];
+            X[3] = x0 * Li[12] + x1 * Li[13] + x2 * Li[14] + x3 * Li[15];
+        }
+        CHOL_ACC(10);
+        __syncthreads();
+        CHOL_ACC(11);
+        // (c) trailing tiles (I,J), kb < J <= I < nb, plus the rhs row (I = nb, kb < J < nb); tile 0 is the next diagonal tile
+        const int n = nb - kb - 1, ntile = n * (n + 1) / 2;
+        if (kPerTile) {
+            for (int e = tid; e < ntile + n; e += nt) {
+                int I, J;
+                if (e < ntile) { int ii, jj; tri_unrank(e, ii, jj); I = kb + 1 + ii; J = kb + 1 + jj; }
+                else { I = nb; J = kb + 1 + (e - ntile); }
+                const double *P = A + tile_off(I, kb), *Q = A + tile_off(J, kb);
+                double *C = A + tile_off(I, J);
+                double q[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) q[k] = Q[k];
+                const int rows = (I == nb) ? 1 : 4;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (r >= rows) break;
+                    const double p0 = P[r * 4], p1 = P[r * 4 + 1], p2 = P[r * 4 + 2], p3 = P[r * 4 + 3];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) C[r * 4 + c] -= p0 * q[c * 4] + p1 * q[c * 4 + 1] + p2 * q[c * 4 + 2] + p3 * q[c * 4 + 3];
+                }
+                if (e == 0) { CHOL_ACC(12); chol_factor4(C, flag_sm); CHOL_ACC(13); }     // look-ahead: tile (kb+1, kb+1) is complete
+            }
+        } else {
+            for (int e4 = tid; e4 < (ntile + n) * 4; e4 += nt) {
+                const int e = e4 >> 2, r = e4 & 3;
+                int I, J;
+                if (e < ntile) { int ii, jj; tri_unrank(e, ii, jj); I = kb + 1 + ii; J = kb + 1 + jj; }
+                else { I = nb; J = kb + 1 + (e - ntile); }
+                if (!(I == nb && r != 0)) {
+                    const double *P = A + tile_off(I, kb) + r * 4, *Q = A + tile_off(J, kb);
+                    double *C = A + tile_off(I, J) + r * 4;
+                    const double p0 = P[0], p1 = P[1], p2 = P[2], p3 = P[3];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) C[c] -= p0 * Q[c * 4] + p1 * Q[c * 4 + 1] + p2 * Q[c * 4 + 2] + p3 * Q[c * 4 + 3];
+                }
+                if (e4 < 4 && n > 0) {                 // threads 0..3 hold the four rows of tile (kb+1, kb+1): look-ahead
+                    __syncwarp(0xFu);
+                    if (e4 == 0) chol_factor4(A + tile_off(kb + 1, kb + 1), flag_sm);
+                }
+            }
+        }
+        CHOL_ACC(14);
+        __syncthreads();
+        CHOL_ACC(15);
+    }
+    if (*flag_sm == 0) return false;
+    // y = L^-1 b now sits in row 0 of the rhs tiles; back substitution x = L^-T y on warp 0
+    chol_back_substitute(A, x, nb);
+    __syncthreads();
+    return true;
+}
+
+// diagonal tile C -= L L^T with L = the panel tile (J, k) of its own block row: one tile load, the lower triangle only
+// (the strict upper triangle of a diagonal tile is never read: chol_factor4 uses L[r][c], c <= r)
+__device__ __forceinline__ void chol_diag_update(double (&c)[16], const double *Lt) {
+    const double2 *P2 = reinterpret_cast<const double2 *>(Lt);
+    double q[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const double2 v = P2[k]; q[2 * k] = v.x; q[2 * k + 1] = v.y; }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int cc = 0; cc <= r; ++cc)
+            c[r * 4 + cc] -= q[r * 4] * q[cc * 4] + q[r * 4 + 1] * q[cc * 4 + 1] + q[r * 4 + 2] * q[cc * 4 + 2] + q[r * 4 + 3] * q[cc * 4 + 3];
+}
+
+// The same factorisation with the TRAILING MATRIX IN REGISTERS and the critical path on a warp of its own (wide CTA of
+// 8 warps, the inertial single window: D = 135 ... 165).  What bounded chol_solve_tiled (profiles/r02j): each block
+// column is a serial chain -- update of the next diagonal tile, its 4 x 4 factorisation + inverse by ONE thread (~750
+// cycles of dependent fp64 rsqrt / multiply-adds) -- and the warp that held that thread also had its share of trailing
+// tiles to do before or after, so the other warps waited ~3.4 K cycles per block column at the barrier.  Here
+//   warp 0        owns the DIAGONAL tiles (lane l: tiles l and l + 32), nothing else: per block column it updates the
+//                 next diagonal tile, one lane factors it, then the lanes update their remaining diagonal tiles;
+//   warps 1..7    own the off-diagonal tiles and the rhs row (tile e = t + s * 224 by descending column, up to kSlots
+//                 per thread) IN REGISTERS for the whole factorisation: a block column costs a tile two 128-byte panel
+//                 tiles read from shared memory and no write (chol_solve_tiled: 512 B per tile and step).
+// Shared memory holds what others need: the inverse factor of each diagonal tile and the finished panel tiles L_Ik
+// (also what the back substitution reads).  Per block column: panel tiles X <- X L_kk^-T by their owners (barrier),
+// trailing update C -= L_Ik L_Jk^T (barrier).
+template <int kSlots>
+__device__ inline bool chol_solve_regs(double *A, double *x, int nb, int *flag_sm) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int ntask = nb * (nb + 1) / 2, nown = nt - 32;      // off-diagonal tiles + the rhs row
+    double *R = A + tile_off(nb, 0);                       // rhs block row: tiles (nb, J), row 0 used
+    for (int i = tid; i < nb * kTP; i += nt) { const int J = i / kTP, o = i - J * kTP; R[i] = (o < 4) ? x[J * 4 + o] : 0.0; }
+    if (tid == 0) *flag_sm = 1;
+    __syncthreads();
+    int tI[kSlots], tJ[kSlots];
+    double c[kSlots][16];
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+        tI[s] = -1; tJ[s] = -1;
+        if (warp == 0) {
+            if (s < 2 && lane + 32 * s < nb) tI[s] = tJ[s] = lane + 32 * s;
+        } else {
+            // columns in DESCENDING order (column J: its nb - 1 - J off-diagonal tiles, then its rhs tile): the tiles still
+            // active at block column kb (J > kb) are the first ones of this order, i.e. they sit in the lowest slots of
+            // all threads -- a warp executes as many tile bodies per block column as slots are still alive, not kSlots --
+            // and the panel tiles of one column are neighbours (one or two warps, one slot)
+            const int e = tid - 32 + s * nown;
+            if (e < ntask) { int ii, jj; tri_unrank(e, ii, jj); tJ[s] = nb - 1 - ii; tI[s] = tJ[s] + 1 + jj; }
+        }
+        if (tI[s] >= 0) {
+            const double2 *src = reinterpret_cast<const double2 *>(A + tile_off(tI[s], tJ[s]));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const double2 v = src[k]; c[s][2 * k] = v.x; c[s][2 * k + 1] = v.y; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) c[s][k] = 0.0;
+        }
+    }
+    if (tid == 0) chol_factor4(A + tile_off(0, 0), flag_sm);      // tile (0, 0) is still intact in shared memory
+    __syncthreads();
+#ifdef PVIO_SOLVE_STAMPS
+    if (tid == 0 && blockIdx.x == 0) for (int k = 10; k < 16; ++k) g_solve_stamps[k] = 0;
+    long long ct__ = clock64();
+#define RSTAMP(t, k) do { if (threadIdx.x == (t) && blockIdx.x == 0) { const long long n__ = clock64(); g_solve_stamps[k] += n__ - ct__; ct__ = n__; } } while (0)
+#else
+#define RSTAMP(t, k) do { } while (0)
+#endif
+    for (int kb = 0; kb < nb; ++kb) {
+        if (*flag_sm == 0) break;                      // uniform
+        // panel: owners of the tiles (I, kb), I > kb, incl. the rhs row.  Warp 0 has no panel tiles: it catches up on the
+        // diagonal tiles of its OTHER slot with the previous block column (off the critical path: nobody waits for them yet)
+        if (warp != 0) {
+            const double *Li = A + tile_off(kb, kb);
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                if (tJ[s] != kb) continue;             // (tI > kb for every off-diagonal tile of column kb)
+                const int rows = (tI[s] == nb) ? 1 : 4;
+                double *X = A + tile_off(tI[s], kb);
+                const double l0 = Li[0], l4 = Li[4], l5 = Li[5], l8 = Li[8], l9 = Li[9], l10 = Li[10], l12 = Li[12], l13 = Li[13],
+                             l14 = Li[14], l15 = Li[15];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (r >= rows) break;
+                    const double x0 = c[s][r * 4], x1 = c[s][r * 4 + 1], x2 = c[s][r * 4 + 2], x3 = c[s][r * 4 + 3];
+                    double2 o0, o1;
+                    o0.x = x0 * l0;
+                    o0.y = x0 * l4 + x1 * l5;
+                    o1.x = x0 * l8 + x1 * l9 + x2 * l10;
+                    o1.y = x0 * l12 + x1 * l13 + x2 * l14 + x3 * l15;
+                    reinterpret_cast<double2 *>(X + r * 4)[0] = o0;
+                    reinterpret_cast<double2 *>(X + r * 4)[1] = o1;
+                }
+            }
+        } else if (kb > 0) {
+            const int sdp = kb >> 5;                   // the slot that took block column kb - 1 in the look-ahead pass
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+                if (s != sdp && tJ[s] > kb - 1) chol_diag_update(c[s], A + tile_off(tJ[s], kb - 1));
+        }
+        RSTAMP(32, 12);
+        __syncthreads();
+        RSTAMP(32, 13); RSTAMP(0, 10);
+        if (warp == 0) {
+            // look-ahead: the slot of the next diagonal tile takes block column kb now, its lane factors tile (kb + 1, kb + 1)
+            const int sd = (kb + 1) >> 5;              // uniform
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s != sd) continue;
+                if (tJ[s] > kb) chol_diag_update(c[s], A + tile_off(tJ[s], kb));
+                if (tJ[s] == kb + 1) {
+                    double2 *dst = reinterpret_cast<double2 *>(A + tile_off(kb + 1, kb + 1));
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { double2 v; v.x = c[s][2 * k]; v.y = c[s][2 * k + 1]; dst[k] = v; }
+                    chol_factor4(A + tile_off(kb + 1, kb + 1), flag_sm);
+                }
+            }
+        } else {
+            // trailing update of the owned off-diagonal / rhs tiles (I, J), kb < J < I
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                if (tJ[s] <= kb) continue;
+                const double2 *P2 = reinterpret_cast<const double2 *>(A + tile_off(tI[s], kb));
+                const double2 *Q2 = reinterpret_cast<const double2 *>(A + tile_off(tJ[s], kb));
+                double q[16];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const double2 v = Q2[k]; q[2 * k] = v.x; q[2 * k + 1] = v.y; }
+                const int rows = (tI[s] == nb) ? 1 : 4;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (r >= rows) break;
+                    const double2 pa = P2[2 * r], pb = P2[2 * r + 1];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+                        c[s][r * 4 + cc] -= pa.x * q[cc * 4] + pa.y * q[cc * 4 + 1] + pb.x * q[cc * 4 + 2] + pb.y * q[cc * 4 + 3];
+                }
+            }
+        }
+        RSTAMP(32, 14); RSTAMP(0, 11);
+        __syncthreads();
+        RSTAMP(32, 15);
+#ifdef PVIO_SOLVE_STAMPS
+        if (threadIdx.x == 0) ct__ = clock64();
+#endif
+    }
+    if (*flag_sm == 0) return false;
+    // y = L^-1 b now sits in row 0 of the rhs tiles; back substitution x = L^-T y on warp 0
+    chol_back_substitute(A, x, nb);
     __syncthreads();
     return true;
 }
@@ -478,13 +657,6 @@ __device__ inline bool chol_solve_tiled(double *A, double *x, int nb, int *flag_
 constexpr int kSolveImuSlab = 15 * 30 + 16;     // raw J + r per factor
 constexpr int kImuRound = 8;                    // IMU factors linearised concurrently by solve_kernel
 constexpr int kImuJx = 15 * 32;                 // whitened Jacobian + residual column of one factor, row pitch 32
-
-#ifdef PVIO_SOLVE_STAMPS          // tuning builds of tools/ only: clock64() at the phase boundaries of solve_kernel
-__device__ long long g_solve_stamps[16];
-#define SOLVE_STAMP(k) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) g_solve_stamps[k] = clock64(); } while (0)
-#else
-#define SOLVE_STAMP(k) do { } while (0)
-#endif
 
 template <bool kFull>
 static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
@@ -1039,7 +1211,12 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     }
     __syncthreads();
     SOLVE_STAMP(7);
-    const bool ok = chol_solve_tiled<kFull>(A, xs, nb, &flag_sm);
+    // wide CTA (8 warps) and a system whose off-diagonal tiles fit into 4 (5) register slots per thread of warps 1..7,
+    // its diagonal into the 64 slots of warp 0: the register-resident factorisation
+    const int n_off = nb * (nb - 1) / 2 + nb;
+    const bool ok = (kFull && nt == 256 && nb <= 64 && n_off <= 4 * 224) ? chol_solve_regs<4>(A, xs, nb, &flag_sm)
+                  : (kFull && nt == 256 && nb <= 64 && n_off <= 5 * 224) ? chol_solve_regs<5>(A, xs, nb, &flag_sm)
+                                                                         : chol_solve_tiled<kFull>(A, xs, nb, &flag_sm);
     SOLVE_STAMP(8);
 
     // ---- outputs

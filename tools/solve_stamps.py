@@ -23,5 +23,8 @@ for name, maker in (("cfg3", synth.make_cfg3), ("cfg4", synth.make_cfg4), ("cfg2
     d = np.diff(st[:10])
     print(name, "total cycles", int(st[9] - st[0]), "=", round((st[9] - st[0]) / 1.965e3, 1), "us at 1.965 GHz")
     for n, v in zip(NAMES[1:], d):
-        print(f"   {n:26s} {int(v):8d} cycles  {v / 1.965e3:7.1f} us")
+        if abs(v) < 1e8:
+            print(f"   {n:26s} {int(v):8d} cycles  {v / 1.965e3:7.1f} us")
+    print("   cholesky, summed over block columns: thread 0 (diagonal warp): wait for the panel", st[10], "diag update + factor + rest", st[11],
+          "| thread 32: panel", st[12], "barrier", st[13], "trailing", st[14], "barrier", st[15])
     ba.close()
