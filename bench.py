@@ -354,11 +354,21 @@ def run_gpu(args):
         try:
             w3, s3, _ = maker()
             b3 = BundleAdjustor(device=local_rank, max_windows=1, max_frames=w3.N, max_landmarks=320, max_obs=2560)
-            ts, (_, sm3) = time_call(lambda: b3.solve(w3, s3, max_iterations=10), 50, warm=3)
-            worst = max(time_call(lambda: b3.solve(w3, s3, max_iterations=10), 1, warm=0)[0] for _ in range(50))
+            for _ in range(3):
+                b3.solve(w3, s3, max_iterations=10)
+            samples = []
+            for _ in range(100):        # per-call samples: the host thread of a shared box is descheduled now and then
+                t0 = time.perf_counter()    # (tens of ms, device time unaffected), which a mean would smear over every call
+                _, sm3 = b3.solve(w3, s3, max_iterations=10)
+                samples.append(time.perf_counter() - t0)
+            samples.sort()
+            ts, worst = samples[len(samples) // 2], samples[-1]
             tc, cs = time_call(lambda: c_oracle.solve(w3, s3, max_iter=10), 5)
             entry = {"N": int(w3.N), "M": int(w3.M), "K_res": int(w3.K), "gpu_solve_call_ms": ts * 1e3,
-                     "gpu_solve_call_ms_worst_of_50": worst * 1e3, "gpu_solve_device_ms": sm3["solve_seconds"] * 1e3,
+                     "gpu_solve_call_ms_p90": samples[89] * 1e3, "gpu_solve_call_ms_worst_of_100": worst * 1e3,
+                     "gpu_solve_call_ms_note": "median / 90th percentile / worst wall time of 100 calls through the C-ABI (pack, upload, "
+                                               "one graph launch, download)",
+                     "gpu_solve_device_ms": sm3["solve_seconds"] * 1e3,
                      "iterations": int(sm3["iterations"]), "cpu_port_solve_ms_1_thread": tc * 1e3,
                      "cpu_port_iterations": int(cs[2]["iterations"]), "speedup_vs_1_thread": tc / ts}
             if name == "cfg3_inertial_prior":
