@@ -674,10 +674,14 @@ static int run_gn_step(Handle *h, int n, const StepCfg &c, const BatchShape &b) 
     return 0;
 }
 
-// One iteration of the device-side trust-region loop (ba_tr.cuh): 9 launches, no host decision.
-static int iteration_body(Handle *h, int n, const StepCfg &c, const BatchShape &b) {
+// One iteration of the device-side trust-region loop (ba_tr.cuh): 8 launches (9 in the first body), no host decision.
+// The linearisation of the STATE is launched in the first body only: afterwards the state's linearisation is either the
+// accepted candidate's (buffer swap) or still valid (rejected step), and the one case that invalidates it -- a failed
+// linear solve, retried with mu * 10 -- is relinearised by the candidate sweep of the same body (pipe_buffer).
+static int iteration_body(Handle *h, int n, const StepCfg &c, const BatchShape &b, bool first) {
     cudaStream_t st = c.stream ? c.stream : h->stream;
-    TRY(run_linearize(h, n, c, b));
+    if (first) TRY(launch_lin(h, n, c, b, true, false, false));
+    TRY(launch_schur(h, n, c, b, false));
     TRY(run_solve(h, n, c, b));
     TRY(launch_update<1>(h, n, c, b, 1));
     {
@@ -710,7 +714,7 @@ static int run_solve_loop(Handle *h, int n, int max_iter, double max_time, doubl
     ++h->launches;
     LAUNCH_CK(h, "init_ctrl_kernel");
     if (!graphable) {
-        for (int it = 0; it < bodies; ++it) TRY(iteration_body(h, n, c, b));
+        for (int it = 0; it < bodies; ++it) TRY(iteration_body(h, n, c, b, it == 0));
         return 0;
     }
     const Handle::GraphKey key(1, n, max_iter, (alias_bias ? 1 : 0) | (b.inertial ? 2 : 0) | (b.planes ? 4 : 0) | (h->hs_double ? 8 : 0) | (b.N << 4));
@@ -723,7 +727,7 @@ static int run_solve_loop(Handle *h, int n, int max_iter, double max_time, doubl
         CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         h->capturing = true;
         int rc = 0;
-        for (int i = 0; i < bodies && rc == 0; ++i) rc = iteration_body(h, n, c, b);
+        for (int i = 0; i < bodies && rc == 0; ++i) rc = iteration_body(h, n, c, b, i == 0);
         h->capturing = false;
         const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
         if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
@@ -1196,7 +1200,7 @@ int pvio_b200_batch_solve_host(pvio_b200_handle hh, int n, const pvio_b200_optio
         const BatchShape b = batch_shape(h, w0, m, false);
         init_ctrl_kernel<<<m, 32, 0, sc>>>(h->ctrl.d, 1e-8, radius0, max_iter, opt ? opt->max_time : 0.0, w0);
         ++h->launches;
-        for (int it = 0; it < max_iter + 2; ++it) TRY(iteration_body(h, m, c, b));
+        for (int it = 0; it < max_iter + 2; ++it) TRY(iteration_body(h, m, c, b, it == 0));
         CK(h, cudaEventRecord(h->ev_done[i], sc));
         CK(h, cudaStreamWaitEvent(h->stream_down, h->ev_done[i], 0));
         CK(h, cudaStreamWaitEvent(h->stream, h->ev_done[i], 0));      // later calls on the handle's stream see the result

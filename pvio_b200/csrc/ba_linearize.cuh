@@ -72,14 +72,22 @@ __device__ __forceinline__ void pipe_select(PipeArgs &a, int b) {
 __device__ __forceinline__ int pipe_buffer(const PipeArgs &a, int w) {
     if (!a.loop) return 0;
     const WinCtrl &c = a.ctrl[w];
-    if (a.spec) return (c.done || c.skip) ? -1 : 1 - c.buf;
+    if (a.spec) {
+        if (c.done) return -1;
+        // a skipped iteration whose linearisation was invalidated (failed linear solve, mu * 10: ba_tr.cuh): this sweep
+        // linearises the STATE again, with the new mu, into the state's own buffer set -- the next body starts from it
+        if (c.skip) return c.have_lin ? -1 : c.buf;
+        return 1 - c.buf;
+    }
     return (c.done || c.have_lin) ? -1 : c.buf;
 }
+// the speculative sweep of a body looks at the CANDIDATE; its retry form (above) at the state
+__device__ __forceinline__ bool pipe_at_candidate(const PipeArgs &a, int w) { return a.spec && !(a.loop && a.ctrl[w].skip); }
 // the pivots of a speculative sweep use the mu the next iteration will have IF its step is accepted (tr_decide)
 __device__ __forceinline__ double pipe_mu(const PipeArgs &a, int w) {
     if (a.mu_override >= 0.0) return a.mu_override;
     const double mu = a.ctrl[w].mu;
-    return a.spec ? fmax(1e-8, 2.0 * mu / 10.0) : mu;
+    return pipe_at_candidate(a, w) ? fmax(1e-8, 2.0 * mu / 10.0) : mu;
 }
 
 // ---- packed pairs: fma.rn.f32x2 (FFMA2 with a scalar-broadcast operand) for float, two DFMA for double
@@ -424,7 +432,7 @@ lin_obs_kernel(PipeArgs a_in) {
     const int bsel = pipe_buffer(a, w);
     if (bsel < 0) return;
     pipe_select(a, bsel);
-    if (a.spec) { a.frames = a.frames_cand; a.rho = a.rho_cand; }
+    if (pipe_at_candidate(a, w)) { a.frames = a.frames_cand; a.rho = a.rho_cand; }
     const WinHdr &H = a.hdr[w];
     const WinConst &wc = a.cst[w];
     const int N = H.N, M = H.M;

@@ -4,13 +4,13 @@
 // trust_region_minimizer.cc / dogleg_strategy.cc), one decision record (WinCtrl) per window.
 //
 // One iteration is a FIXED kernel sequence (api.cu: iteration_body), every kernel looks at its window's flags first:
-//   lin_obs (state)            only when the window has no valid linearisation (first iteration, retry after a failed
-//                              linear solve with mu * 10): into the window's buffer set WinCtrl::buf
+//   lin_obs (state)            FIRST body only (the window has no linearisation yet): into the window's buffer set WinCtrl::buf
 //   schur, solve               skipped when the previous step was rejected (`reuse`: same linearisation, same GN step)
 //   backsub  (+ tr_after_backsub)   GN step of the inverse depths; is the GN step inside the trust region?
 //   jv_vision, jv_aux (+ tr_after_jv)   only when it is not: |J v|^2 for the Cauchy point, dogleg interpolation
 //   candidate                  Plus(x, step)
-//   lin_obs (candidate)        the FULL linearisation of the candidate into the other buffer set: its cost is the
+//   lin_obs (candidate)        (a body skipped because its linear solve failed, mu * 10: the STATE again, with the new mu)
+//                              the FULL linearisation of the candidate into the other buffer set: its cost is the
 //                              reprojection cost the decision needs; on acceptance the buffer sets swap, so the
 //                              residual-only evaluation of ceres and the relinearisation after it are one sweep
 //   aux_cost (+ tr_decide)     IMU / prior / plane cost at the candidate; accept / reject, radius, mu, termination

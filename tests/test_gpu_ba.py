@@ -1,6 +1,8 @@
 """GPU parity tests (run on the B200 box): the CUDA path through the C-ABI against the fp64
 oracle on identical seeded inputs.  Tolerance: BASELINE.json north_star -- dx within 1e-5
 relative of the reference step; integer/index results bit-exact."""
+import copy
+
 import numpy as np
 import pytest
 
@@ -555,3 +557,23 @@ def test_resident_window_follows_the_repacked_sequence(ba):
     res.close()
     print("resident window vs re-packed sequence: worst state / inverse-depth difference", worst)
     assert worst < 1e-7       # measured 3e-9 after 20 keyframes: the landmarks enter the two packings in different orders
+
+
+def test_failed_linear_solve_is_retried_with_larger_mu_and_ends_in_failure(ba):
+    """ceres' dogleg retries a failed linear solve with mu * 10 (dogleg_strategy.cc) and the minimiser gives up once mu
+    leaves its range: a window whose system can never be factored (a NaN observation) walks that whole path on the device
+    -- every retry relinearises the state through the candidate sweep of the same body -- and must end as a FAILURE with
+    the state untouched, on the single-window graph and inside a batch next to healthy windows."""
+    for maker, kw in ((synth.make_cfg2, dict(N=6, M=80, seed=31)), (synth.make_cfg3, dict(N=6, M=100, seed=32))):
+        w, st, _ = maker(**kw)
+        good_out, good_sum = ba.solve(w, st, max_iterations=6)
+        wb = copy.deepcopy(w)
+        wb.obs_z = wb.obs_z.copy()
+        wb.obs_z[3, 0] = np.nan
+        out, summ = ba.solve(wb, st, max_iterations=10, postpass=False)     # 9 retries (1e-8 -> 10) fit into 10 + 2 bodies
+        assert summ['termination'] == 2 and summ['usable'] == 0 and summ['accepted_steps'] == 0      # PVIO_B200_TERM_FAILURE
+        assert summ['final_mu'] > 1.0
+        assert np.array_equal(out.p, st.p) and np.array_equal(out.q, st.q) and np.array_equal(out.rho, st.rho)
+        # the handle is intact: the healthy window solves as before
+        again, again_sum = ba.solve(w, st, max_iterations=6)
+        assert again_sum['iterations'] == good_sum['iterations'] and np.allclose(again.p, good_out.p, rtol=0, atol=1e-12)
