@@ -67,7 +67,10 @@ def _build_variant(defines, out):
         obj = os.path.join(odir, s[:-3] + ".o")
         extra = ["-fmad=false"] if s in ("klt.cu", "detect.cu", "fmat.cu") else []
         ref = os.path.join(CSRC, s[:-3] + ".o")
-        if s != "api.cu" and os.path.exists(ref):      # only api.cu depends on the tuning defines
+        names = [d.split("=")[0] for d in defines]
+        text = open(os.path.join(CSRC, s)).read()
+        uses = s == "api.cu" or any(n in text for n in names)      # api.cu includes every .cuh; other files: only if they name the define
+        if not uses and os.path.exists(ref):
             objs.append(ref)
             continue
         r = subprocess.run([NVCC] + [f for f in FLAGS if f not in ("-Xptxas", "-v")] + extra + ["-D" + d for d in defines] +

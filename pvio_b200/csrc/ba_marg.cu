@@ -247,20 +247,27 @@ __device__ __forceinline__ double block_sum(double v, double *red, int tid, int 
     return s;
 }
 
-__global__ void __launch_bounds__(256) marg_eig_kernel(const double *Ain, const double *bvec, int n, double *S, double *evec) {
+#ifdef PVIO_MARG_STAMPS            // tuning builds of tools/ only: phase times of the eigen-solver
+__device__ long long g_marg_stamps[8];
+#define MARG_STAMP(k) do { __syncthreads(); if (threadIdx.x == 0) g_marg_stamps[k] = clock64(); } while (0)
+#else
+#define MARG_STAMP(k) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(256) marg_eig_kernel(const double *Ain, const double *bvec, int n, int ring, double *S, double *evec) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int ld = n | 1;
     double *a = reinterpret_cast<double *>(smem_raw);       // [n][ld]: matrix -> eigenvectors (columns)
     double *d = a + (size_t)n * ld;                         // [n]
     double *e = d + n;                                      // [n]
-    double *rc = e + n;                                     // [n] rotation cosines of the current QL sweep
-    double *rs = rc + n;                                    // [n] sines
+    double *rot = e + n;                                    // [ring][2][n] rotation cosines / sines of the QL sweeps in flight
     __shared__ double red[8];
     __shared__ double sc_sm[4];
-    __shared__ int ctl[4];                                  // 0: m, 1: first rotation index, 2: last, 3: flags
+    __shared__ int ctl[2 + 2 * 4];                          // produced, consumed, index range of each ring slot
     for (int idx = tid; idx < n * n; idx += nt) a[(idx / n) * ld + idx % n] = Ain[idx];
     __syncthreads();
+    MARG_STAMP(0);
     // ---- tred2
     for (int i = n - 1; i > 0; --i) {
         const int l = i - 1;
@@ -313,6 +320,7 @@ __global__ void __launch_bounds__(256) marg_eig_kernel(const double *Ain, const 
     }
     if (tid == 0) { d[0] = 0.0; e[0] = 0.0; }
     __syncthreads();
+    MARG_STAMP(1);
     for (int i = 0; i < n; ++i) {                            // accumulate the transformations
         const int l = i - 1;
         double *ai = a + (size_t)i * ld;
@@ -328,16 +336,27 @@ __global__ void __launch_bounds__(256) marg_eig_kernel(const double *Ain, const 
         for (int j = tid; j <= l; j += nt) { a[(size_t)j * ld + i] = 0.0; ai[j] = 0.0; }
         __syncthreads();
     }
-    // ---- tql2
+    MARG_STAMP(2);
+    // ---- tql2, producer / consumer: the scalar recurrence of the implicit QL sweeps touches only d and e -- it does not
+    // depend on the eigenvector matrix -- so ONE thread (lane 0 of warp 0) runs ahead through all sweeps, publishing each
+    // sweep's rotations (cosines, sines, index range) in a ring of `ring` slots, while warps 1..7 apply the batches in
+    // order, row k of the matrix per thread.  The sweep time was scalar chain + application + three CTA barriers
+    // (13 K cycles per sweep, ~220 sweeps at n = 120); it is now the longer of the two.
     if (tid == 0) { for (int i = 1; i < n; ++i) e[i - 1] = e[i]; e[n - 1] = 0.0; }
+    volatile int *vctl = ctl;                                // [0] batches produced, [1] batches consumed
+    if (tid == 0) { vctl[0] = 0; vctl[1] = 0; }
+    int *rng = ctl + 2;                                      // [ring][2] index range of each slot (i_hi, i_lo); i_hi = -2: the end
     __syncthreads();
-    for (int l = 0; l < n; ++l) {
-        for (int iter = 0; iter < 64; ++iter) {
-            if (tid == 0) {                                  // scalar recurrence of one implicit QL sweep
-                int m = l;
-                for (; m < n - 1; ++m) { const double dd = fabs(d[m]) + fabs(d[m + 1]); if (fabs(e[m]) <= 2.3e-16 * dd) break; }
-                ctl[0] = m; ctl[1] = 0; ctl[2] = -1;
-                if (m != l) {
+    if (tid < 32) {
+        if (tid == 0) {
+            int prod = 0;
+            for (int l = 0; l < n; ++l) {
+                for (int iter = 0; iter < 64; ++iter) {
+                    int m = l;
+                    for (; m < n - 1; ++m) { const double dd = fabs(d[m]) + fabs(d[m + 1]); if (fabs(e[m]) <= 2.3e-16 * dd) break; }
+                    if (m == l) break;
+                    while (prod - vctl[1] >= ring) __nanosleep(40);       // every slot still in use
+                    double *rc = rot + (size_t)(prod % ring) * 2 * n, *rs = rc + n;
                     // (sqrt(f^2 + g^2) instead of hypot, one reciprocal instead of two divisions: this scalar chain is the
                     // critical path of the kernel -- ~60 dependent rotations per sweep, ~200 sweeps; the magnitudes here
                     // (<= 1e15 from the gauge prior) are far from the range where hypot's rescaling matters)
@@ -360,16 +379,28 @@ __global__ void __launch_bounds__(256) marg_eig_kernel(const double *Ain, const 
                         rc[i] = c; rs[i] = s;
                         d_i1 = d_i; e_i = e_nx; d_i = d_nx;
                     }
-                    ctl[1] = m - 1; ctl[2] = broke ? i + 1 : l;      // rotations i = m-1 .. ctl[2], in this order
                     if (!broke) { d[l] -= p; e[l] = g; e[m] = 0.0; }
+                    rng[2 * (prod % ring)] = m - 1;                      // rotations i = m - 1 .. i_lo, in this order
+                    rng[2 * (prod % ring) + 1] = broke ? i + 1 : l;
+                    __threadfence_block();
+                    vctl[0] = ++prod;
                 }
             }
-            __syncthreads();
-            const int m = ctl[0], i_hi = ctl[1], i_lo = ctl[2];
-            __syncthreads();                                 // everybody has read the sweep record before it is rewritten
-            if (m == l) break;                               // uniform
-            for (int k = tid; k < n; k += nt) {              // row k of the eigenvector matrix takes the whole batch
-                double *zk = a + (size_t)k * ld;
+            while (prod - vctl[1] >= ring) __nanosleep(40);
+            rng[2 * (prod % ring)] = -2;
+            __threadfence_block();
+            vctl[0] = prod + 1;
+        }
+    } else {
+        const int ct = tid - 32, nct = nt - 32;
+        for (int k = 0;; ++k) {
+            while (vctl[0] <= k) __nanosleep(20);
+            __threadfence_block();
+            const int i_hi = rng[2 * (k % ring)], i_lo = rng[2 * (k % ring) + 1];
+            if (i_hi == -2) break;
+            const double *rc = rot + (size_t)(k % ring) * 2 * n, *rs = rc + n;
+            for (int row = ct; row < n; row += nct) {        // row `row` of the eigenvector matrix takes the whole batch
+                double *zk = a + (size_t)row * ld;
                 double zi1 = zk[i_hi + 1];
                 for (int i = i_hi; i >= i_lo; --i) {
                     const double zi = zk[i], c = rc[i], s = rs[i];
@@ -378,10 +409,12 @@ __global__ void __launch_bounds__(256) marg_eig_kernel(const double *Ain, const 
                 }
                 zk[i_lo] = zi1;
             }
-            __syncthreads();
+            asm volatile("bar.sync 1, %0;" ::"r"(nct) : "memory");       // the consumers are done with the slot
+            if (ct == 0) { vctl[1] = k + 1; }
         }
     }
     __syncthreads();
+    MARG_STAMP(3);
     // S = sqrt(lambda_clamped) V^T ; e = sqrt(1 / lambda) V^T b
     for (int i = tid; i < n; i += nt) {
         const double lam = d[i];
@@ -395,7 +428,14 @@ __global__ void __launch_bounds__(256) marg_eig_kernel(const double *Ain, const 
         }
         evec[i] = il * dot;
     }
+    MARG_STAMP(4);
 }
+
+#ifdef PVIO_MARG_STAMPS
+extern "C" int pvio_b200_debug_marg_stamps(long long *out) {
+    return cudaMemcpyFromSymbol(out, g_marg_stamps, sizeof(long long) * 8) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // Persistent device scratch of the marginaliser (it runs at every keyframe: nothing is allocated in the steady state).
 struct MargScratch {
@@ -421,7 +461,7 @@ int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state
     if (!w->use_inertial) return fail(h, PVIO_B200_EINVAL, "marginalize: the window must carry motion states");
     const int n = 15 * N, dk = n - 15;
     if (keep_on_device && index != 0) return fail(h, PVIO_B200_EINVAL, "marginalize: the resident prior is defined for index 0");
-    if ((S_out || e_out || keep_on_device) && sizeof(double) * ((size_t)dk * (dk | 1) + 4 * (size_t)dk) > 224 * 1024)
+    if ((S_out || e_out || keep_on_device) && sizeof(double) * ((size_t)dk * (dk | 1) + 6 * (size_t)dk) > 226 * 1024)
         return fail(h, PVIO_B200_EINVAL, "marginalize: window too large for the shared-memory eigen-solver (15 (N - 1) <= 165)");
     int rc = pack_and_upload(h, w, s);
     if (rc != 0) return rc;
@@ -451,10 +491,13 @@ int marginalize_impl(Handle *h, const pvio_b200_window *w, const pvio_b200_state
     if (H_out) CK(h, cudaMemcpyAsync(H_out, dHk, sizeof(double) * dk * dk, cudaMemcpyDeviceToHost, h->stream));
     if (b_out) CK(h, cudaMemcpyAsync(b_out, dbk, sizeof(double) * dk, cudaMemcpyDeviceToHost, h->stream));
     if (S_out || e_out || keep_on_device) {
-        const size_t esm = sizeof(double) * ((size_t)dk * (dk | 1) + 4 * (size_t)dk);
+        // matrix + d, e + the ring of rotation batches (4 slots; 2 when the matrix leaves no room: dk = 165)
+        const size_t esm4 = sizeof(double) * ((size_t)dk * (dk | 1) + 10 * (size_t)dk);
+        const int ring = esm4 <= 226 * 1024 ? 4 : 2;
+        const size_t esm = sizeof(double) * ((size_t)dk * (dk | 1) + (2 + 2 * (size_t)ring) * dk);
         static bool attr_set = false;
-        if (!attr_set) { CK(h, cudaFuncSetAttribute(marg_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); attr_set = true; }
-        marg_eig_kernel<<<1, 256, esm, h->stream>>>(dHk, dbk, dk, dS, de);
+        if (!attr_set) { CK(h, cudaFuncSetAttribute(marg_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); attr_set = true; }
+        marg_eig_kernel<<<1, 256, esm, h->stream>>>(dHk, dbk, dk, ring, dS, de);
         ++h->launches;
         if (S_out) CK(h, cudaMemcpyAsync(S_out, dS, sizeof(double) * dk * dk, cudaMemcpyDeviceToHost, h->stream));
         if (e_out) CK(h, cudaMemcpyAsync(e_out, de, sizeof(double) * dk, cudaMemcpyDeviceToHost, h->stream));

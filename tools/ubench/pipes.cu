@@ -59,6 +59,31 @@ __global__ void __launch_bounds__(256) smem_kernel(float *out, int iters) {
     if (acc == 12345.678f || sf[tid] == -1.f || sd[tid] == -1.0) out[0] = acc;
 }
 
+
+// Dependent-chain latencies seen by ONE warp (clock64 around an unrolled chain): DFMA, DMUL->DFMA, rsqrt(double), FFMA,
+// an LDS round trip, a CTA barrier of 8 warps.
+template <int MODE>
+__global__ void lat_kernel(long long *out, double seed, int n) {
+    __shared__ double sm[64];
+    double x = seed, y = 1.0000001;
+    float xf = (float)seed;
+    sm[threadIdx.x & 63] = seed;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+        if (MODE == 0) x = fma(x, y, 0.5);
+        else if (MODE == 1) x = rsqrt(x + 2.0);
+        else if (MODE == 2) xf = fmaf(xf, 1.0001f, 0.5f);
+        else if (MODE == 3) { x = sm[((int)x) & 63] + 1.0; }          // LDS -> convert -> address
+        else if (MODE == 4) { __syncthreads(); }
+        else if (MODE == 5) x = 1.0 / (x + 2.0);
+        else if (MODE == 6) x = sqrt(x + 2.0);
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[MODE] = (t1 - t0);
+    if (x == 12345.678 || xf == 1234.5f) out[15] = 1;
+}
+
 template <typename F>
 static float time_it(F launch) {
     cudaEvent_t e0, e1;
@@ -99,5 +124,18 @@ int main() {
     rep("LDS.128", time_it([&] { smem_kernel<2><<<grid, 256>>>(out, iters); }), 8, iters);
     rep("LDS.64", time_it([&] { smem_kernel<3><<<grid, 256>>>(out, iters); }), 8, iters);
     rep("LDS.32", time_it([&] { smem_kernel<4><<<grid, 256>>>(out, iters); }), 8, iters);
+    {
+        long long *d_lat, h_lat[16] = {0};
+        CK(cudaMalloc(&d_lat, sizeof(h_lat)));
+        CK(cudaMemset(d_lat, 0, sizeof(h_lat)));
+        const int n = 4096;
+        lat_kernel<0><<<1, 32>>>(d_lat, 1.5, n); lat_kernel<1><<<1, 32>>>(d_lat, 1.5, n); lat_kernel<2><<<1, 32>>>(d_lat, 1.5, n);
+        lat_kernel<3><<<1, 32>>>(d_lat, 1.5, n); lat_kernel<4><<<1, 256>>>(d_lat, 1.5, n); lat_kernel<5><<<1, 32>>>(d_lat, 1.5, n);
+        lat_kernel<6><<<1, 32>>>(d_lat, 1.5, n);
+        CK(cudaMemcpy(h_lat, d_lat, sizeof(h_lat), cudaMemcpyDeviceToHost));
+        const char *nm[7] = {"DFMA dependent chain", "rsqrt(double) chain (+ DADD)", "FFMA dependent chain", "LDS.64 -> F2I -> address chain (+ DADD)",
+                             "__syncthreads, 8 warps", "1.0 / x (double) chain (+ DADD)", "sqrt(double) chain (+ DADD)"};
+        for (int i = 0; i < 7; ++i) printf("%-44s %7.1f cycles per step\n", nm[i], (double)h_lat[i] / n);
+    }
     return 0;
 }
