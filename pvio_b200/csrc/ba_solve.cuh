@@ -700,8 +700,15 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
     for (int i = tid; i < nA; i += nt) A[i] = 0.0;
     for (int i = tid; i < 4 * Dp; i += nt) g[i] = 0.0;      // g, gu, hcorr, xs contiguous
     if (tid < 4) cost_sm[tid] = 0.0;
+    __shared__ double x2_sm[kMaxFrames];                    // |x|^2 of each frame's ambient parameter blocks
     if (tid < N) {
         const double *fs = frames + tid * kFrameStride;
+        {   // ceres takes norms of the 4-vector quaternion; constant pose blocks are not parameters
+            double x2 = 0.0;
+            if (!((H.fixed_mask >> tid) & 1)) for (int k = 0; k < 7; ++k) x2 += fs[k] * fs[k];
+            if (inertial) for (int k = 7; k < 16; ++k) x2 += fs[k] * fs[k];
+            x2_sm[tid] = x2;
+        }
         double R[9];
         quat_to_mat(fs, R);
         const double p[3] = {fs[4] - wc.origin[0], fs[5] - wc.origin[1], fs[6] - wc.origin[2]};
@@ -1255,22 +1262,26 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
         if (tid < D) { red[tid * 7 + 0] = gdx; red[tid * 7 + 1] = rdx; red[tid * 7 + 2] = gn2; red[tid * 7 + 3] = dx2; red[tid * 7 + 4] = gmax;
                        red[tid * 7 + 5] = g2; red[tid * 7 + 6] = vrd; }
         __syncthreads();
-        if (tid == 0) {
+        if (tid < 32) {                  // warp 0: strided partial sums, then a shuffle tree (fixed order: reproducible)
             gdx = rdx = gn2 = dx2 = gmax = g2 = vrd = 0.0;
             const int nred = min(nt, D);
-            for (int t = 0; t < nred; ++t) {
+            for (int t = tid; t < nred; t += 32) {
                 gdx += red[t * 7]; rdx += red[t * 7 + 1]; gn2 += red[t * 7 + 2]; dx2 += red[t * 7 + 3];
                 gmax = fmax(gmax, red[t * 7 + 4]); g2 += red[t * 7 + 5]; vrd += red[t * 7 + 6];
             }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                gdx += __shfl_xor_sync(0xffffffffu, gdx, off); rdx += __shfl_xor_sync(0xffffffffu, rdx, off);
+                gn2 += __shfl_xor_sync(0xffffffffu, gn2, off); dx2 += __shfl_xor_sync(0xffffffffu, dx2, off);
+                gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+                g2 += __shfl_xor_sync(0xffffffffu, g2, off); vrd += __shfl_xor_sync(0xffffffffu, vrd, off);
+            }
+        }
+        if (tid == 0) {
             ctrl.grad2 = g2;
             ctrl.v_reg_dx = vrd;
-            // |x|^2 over the ambient parameter blocks (ceres takes norms of the 4-vector quaternion)
             double x2 = 0.0;
-            for (int f = 0; f < N; ++f) {
-                const double *fs = frames + f * kFrameStride;
-                if (!((H.fixed_mask >> f) & 1)) for (int k = 0; k < 7; ++k) x2 += fs[k] * fs[k];
-                if (inertial) for (int k = 7; k < 16; ++k) x2 += fs[k] * fs[k];
-            }
+            for (int f = 0; f < N; ++f) x2 += x2_sm[f];
             ctrl.g_dot_dx = gdx;
             ctrl.dx_reg_dx = rdx;
             ctrl.gn_norm2 = gn2;
