@@ -397,6 +397,7 @@ struct StepCfg {
     int dump = 0;
     int loop = 0;                  // kernels obey the per-window trust-region flags
     int w0 = 0;                    // first window (sub-batch pipelining)
+    int fork_aux = 0;              // latency path: the non-vision candidate cost runs beside the candidate's linearisation sweep
     cudaStream_t stream = nullptr; // nullptr: the handle's stream
 };
 
@@ -415,7 +416,7 @@ static size_t solve_smem_one(const WinHdr &H, bool lean) {
     }
     const size_t nb = (D + 3) / 4, Dp = nb * 4;
     const size_t np_ = (size_t)H.N * (H.N + 1) / 2;
-    size_t scr = lean ? Dp + 10 * 36 + 36 : std::max<size_t>(Dp, np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);
+    size_t scr = lean ? Dp + 10 * 36 + 36 : std::max<size_t>(Dp, 2 * np_ * 36 + (size_t)H.N * 36 + (size_t)H.N * 12);   // X blocks, X T_g, diagonal, gradients
     if (H.use_inertial) scr = std::max<size_t>(scr, 8 * 450 + 8 * 16 + 8 * 480 + 8 * 225);      // kImuRound factors: raw J, r; whitened [J | r]; their W
     if (H.n_prior > 0) scr = std::max<size_t>(scr, 3 * 15 * (size_t)H.n_prior + 9 * (size_t)H.n_prior + 8 * 225);   // + one 15 x 15 block per warp
     return sizeof(double) * ((nb + 1) * (nb + 2) / 2 * 18 + 4 * Dp + (size_t)H.N * 36 + scr);   // tiles of kTP = 18 doubles (ba_solve.cuh)
@@ -652,11 +653,16 @@ static int launch_update(Handle *h, int n, const StepCfg &c, const BatchShape &b
     return 0;
 }
 
-static int launch_aux_cost(Handle *h, int n, const StepCfg &c, const BatchShape &b) {
-    cudaStream_t st = c.stream ? c.stream : h->stream;
+// part 0: cost + decision in one launch; 1: cost only, on stream `on`; 2: decision only (aux_cost_kernel)
+static int launch_aux_cost(Handle *h, int n, const StepCfg &c, const BatchShape &b, int part = 0, cudaStream_t on = nullptr) {
+    cudaStream_t st = on ? on : (c.stream ? c.stream : h->stream);
     const CostArgs k = make_cost_args(h, c);
     // inertial windows: 8 warps share the prior's S r0 product; reprojection-only batches only need the acceptance copy
-    aux_cost_kernel<<<n, b.inertial ? 256 : 64, sizeof(double) * 2 * 15 * kMaxFrames, st>>>(k);
+    const int threads = (b.inertial && part != 2) ? 256 : 64;
+    const size_t smem = sizeof(double) * 2 * 15 * kMaxFrames;
+    if (part == 1) aux_cost_kernel<1><<<n, threads, smem, st>>>(k);
+    else if (part == 2) aux_cost_kernel<2><<<n, threads, smem, st>>>(k);
+    else aux_cost_kernel<0><<<n, threads, smem, st>>>(k);
     ++h->launches;
     LAUNCH_CK(h, "aux_cost_kernel");
     return 0;
@@ -696,8 +702,20 @@ static int iteration_body(Handle *h, int n, const StepCfg &c, const BatchShape &
         h->launches += 2;
     }
     TRY(launch_update<2>(h, n, c, b, 1));
+    const bool fork = c.fork_aux && (b.inertial || b.planes);   // the candidate's IMU / prior / plane cost on a parallel branch
+    if (fork) {
+        CK(h, cudaEventRecord(h->ev_aux_fork, st));
+        CK(h, cudaStreamWaitEvent(h->stream_aux, h->ev_aux_fork, 0));
+        TRY(launch_aux_cost(h, n, c, b, 1, h->stream_aux));
+        CK(h, cudaEventRecord(h->ev_aux_join, h->stream_aux));
+    }
     TRY(launch_lin(h, n, c, b, true, false, true));      // the candidate's linearisation: its cost decides, its Jacobians stay
-    TRY(launch_aux_cost(h, n, c, b));
+    if (fork) {
+        CK(h, cudaStreamWaitEvent(st, h->ev_aux_join, 0));
+        TRY(launch_aux_cost(h, n, c, b, 2));
+    } else {
+        TRY(launch_aux_cost(h, n, c, b));
+    }
     return 0;
 }
 
@@ -724,6 +742,12 @@ static int run_solve_loop(Handle *h, int n, int max_iter, double max_time, doubl
         const int64_t l0 = h->launches;
         cudaGraph_t g = nullptr;
         cudaGraphExec_t ge = nullptr;
+        if (!h->stream_aux) {
+            CK(h, cudaStreamCreateWithFlags(&h->stream_aux, cudaStreamNonBlocking));
+            CK(h, cudaEventCreateWithFlags(&h->ev_aux_fork, cudaEventDisableTiming));
+            CK(h, cudaEventCreateWithFlags(&h->ev_aux_join, cudaEventDisableTiming));
+        }
+        c.fork_aux = 1;                // a second branch of the graph (captured through h->stream_aux)
         CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         h->capturing = true;
         int rc = 0;
@@ -921,6 +945,7 @@ void pvio_b200_destroy(pvio_b200_handle hh) {
     if (h->stream_down) cudaStreamDestroy(h->stream_down);
     for (auto &st : h->stream_c) cudaStreamDestroy(st);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->stream_aux) { cudaStreamDestroy(h->stream_aux); cudaEventDestroy(h->ev_aux_fork); cudaEventDestroy(h->ev_aux_join); }
     cudaStreamDestroy(h->stream);
     delete h;
 }

@@ -30,6 +30,8 @@ struct Handle {
     cudaStream_t stream_up = nullptr, stream_down = nullptr;   // copy streams of the pipelined host path
     std::vector<cudaStream_t> stream_c;                        // compute streams of the pipelined host path
     cudaEvent_t ev_fork = nullptr;
+    cudaStream_t stream_aux = nullptr;                         // second branch of the captured single-window solve (api.cu: iteration_body)
+    cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_done, ev_down;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;

@@ -823,31 +823,30 @@ static __device__ __forceinline__ void solve_body(const SolveArgs &a) {
             }
             hcorr[f * stride + i] = sd;
         }
-        const int per_pass = (nt / 36) * 36;     // whole blocks per pass: in-place update is safe
-        for (int base = 0; base < npairs * 36; base += per_pass) {
-            const int e = base + tid;
-            const bool act = tid < per_pass && e < npairs * 36;
+        // M = X T_g into a second buffer (one barrier; the in-place form needed two per pass of 252 entries), then
+        // T_f^T M into the packed system
+        double *Ms = gx + 2 * N * 6;             // [npairs][36]
+        for (int e = tid; e < npairs * 36; e += nt) {
+            const int p = e / 36, ij = e - p * 36, i = ij / 6, j = ij - i * 6;
+            int f = 0;
+            while ((f + 1) * (f + 2) / 2 <= p) ++f;
+            const int gf = p - f * (f + 1) / 2;
+            const double *X = Xs + p * 36 + i * 6, *Tg = T + gf * 36 + j;
             double v = 0.0;
-            if (act) {
-                const int p = e / 36, ij = e - p * 36, i = ij / 6, j = ij - i * 6;
-                int f = 0;
-                while ((f + 1) * (f + 2) / 2 <= p) ++f;
-                const int gf = p - f * (f + 1) / 2;
-                const double *X = Xs + p * 36 + i * 6, *Tg = T + gf * 36 + j;
-                for (int bb = 0; bb < 6; ++bb) v += X[bb] * Tg[bb * 6];
-            }
-            __syncthreads();
-            if (act) Xs[e] = v;
-            __syncthreads();
+#pragma unroll
+            for (int bb = 0; bb < 6; ++bb) v += X[bb] * Tg[bb * 6];
+            Ms[e] = v;
         }
+        __syncthreads();
         for (int e = tid; e < npairs * 36; e += nt) {
             const int p = e / 36, ij = e - p * 36, i = ij / 6, j = ij - i * 6;
             int f = 0;
             while ((f + 1) * (f + 2) / 2 <= p) ++f;
             const int gf = p - f * (f + 1) / 2;
             if (f == gf && j > i) continue;
-            const double *Tf = T + f * 36 + i, *Mx = Xs + p * 36 + j;
+            const double *Tf = T + f * 36 + i, *Mx = Ms + p * 36 + j;
             double sv = 0.0;
+#pragma unroll
             for (int aa = 0; aa < 6; ++aa) sv += Tf[aa * 6] * Mx[aa * 6];
             const int gi = f * stride + i, gj = gf * stride + j;
             A[tri(gi, gj)] = sv;
@@ -1336,6 +1335,10 @@ struct CostArgs {
     double beta;                   // loop == 0: the step was beta * dx_gn (model change of the truncated step)
 };
 
+// kPart 0: cost of the IMU / prior / plane blocks at the candidate + the step decision (one launch, batches);
+// 1: the cost only (-> a.out[w]); 2: the decision only, cost read from a.out[w].  The latency path launches part 1 on a
+// parallel branch of the solve graph, beside the candidate's linearisation sweep: both only need the candidate.
+template <int kPart>
 static __global__ void aux_cost_kernel(CostArgs a) {
     const int w = blockIdx.x + a.w0;
     const WinHdr &H = a.hdr[w];
@@ -1348,10 +1351,10 @@ static __global__ void aux_cost_kernel(CostArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *r0 = reinterpret_cast<double *>(smem_raw);
     WinCtrl &ctrl = a.ctrl[w];
-    if (a.loop && (ctrl.done || ctrl.skip)) { if (tid == 0) ctrl.fresh = 0; return; }
-    if (tid == 0) acc = 0.0;
+    if (a.loop && (ctrl.done || ctrl.skip)) { if (tid == 0 && kPart != 1) ctrl.fresh = 0; return; }
+    if (tid == 0) acc = kPart == 2 ? a.out[w] : 0.0;
     __syncthreads();
-    if (H.use_inertial) {
+    if (kPart != 2 && H.use_inertial) {
         const int32_t *idx = a.imu_idx + (size_t)w * a.Ncap * 2;
         const double *recs = a.imu_data + (size_t)w * a.Ncap * kImuStride;
         __shared__ double imu_c[kMaxFrames];
@@ -1418,7 +1421,7 @@ static __global__ void aux_cost_kernel(CostArgs a) {
         }
         __syncthreads();
     }
-    if (H.n_ptracks > 0) {
+    if (kPart != 2 && H.n_ptracks > 0) {
         const double *pl = a.plane_param + (size_t)w * a.Pcap * 4;
         const int32_t *ptp = a.pt_plane + (size_t)w * a.Tcap;
         const int32_t *ptb = a.pt_begin + (size_t)w * (a.Tcap + 1);
@@ -1433,6 +1436,7 @@ static __global__ void aux_cost_kernel(CostArgs a) {
         }
     }
     __syncthreads();
+    if (kPart == 1) { if (tid == 0) a.out[w] = acc; return; }
     // ---- step acceptance: what ceres does after evaluating the candidate (trust_region_minimizer.cc)
     if (tid == 0) {
         a.out[w] = acc;
