@@ -40,3 +40,30 @@ ba.batch_set(0, w, st); ba.batch_replicate(80); ba.batch_upload(80); ba.batch_so
 fr, rh, sm = ba.batch_download_state(80, w.N, w.M)
 print('batch solve', sm[0]['iterations'], sm[79]['final_cost'])
 ba.close()
+# round 2: F-matrix RANSAC (+ LMedS branch, whole track_keypoints), detector, the 135-dim inertial window (register-resident
+# Cholesky, 5-slot instantiation at N = 11), the failure / retry path, the producer / consumer eigen-solver at D = 135
+from pvio_b200.detect import detect_keypoints
+b2 = BundleAdjustor(max_windows=1, max_frames=12, max_landmarks=512, max_obs=4608)
+fp, fq = synth.make_fm_matches(5, 200, 0.3)
+m, F, info = klt.find_fundamental_mask(b2, fp, fq, return_info=True)
+print('fm ransac', int(m.sum()), info)
+m, F, info = klt.find_fundamental_mask(b2, fp[:14], fq[:14], return_info=True)
+print('fm lmeds', int(m.sum()), info)
+nx, stt = klt.track_keypoints_ransac(b2, prev, nxt, pts, prev_id=11, next_id=12)
+print('track_keypoints whole', int(stt.sum()))
+kp = detect_keypoints(b2, nxt, pts[:5], keypoint_distance=15.0, clahe_clip=6.0, frame_id=12)
+print('detect', len(kp))
+for N in (9, 11):
+    wN, sN, _ = synth.make_cfg3(N=N, M=120)
+    o, sm_ = b2.solve(wN, sN, max_iterations=3)
+    print('solve cfg3 N', N, sm_['iterations'], sm_['final_cost'])
+    S, e = b2.marginalize_frame(wN, sN, 0)
+    print('marg N', N, np.linalg.norm(S))
+w4b, s4b, _ = synth.make_cfg4(N=9, M=100)
+o, sm_ = b2.solve(w4b, s4b, max_iterations=2)
+print('solve cfg4', sm_['iterations'])
+import copy
+wb = copy.deepcopy(wN); wb.obs_z = wb.obs_z.copy(); wb.obs_z[3, 0] = np.nan
+o, sm_ = b2.solve(wb, sN, max_iterations=10, postpass=False)
+print('failure path', sm_['termination'], sm_['usable'])
+b2.close()
