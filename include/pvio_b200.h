@@ -307,6 +307,11 @@ int pvio_b200_detect_keypoints(pvio_b200_handle h, uint64_t frame_id, const uint
 int pvio_b200_find_fundamental_mask(pvio_b200_handle h, int n, const float *p, const float *q, double threshold, double confidence,
                                     int max_iters, const int32_t *schedule, int n_schedule, uint8_t *mask, double *F, int32_t *info);
 
+/* Host only (no device, no handle): the sample schedule the call above uses when schedule == NULL, i.e. the subsets
+ * cv::findFundamentalMat draws for these n >= 8 matches with cv::RNG((uint64)-1): int32 [iters][7].  Returns the number of
+ * iterations that have a subset (< iters only if getSubset gives up: degenerate, collinear input), or a negative error. */
+int pvio_b200_fm_sample_schedule(int n, const float *p, const float *q, int iters, int32_t *schedule);
+
 /* OpenCvImage::track_keypoints as a whole (opencv_image.cpp:88-136): pvio_b200_klt_track_cached (LK on the cached pyramids,
  * 20-pixel border on the device) followed by the F-matrix rejection above over the surviving matches when there are at
  * least 8 (:121).  next_pts holds the initial guess on entry (:91-96: the caller's next_keypoints, or a copy of prev_pts);

@@ -75,7 +75,7 @@ EXPORTS = [
     "pvio_b200_window_reset", "pvio_b200_window_append_frame", "pvio_b200_window_add_tracks",
     "pvio_b200_window_add_observations", "pvio_b200_window_remove_track", "pvio_b200_window_set_prior",
     "pvio_b200_window_solve", "pvio_b200_window_drop_victim", "pvio_b200_window_get", "pvio_b200_detect_keypoints",
-    "pvio_b200_find_fundamental_mask", "pvio_b200_track_keypoints",
+    "pvio_b200_find_fundamental_mask", "pvio_b200_track_keypoints", "pvio_b200_fm_sample_schedule",
 ]
 
 _lib = None

@@ -1381,6 +1381,11 @@ int pvio_b200_find_fundamental_mask(pvio_b200_handle hh, int n, const float *p, 
     return fm_ransac_impl(h, n, p, q, threshold, confidence, max_iters, schedule, n_schedule, mask, F, info);
 }
 
+int pvio_b200_fm_sample_schedule(int n, const float *p, const float *q, int iters, int32_t *schedule) {
+    if (n < 8 || !p || !q || iters < 1 || !schedule) return PVIO_B200_EINVAL;
+    return fm_cv_schedule(n, p, q, iters, schedule);
+}
+
 int pvio_b200_track_keypoints(pvio_b200_handle hh, uint64_t prev_id, const uint8_t *prev, uint64_t next_id, const uint8_t *next,
                               int width, int height, int stride, const float *prev_pts, float *next_pts, uint8_t *status,
                               int n_points, int max_level, int max_iter, double eps, double clahe_clip, int tiles_x, int tiles_y,

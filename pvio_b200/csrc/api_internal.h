@@ -133,6 +133,7 @@ void marg_free(Handle *h);
 int fm_ransac_impl(Handle *h, int n, const float *p, const float *q, double threshold, double confidence, int max_iters,
                    const int32_t *schedule, int n_schedule, uint8_t *mask, double *F_out, int32_t *info);
 void fm_free(Handle *h);
+int fm_cv_schedule(int n, const float *p, const float *q, int iters, int32_t *schedule);
 // selftest.cu
 int selftest_lie_impl(Handle *h, int n, const double *w_in, double *out);
 

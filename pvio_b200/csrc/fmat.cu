@@ -396,6 +396,11 @@ int fm_reserve(Handle *h, int n, int s) {
 
 }  // namespace
 
+// host-only: the subsets OpenCV would draw (exported as pvio_b200_fm_sample_schedule)
+int fm_cv_schedule(int n, const float *p, const float *q, int iters, int32_t *schedule) {
+    return cv_schedule(p, q, n, iters, n >= 15 ? 10000 : 1000, schedule);
+}
+
 int fm_ransac_impl(Handle *h, int n, const float *p, const float *q, double threshold, double confidence, int max_iters,
                    const int32_t *schedule, int n_schedule, uint8_t *mask, double *F_out, int32_t *info) {
     int inf[4] = {0, -1, -1, 0};              // iterations run, winning iteration, winning model, method (1 RANSAC, 2 LMedS, 3 seven points)
