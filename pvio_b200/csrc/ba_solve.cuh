@@ -527,8 +527,9 @@ __device__ __forceinline__ void chol_diag_update(double (&c)[16], const double *
 //                 per thread) IN REGISTERS for the whole factorisation: a block column costs a tile two 128-byte panel
 //                 tiles read from shared memory and no write (chol_solve_tiled: 512 B per tile and step).
 // Shared memory holds what others need: the inverse factor of each diagonal tile and the finished panel tiles L_Ik
-// (also what the back substitution reads).  Per block column: panel tiles X <- X L_kk^-T by their owners (barrier),
-// trailing update C -= L_Ik L_Jk^T (barrier).
+// (also what the back substitution reads).  ONE barrier per block column: trailing update C -= L_Ik L_Jk^T, then the
+// owners of the next column's tiles wait for warp 0 to publish the inverse factor (a shared flag, no barrier) and store
+// their panel tiles X <- X L^-T.
 template <int kSlots>
 __device__ inline bool chol_solve_regs(double *A, double *x, int nb, int *flag_sm) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -563,67 +564,66 @@ __device__ inline bool chol_solve_regs(double *A, double *x, int nb, int *flag_s
     }
     if (tid == 0) chol_factor4(A + tile_off(0, 0), flag_sm);      // tile (0, 0) is still intact in shared memory
     __syncthreads();
-#ifdef PVIO_SOLVE_STAMPS
-    if (tid == 0 && blockIdx.x == 0) for (int k = 10; k < 16; ++k) g_solve_stamps[k] = 0;
-    long long ct__ = clock64();
-#define RSTAMP(t, k) do { if (threadIdx.x == (t) && blockIdx.x == 0) { const long long n__ = clock64(); g_solve_stamps[k] += n__ - ct__; ct__ = n__; } } while (0)
-#else
-#define RSTAMP(t, k) do { } while (0)
-#endif
+    // panel tile X <- X L_kk^-T of column `col` for every owned tile of that column (incl. the rhs row), into shared memory
+    auto panel = [&](int col) {
+        const double *Li = A + tile_off(col, col);
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+            if (tJ[s] != col) continue;                // (tI > col for every off-diagonal tile of the column)
+            const int rows = (tI[s] == nb) ? 1 : 4;
+            double *X = A + tile_off(tI[s], col);
+            const double l0 = Li[0], l4 = Li[4], l5 = Li[5], l8 = Li[8], l9 = Li[9], l10 = Li[10], l12 = Li[12], l13 = Li[13],
+                         l14 = Li[14], l15 = Li[15];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (r >= rows) break;
+                const double x0 = c[s][r * 4], x1 = c[s][r * 4 + 1], x2 = c[s][r * 4 + 2], x3 = c[s][r * 4 + 3];
+                double2 o0, o1;
+                o0.x = x0 * l0;
+                o0.y = x0 * l4 + x1 * l5;
+                o1.x = x0 * l8 + x1 * l9 + x2 * l10;
+                o1.y = x0 * l12 + x1 * l13 + x2 * l14 + x3 * l15;
+                reinterpret_cast<double2 *>(X + r * 4)[0] = o0;
+                reinterpret_cast<double2 *>(X + r * 4)[1] = o1;
+            }
+        }
+    };
+    __shared__ int diag_ready_sm;                      // the last block column whose diagonal tile is factored (inverse in shared memory)
+    volatile int *diag_ready = &diag_ready_sm;
+    if (tid == 0) *diag_ready = 0;
+    if (warp != 0) panel(0);
+    __syncthreads();
+    // One barrier per block column.  After it the panel tiles of column kb are in shared memory.  Warp 0 updates the next
+    // diagonal tile, factors it and PUBLISHES it (diag_ready, no barrier); the other warps update their tiles with column
+    // kb -- and the owners of the tiles of column kb + 1 then pick the inverse factor up as soon as it is published and
+    // store their finished panel tiles, so that the next block column starts right after the barrier.
     for (int kb = 0; kb < nb; ++kb) {
         if (*flag_sm == 0) break;                      // uniform
-        // panel: owners of the tiles (I, kb), I > kb, incl. the rhs row.  Warp 0 has no panel tiles: it catches up on the
-        // diagonal tiles of its OTHER slot with the previous block column (off the critical path: nobody waits for them yet)
-        if (warp != 0) {
-            const double *Li = A + tile_off(kb, kb);
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                if (tJ[s] != kb) continue;             // (tI > kb for every off-diagonal tile of column kb)
-                const int rows = (tI[s] == nb) ? 1 : 4;
-                double *X = A + tile_off(tI[s], kb);
-                const double l0 = Li[0], l4 = Li[4], l5 = Li[5], l8 = Li[8], l9 = Li[9], l10 = Li[10], l12 = Li[12], l13 = Li[13],
-                             l14 = Li[14], l15 = Li[15];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    if (r >= rows) break;
-                    const double x0 = c[s][r * 4], x1 = c[s][r * 4 + 1], x2 = c[s][r * 4 + 2], x3 = c[s][r * 4 + 3];
-                    double2 o0, o1;
-                    o0.x = x0 * l0;
-                    o0.y = x0 * l4 + x1 * l5;
-                    o1.x = x0 * l8 + x1 * l9 + x2 * l10;
-                    o1.y = x0 * l12 + x1 * l13 + x2 * l14 + x3 * l15;
-                    reinterpret_cast<double2 *>(X + r * 4)[0] = o0;
-                    reinterpret_cast<double2 *>(X + r * 4)[1] = o1;
-                }
-            }
-        } else if (kb > 0) {
-            const int sdp = kb >> 5;                   // the slot that took block column kb - 1 in the look-ahead pass
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-                if (s != sdp && tJ[s] > kb - 1) chol_diag_update(c[s], A + tile_off(tJ[s], kb - 1));
-        }
-        RSTAMP(32, 12);
-        __syncthreads();
-        RSTAMP(32, 13); RSTAMP(0, 10);
         if (warp == 0) {
-            // look-ahead: the slot of the next diagonal tile takes block column kb now, its lane factors tile (kb + 1, kb + 1)
-            const int sd = (kb + 1) >> 5;              // uniform
+            const int sd = (kb + 1) >> 5;              // uniform: the slot of the next diagonal tile goes first
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (s != sd) continue;
-                if (tJ[s] > kb) chol_diag_update(c[s], A + tile_off(tJ[s], kb));
-                if (tJ[s] == kb + 1) {
-                    double2 *dst = reinterpret_cast<double2 *>(A + tile_off(kb + 1, kb + 1));
+            for (int pass = 0; pass < 2; ++pass)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) { double2 v; v.x = c[s][2 * k]; v.y = c[s][2 * k + 1]; dst[k] = v; }
-                    chol_factor4(A + tile_off(kb + 1, kb + 1), flag_sm);
+                for (int s = 0; s < 2; ++s) {
+                    if ((pass == 0) != (s == sd)) continue;
+                    if (tJ[s] > kb) chol_diag_update(c[s], A + tile_off(tJ[s], kb));
+                    if (pass == 0 && tJ[s] == kb + 1) {
+                        double2 *dst = reinterpret_cast<double2 *>(A + tile_off(kb + 1, kb + 1));
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { double2 v; v.x = c[s][2 * k]; v.y = c[s][2 * k + 1]; dst[k] = v; }
+                        chol_factor4(A + tile_off(kb + 1, kb + 1), flag_sm);
+                        __threadfence_block();
+                        *diag_ready = kb + 1;
+                    }
                 }
-            }
         } else {
-            // trailing update of the owned off-diagonal / rhs tiles (I, J), kb < J < I
+            // trailing update of the owned off-diagonal / rhs tiles (I, J), kb < J < I; the highest live slot first: it
+            // holds the tiles of column kb + 1
+            bool next_panel = false;
 #pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
+            for (int s = kSlots - 1; s >= 0; --s) {
                 if (tJ[s] <= kb) continue;
+                next_panel |= tJ[s] == kb + 1;
                 const double2 *P2 = reinterpret_cast<const double2 *>(A + tile_off(tI[s], kb));
                 const double2 *Q2 = reinterpret_cast<const double2 *>(A + tile_off(tJ[s], kb));
                 double q[16];
@@ -639,13 +639,13 @@ __device__ inline bool chol_solve_regs(double *A, double *x, int nb, int *flag_s
                         c[s][r * 4 + cc] -= pa.x * q[cc * 4] + pa.y * q[cc * 4 + 1] + pb.x * q[cc * 4 + 2] + pb.y * q[cc * 4 + 3];
                 }
             }
+            if (next_panel) {
+                while (*diag_ready < kb + 1) { }
+                __threadfence_block();
+                panel(kb + 1);
+            }
         }
-        RSTAMP(32, 14); RSTAMP(0, 11);
         __syncthreads();
-        RSTAMP(32, 15);
-#ifdef PVIO_SOLVE_STAMPS
-        if (threadIdx.x == 0) ct__ = clock64();
-#endif
     }
     if (*flag_sm == 0) return false;
     // y = L^-1 b now sits in row 0 of the rhs tiles; back substitution x = L^-T y on warp 0
